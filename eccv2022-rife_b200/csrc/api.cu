@@ -1,0 +1,601 @@
+// C ABI of librife_b200.so (include/rife_b200.h): weight repacking, plan/workspace, the IFNet pipeline.
+// Host-side orchestration of train_log/IFNet_HDv3.py:119-169 and train_log/RIFE_HDv3.py:56-60.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace rife {
+
+std::atomic<uint64_t> g_launch_count{0};
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+
+static const int kBlockC[5] = {192, 128, 96, 64, 32};  // train_log/IFNet_HDv3.py:95-99
+static const int kLastCo = 52;                          // ConvTranspose2d(c, 4*13, 4, 2, 1), IFNet_HDv3.py:74
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// --------------------------------------------------------------------------------------------------
+// host-side repacking into the implicit-GEMM layouts [tap][cin_pad][npad]
+struct HostLayer {
+  int kind = CONV_3x3, cin = 0, n = 0, npad = 0, taps = 9;
+  std::vector<float> w, bias, beta;
+};
+
+// Conv2d OIHW (co, ci, 3, 3), stride 1
+static HostLayer pack_conv3x3(const float* W, const float* b, int co, int ci, int cin_pad) {
+  HostLayer L;
+  L.kind = CONV_3x3; L.taps = 9; L.cin = cin_pad; L.n = round_up(co, 4); L.npad = round_up(co, 16);
+  L.w.assign((size_t)9 * cin_pad * L.npad, 0.f);
+  L.bias.assign(L.npad, 0.f);
+  for (int o = 0; o < co; ++o) {
+    if (b) L.bias[o] = b[o];
+    for (int i = 0; i < ci; ++i)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          L.w[((size_t)(ky * 3 + kx) * cin_pad + i) * L.npad + o] = W[(((size_t)o * ci + i) * 3 + ky) * 3 + kx];
+  }
+  return L;
+}
+
+// Conv2d OIHW (co, ci, 3, 3), stride 2, expressed on the space-to-depth input whose channel index is
+// par * cs + i  (par = py*2+px): taps (dy,dx) in {-1,0}^2 with ky = 2*dy + py + 1, kx = 2*dx + px + 1.
+static HostLayer pack_conv3x3_s2d(const float* W, const float* b, int co, int ci, int cs, int cin_pad) {
+  HostLayer L;
+  L.kind = CONV_S2D; L.taps = 4; L.cin = cin_pad; L.n = round_up(co, 4); L.npad = round_up(co, 16);
+  L.w.assign((size_t)4 * cin_pad * L.npad, 0.f);
+  L.bias.assign(L.npad, 0.f);
+  for (int o = 0; o < co; ++o) {
+    if (b) L.bias[o] = b[o];
+    for (int i = 0; i < ci; ++i)
+      for (int dy = -1; dy <= 0; ++dy)
+        for (int dx = -1; dx <= 0; ++dx)
+          for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+              const int ky = 2 * dy + py + 1, kx = 2 * dx + px + 1;
+              if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+              const int t = (dy + 1) * 2 + (dx + 1);
+              const int c = (py * 2 + px) * cs + i;
+              L.w[((size_t)t * cin_pad + c) * L.npad + o] = W[(((size_t)o * ci + i) * 3 + ky) * 3 + kx];
+            }
+  }
+  return L;
+}
+
+// ConvTranspose2d IOHW (ci, co, 4, 4), stride 2, pad 1 as a 3x3-tap GEMM with N = 4 parities x co:
+// out[(2y+py, 2x+px), o] = sum_{dy,dx} in[(y+dy, x+dx)] * W[., o, py+1-2dy, px+1-2dx]   
+static HostLayer pack_convT(const float* W, const float* b, int ci, int co, int cin_pad) {
+  HostLayer L;
+  L.kind = CONV_3x3; L.taps = 9; L.cin = cin_pad; L.n = 4 * co; L.npad = round_up(4 * co, 16);
+  L.w.assign((size_t)9 * cin_pad * L.npad, 0.f);
+  L.bias.assign(L.npad, 0.f);
+  for (int par = 0; par < 4; ++par) {
+    const int py = par >> 1, px = par & 1;
+    for (int o = 0; o < co; ++o) {
+      if (b) L.bias[par * co + o] = b[o];
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int ky = py + 1 - 2 * dy, kx = px + 1 - 2 * dx;
+          if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
+          const int t = (dy + 1) * 3 + (dx + 1);
+          for (int i = 0; i < ci; ++i)
+            L.w[((size_t)t * cin_pad + i) * L.npad + par * co + o] = W[(((size_t)i * co + o) * 4 + ky) * 4 + kx];
+        }
+    }
+  }
+  return L;
+}
+
+struct DevLayer {
+  ConvLayerF32 f32;   // always present (fp32 FMA path)
+  UmmaLayer h16;      // present when precision == FP16
+};
+
+}  // namespace rife
+
+using namespace rife;
+
+struct rife_weights {
+  int device = 0;
+  int precision = RIFE_PRECISION_FP32;
+  std::vector<void*> allocs;
+  DevLayer head[4];
+  struct Block {
+    DevLayer conv00, conv01, res[8], last;
+    int c;
+  } blk[5];
+};
+
+static int upload(rife_weights* w, const void* host, size_t bytes, void** dev) {
+  RIFE_CUDA_TRY(cudaMalloc(dev, bytes));
+  w->allocs.push_back(*dev);
+  RIFE_CUDA_TRY(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return RIFE_OK;
+}
+
+static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d) {
+  void *pw, *pb, *pbeta = nullptr;
+  RIFE_TRY(upload(w, h.w.data(), h.w.size() * 4, &pw));
+  RIFE_TRY(upload(w, h.bias.data(), h.bias.size() * 4, &pb));
+  if (!h.beta.empty()) RIFE_TRY(upload(w, h.beta.data(), h.beta.size() * 4, &pbeta));
+  d->f32.w = (const float*)pw;
+  d->f32.bias = (const float*)pb;
+  d->f32.beta = (const float*)pbeta;
+  d->f32.kind = h.kind; d->f32.cin = h.cin; d->f32.n = h.n; d->f32.npad = h.npad;
+  if (w->precision == RIFE_PRECISION_FP16) {
+    void* ph = nullptr;
+    std::vector<__half> packed;
+    RIFE_TRY(umma_pack_weights(h.w.data(), h.taps, h.cin, h.npad, &packed, &d->h16));
+    RIFE_TRY(upload(w, packed.data(), packed.size() * sizeof(__half), &ph));
+    d->h16.w = (const __half*)ph;
+    d->h16.bias = d->f32.bias;
+    d->h16.beta = d->f32.beta;
+    d->h16.kind = h.kind; d->h16.n = h.n;
+  }
+  return RIFE_OK;
+}
+
+extern "C" {
+
+int rife_abi_version(void) { return RIFE_B200_ABI_VERSION; }
+const char* rife_last_error(void) { return t_error.c_str(); }
+uint64_t rife_launch_count(void) { return g_launch_count.load(); }
+
+int rife_weights_create(rife_weights** out, int n, const char* const* names, const float* const* data,
+                        const int64_t* numel, int precision) {
+  if (!out || !names || !data || !numel) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_weights_create: null argument");
+  if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16)
+    RIFE_FAIL(RIFE_ERR_DTYPE, "rife_weights_create: precision must be RIFE_PRECISION_FP32 or RIFE_PRECISION_FP16");
+  std::map<std::string, std::pair<const float*, int64_t>> sd;
+  for (int i = 0; i < n; ++i) sd[names[i]] = {data[i], numel[i]};
+  std::string missing;
+  auto get = [&](const std::string& k, int64_t want) -> const float* {
+    auto it = sd.find(k);
+    if (it == sd.end() || it->second.second != want) {
+      if (missing.empty())
+        missing = k + (it == sd.end() ? " (absent)" : " (numel " + std::to_string(it->second.second) + ", want " +
+                                                           std::to_string(want) + ")");
+      return nullptr;
+    }
+    return it->second.first;
+  };
+  auto* w = new rife_weights();
+  w->precision = precision;
+  cudaGetDevice(&w->device);
+  int st = RIFE_OK;
+  auto fail = [&](int code) {
+    rife_weights_destroy(w);
+    return code;
+  };
+  // ---- Head (train_log/IFNet_HDv3.py:27-30)
+  {
+    const float *w0 = get("encode.cnn0.weight", 16 * 3 * 9), *b0 = get("encode.cnn0.bias", 16);
+    const float *w1 = get("encode.cnn1.weight", 16 * 16 * 9), *b1 = get("encode.cnn1.bias", 16);
+    const float *w2 = get("encode.cnn2.weight", 16 * 16 * 9), *b2 = get("encode.cnn2.bias", 16);
+    const float *w3 = get("encode.cnn3.weight", 16 * 4 * 16), *b3 = get("encode.cnn3.bias", 4);
+    if (!missing.empty()) { set_error("rife_weights_create: bad tensor " + missing); return fail(RIFE_ERR_WEIGHTS); }
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w0, b0, 16, 3, 3, 16), &w->head[0]))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3(w1, b1, 16, 16, 16), &w->head[1]))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3(w2, b2, 16, 16, 16), &w->head[2]))) return fail(st);
+    if ((st = upload_layer(w, pack_convT(w3, b3, 16, 4, 16), &w->head[3]))) return fail(st);
+  }
+  // ---- IFBlocks (train_log/IFNet_HDv3.py:57-76, 95-99)
+  for (int i = 0; i < 5; ++i) {
+    const int c = kBlockC[i], p = (i == 0) ? 15 : 28;
+    const std::string pre = "block" + std::to_string(i) + ".";
+    auto& B = w->blk[i];
+    B.c = c;
+    const float *w00 = get(pre + "conv0.0.0.weight", (int64_t)(c / 2) * p * 9), *b00 = get(pre + "conv0.0.0.bias", c / 2);
+    const float *w01 = get(pre + "conv0.1.0.weight", (int64_t)c * (c / 2) * 9), *b01 = get(pre + "conv0.1.0.bias", c);
+    const float *wl = get(pre + "lastconv.0.weight", (int64_t)c * kLastCo * 16), *bl = get(pre + "lastconv.0.bias", kLastCo);
+    if (!missing.empty()) { set_error("rife_weights_create: bad tensor " + missing); return fail(RIFE_ERR_WEIGHTS); }
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w00, b00, c / 2, p, XIN_C, 4 * XIN_C), &B.conv00))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w01, b01, c, c / 2, c / 2, 2 * c), &B.conv01))) return fail(st);
+    for (int j = 0; j < 8; ++j) {
+      const std::string rp = pre + "convblock." + std::to_string(j) + ".";
+      const float *wr = get(rp + "conv.weight", (int64_t)c * c * 9), *br = get(rp + "conv.bias", c);
+      const float* be = get(rp + "beta", c);
+      if (!missing.empty()) { set_error("rife_weights_create: bad tensor " + missing); return fail(RIFE_ERR_WEIGHTS); }
+      HostLayer L = pack_conv3x3(wr, br, c, c, c);
+      L.beta.assign(L.npad, 0.f);
+      for (int k = 0; k < c; ++k) L.beta[k] = be[k];
+      if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
+    }
+    if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last))) return fail(st);
+  }
+  *out = w;
+  return RIFE_OK;
+}
+
+int rife_weights_destroy(rife_weights* w) {
+  if (!w) return RIFE_OK;
+  for (void* p : w->allocs) cudaFree(p);
+  delete w;
+  return RIFE_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------------
+// plan
+struct PlanLayout {
+  size_t src, head_in, head_a, head_b, xin, c0, act_a, act_b, tmp[5], gridx, gridy, tstep, stage_in0, stage_in1,
+      stage_out, total;
+  int s[5];
+};
+
+static int plan_layout(int B, int C, int H, int W, float scale, int precision, PlanLayout* L) {
+  if (B < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: B, H, W must be positive");
+  if (C != 3 && C != 4) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: C must be 3 or 4 (IFNet_HDv3.py:121-123 splits an RGB/RGBA pair)");
+  if (!(scale == 1.f || scale == 0.5f || scale == 0.25f))
+    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be 1, 0.5 or 0.25 (scale > 1 up-samples the block input; not built)");
+  if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16) RIFE_FAIL(RIFE_ERR_DTYPE, "plan: bad precision");
+  const int inv = (int)lroundf(1.f / scale);
+  const int base[5] = {16, 8, 4, 2, 1};
+  for (int i = 0; i < 5; ++i) L->s[i] = base[i] * inv;  // scale_list, RIFE_HDv3.py:58
+  const int mult = 64 * inv;
+  if (H % mult || W % mult)
+    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale = " + std::to_string(mult) + " (got " +
+                                  std::to_string(H) + "x" + std::to_string(W) + ")");
+  const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
+  const size_t N = (size_t)B * H * W;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L->src = take(2 * N * SRC_C * E);
+  L->head_in = take(2 * (N / 4) * 16 * E);
+  L->head_a = take(2 * (N / 4) * 16 * E);
+  L->head_b = take(2 * (N / 4) * 16 * E);
+  size_t xin = 0, c0 = 0, act = 0;
+  for (int i = 0; i < 5; ++i) {
+    const size_t n = N / ((size_t)L->s[i] * L->s[i]);
+    const size_t c = kBlockC[i];
+    xin = xin > n * XIN_C ? xin : n * XIN_C;
+    c0 = c0 > (n / 4) * (c / 2) ? c0 : (n / 4) * (c / 2);
+    act = act > (n / 16) * c ? act : (n / 16) * c;
+  }
+  L->xin = take(xin * E);
+  L->c0 = take(c0 * E);
+  L->act_a = take(act * E);
+  L->act_b = take(act * E);
+  for (int i = 0; i < 5; ++i) L->tmp[i] = take(N / ((size_t)L->s[i] * L->s[i]) * TMP_C * E);
+  L->gridx = take((size_t)W * 4);
+  L->gridy = take((size_t)H * 4);
+  L->tstep = take((size_t)B * 4);
+  L->stage_in0 = take(N * C * 4);
+  L->stage_in1 = take(N * C * 4);
+  L->stage_out = take(N * C * 4);
+  L->total = off;
+  return RIFE_OK;
+}
+
+struct rife_plan {
+  const rife_weights* w = nullptr;
+  int B = 0, C = 0, H = 0, W = 0, precision = 0, device = 0;
+  PlanLayout L{};
+  char* ws = nullptr;
+  void* at(size_t off) const { return ws + off; }
+};
+
+extern "C" {
+
+size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int precision) {
+  PlanLayout L;
+  if (plan_layout(B, C, H, W, scale, precision, &L) != RIFE_OK) return 0;
+  return L.total;
+}
+
+int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H, int W, float scale, void* workspace,
+                     size_t workspace_bytes, const float* gridx_host, const float* gridy_host) {
+  if (!out || !w || !workspace) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: null argument");
+  PlanLayout L;
+  RIFE_TRY(plan_layout(B, C, H, W, scale, w->precision, &L));
+  if (workspace_bytes < L.total)
+    RIFE_FAIL(RIFE_ERR_WORKSPACE, "rife_plan_create: workspace has " + std::to_string(workspace_bytes) + " bytes, need " +
+                                      std::to_string(L.total));
+  if (((uintptr_t)workspace) % 256) RIFE_FAIL(RIFE_ERR_WORKSPACE, "rife_plan_create: workspace must be 256-byte aligned");
+  if (!is_device_ptr(workspace)) RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_plan_create: workspace is not device memory");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != w->device) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: weights live on another device");
+  auto* p = new rife_plan();
+  p->w = w; p->B = B; p->C = C; p->H = H; p->W = W; p->precision = w->precision; p->device = dev;
+  p->L = L;
+  // 1024-byte alignment for TMA/UMMA-facing buffers: offsets are 1024-aligned, so align the base too
+  p->ws = (char*)workspace;
+  cudaError_t e = cudaMemset(p->ws, 0, L.total);
+  if (e == cudaSuccess) {
+    if (gridx_host) e = cudaMemcpy(p->at(L.gridx), gridx_host, (size_t)W * 4, cudaMemcpyHostToDevice);
+    else if (launch_fill_grid((float*)p->at(L.gridx), W, 0) != RIFE_OK) e = cudaErrorUnknown;
+  }
+  if (e == cudaSuccess) {
+    if (gridy_host) e = cudaMemcpy(p->at(L.gridy), gridy_host, (size_t)H * 4, cudaMemcpyHostToDevice);
+    else if (launch_fill_grid((float*)p->at(L.gridy), H, 0) != RIFE_OK) e = cudaErrorUnknown;
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error(std::string("rife_plan_create: ") + cudaGetErrorString(e));
+    delete p;
+    return RIFE_ERR_CUDA;
+  }
+  *out = p;
+  return RIFE_OK;
+}
+
+int rife_plan_destroy(rife_plan* p) {
+  delete p;
+  return RIFE_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------------
+// pipeline
+static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, cudaStream_t st) {
+  if (p->precision == RIFE_PRECISION_FP16) return launch_conv_umma(L.h16, io, st);
+  return launch_conv_f32(L.f32, io, st);
+}
+
+static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
+                        const rife_ifnet_outputs* outs, int io_dtype, cudaStream_t st) {
+  if (!p || !img0 || !img1 || !timestep_host || !outs) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: null argument");
+  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16) RIFE_FAIL(RIFE_ERR_DTYPE, "rife: io_dtype must be RIFE_F32 or RIFE_F16");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != p->device) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: plan belongs to another device");
+  const rife_weights* w = p->w;
+  const PlanLayout& L = p->L;
+  const int B = p->B, H = p->H, W = p->W;
+  const bool half_act = p->precision == RIFE_PRECISION_FP16;
+  const size_t E = half_act ? 2 : 4;
+  const size_t N = (size_t)B * H * W;
+
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(L.tstep), timestep_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+
+  PixelCtx c;
+  c.B = B; c.C = p->C; c.H = H; c.W = W;
+  c.gridx = (const float*)p->at(L.gridx);
+  c.gridy = (const float*)p->at(L.gridy);
+  c.tstep = (const float*)p->at(L.tstep);
+  c.src0 = p->at(L.src);
+  c.src1 = (char*)p->at(L.src) + N * SRC_C * E;
+  c.half_act = half_act;
+
+  // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
+  RIFE_TRY(launch_prep(c, img0, img1, io_dtype, (void*)c.src0, (void*)c.src1, p->at(L.head_in), st));
+  {
+    ConvIO io;
+    io.B = 2 * B; io.H = H / 2; io.W = W / 2;
+    io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;
+    RIFE_TRY(run_conv(p, w->head[0], io, st));
+    io.in = p->at(L.head_a); io.out = p->at(L.head_b);
+    RIFE_TRY(run_conv(p, w->head[1], io, st));
+    io.in = p->at(L.head_b); io.out = p->at(L.head_a);
+    RIFE_TRY(run_conv(p, w->head[2], io, st));
+    io.in = p->at(L.head_a); io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
+    RIFE_TRY(run_conv(p, w->head[3], io, st));
+  }
+
+  // ---- 5 IFBlocks (IFNet_HDv3.py:139-157)
+  TmpLevel lev[5];
+  for (int i = 0; i < 5; ++i) {
+    const int s = L.s[i], c_ = kBlockC[i];
+    const int hs = H / s, wsz = W / s;
+    RIFE_TRY(launch_block_input(c, i, lev, s, p->at(L.xin), st));
+    ConvIO io;
+    io.B = B;
+    // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
+    io.H = hs / 2; io.W = wsz / 2; io.in = p->at(L.xin); io.out = p->at(L.c0); io.epi = EPI_LRELU_S2D; io.out_c = c_ / 2;
+    RIFE_TRY(run_conv(p, w->blk[i].conv00, io, st));
+    // conv0.1: stride 2 on (hs/2, wsz/2) == 2x2 taps on (hs/4, wsz/4)
+    io.H = hs / 4; io.W = wsz / 4; io.in = p->at(L.c0); io.out = p->at(L.act_a); io.epi = EPI_LRELU; io.out_c = c_;
+    RIFE_TRY(run_conv(p, w->blk[i].conv01, io, st));
+    void* cur = p->at(L.act_a);
+    void* nxt = p->at(L.act_b);
+    for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
+      io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
+      RIFE_TRY(run_conv(p, w->blk[i].res[j], io, st));
+      void* t = cur; cur = nxt; nxt = t;
+    }
+    // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
+    io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
+    RIFE_TRY(run_conv(p, w->blk[i].last, io, st));
+    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = s;
+
+    EvalOut eo;
+    eo.flow = outs->flow[i];
+    eo.warped0 = outs->warped0[i];
+    eo.warped1 = outs->warped1[i];
+    if (i == 4) {
+      eo.mask = outs->mask;
+      eo.merged = outs->merged;
+    }
+    if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged) RIFE_TRY(launch_eval(c, i + 1, lev, eo, io_dtype, st));
+  }
+  return RIFE_OK;
+}
+
+extern "C" {
+
+int rife_ifnet_forward(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
+                       const rife_ifnet_outputs* outs, int io_dtype, void* stream) {
+  return run_pipeline(p, img0, img1, timestep_host, outs, io_dtype, (cudaStream_t)stream);
+}
+
+int rife_inference(rife_plan* p, const void* img0, const void* img1, const float* timestep_host, void* out, int io_dtype,
+                   void* stream) {
+  if (!out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference: out is null");
+  rife_ifnet_outputs o;
+  memset(&o, 0, sizeof(o));
+  o.merged = out;
+  return run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, (cudaStream_t)stream);
+}
+
+int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,
+                        void* out_host, int io_dtype, void* stream) {
+  if (!p || !img0_host || !img1_host || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host: null argument");
+  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host: bad io_dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)p->B * p->C * p->H * p->W * (io_dtype == RIFE_F16 ? 2 : 4);
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, bytes, cudaMemcpyHostToDevice, st));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, bytes, cudaMemcpyHostToDevice, st));
+  RIFE_TRY(rife_inference(p, p->at(p->L.stage_in0), p->at(p->L.stage_in1), timestep_host, p->at(p->L.stage_out), io_dtype,
+                          stream));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), bytes, cudaMemcpyDeviceToHost, st));
+  return RIFE_OK;
+}
+
+// ---- single operators ----------------------------------------------------------------------------
+int rife_warp(const void* input, const void* flow, void* out, int B, int C, int H, int W, int dtype,
+              const float* gridx_dev, const float* gridy_dev, void* stream) {
+  if (!input || !flow || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_warp: null argument");
+  if (B < 1 || C < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_warp: empty shape");
+  if (!is_device_ptr(input) || !is_device_ptr(flow) || !is_device_ptr(out))
+    RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_warp: tensors must be CUDA device memory (no CPU fallback)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tmpg = nullptr;
+  if (!gridx_dev || !gridy_dev) {
+    RIFE_CUDA_TRY(cudaMallocAsync((void**)&tmpg, (size_t)(W + H) * 4, st));
+    RIFE_TRY(launch_fill_grid(tmpg, W, st));
+    RIFE_TRY(launch_fill_grid(tmpg + W, H, st));
+    gridx_dev = tmpg;
+    gridy_dev = tmpg + W;
+  }
+  int rc = launch_warp_op(input, flow, out, B, C, H, W, dtype, gridx_dev, gridy_dev, st);
+  if (tmpg) cudaFreeAsync(tmpg, st);
+  return rc;
+}
+
+int rife_resize_bilinear(const void* x, void* out, int B, int C, int H, int W, int num, int den, float post_mul,
+                         void* stream) {
+  if (!x || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_resize_bilinear: null argument");
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  if (!pow2(num) || !pow2(den) || (num != 1 && den != 1))
+    RIFE_FAIL(RIFE_ERR_SHAPE, "rife_resize_bilinear: scale_factor must be 2^k or 2^-k");
+  if ((H * (long long)num) % den || (W * (long long)num) % den) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_resize_bilinear: size not divisible");
+  if (!is_device_ptr(x) || !is_device_ptr(out)) RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_resize_bilinear: device memory required");
+  return launch_resize_op((const float*)x, (float*)out, B, C, H, W, num, den, post_mul, (cudaStream_t)stream);
+}
+
+// Test entry points: repack on the fly (synchronous), run the same kernels/epilogues as the pipeline.
+static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int B, int Cin, int H, int W, bool s2d,
+                           const float* residual_nchw, float* y_nchw, int epi, int out_c_store, int cpp, int out_C,
+                           int out_H, int out_W, int out_Cpad, cudaStream_t st) {
+  rife_weights tmpw;
+  tmpw.precision = precision;
+  cudaGetDevice(&tmpw.device);
+  DevLayer d;
+  int rc = upload_layer(&tmpw, h, &d);
+  const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
+  (void)E;
+  float *xin = nullptr, *res = nullptr, *yout = nullptr;
+  const int gh = s2d ? H / 2 : H, gw = s2d ? W / 2 : W;  // GEMM row grid
+  const int cin_act = s2d ? h.cin / 4 : h.cin;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    if (xin) cudaFree(xin);
+    if (res) cudaFree(res);
+    if (yout) cudaFree(yout);
+    for (void* p : tmpw.allocs) cudaFree(p);
+    tmpw.allocs.clear();
+  };
+  if (rc != RIFE_OK) { cleanup(); return rc; }
+#define RIFE_SC_TRY(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error(std::string(#e) + ": " + cudaGetErrorString(_e)); cleanup(); return RIFE_ERR_CUDA; } } while (0)
+#define RIFE_SC(e) do { int _r = (e); if (_r != RIFE_OK) { cleanup(); return _r; } } while (0)
+  const size_t nin = (size_t)B * H * W * cin_act;
+  const size_t nout = (size_t)B * out_H * out_W * out_Cpad;
+  RIFE_SC_TRY(cudaMalloc((void**)&xin, nin * 4));
+  RIFE_SC_TRY(cudaMalloc((void**)&yout, nout * 4));
+  RIFE_SC_TRY(cudaMemsetAsync(yout, 0, nout * 4, st));
+  RIFE_SC(launch_nchw_to_nhwc_f32(x_nchw, xin, B, Cin, H, W, cin_act, s2d, st));
+  if (residual_nchw) {
+    RIFE_SC_TRY(cudaMalloc((void**)&res, (size_t)B * gh * gw * out_c_store * 4));
+    RIFE_SC(launch_nchw_to_nhwc_f32(residual_nchw, res, B, out_C, gh, gw, out_c_store, false, st));
+  }
+  ConvIO io;
+  io.B = B; io.H = gh; io.W = gw; io.in = xin; io.res = res; io.out = yout; io.epi = epi; io.out_c = out_c_store;
+  io.co_per_par = cpp;
+  if (precision == RIFE_PRECISION_FP16) {
+    RIFE_SC(launch_conv_umma_f32io(d.h16, io, st));
+  } else {
+    RIFE_SC(launch_conv_f32(d.f32, io, st));
+  }
+  RIFE_SC(launch_nhwc_to_nchw_f32(yout, y_nchw, B, out_C, out_H, out_W, out_Cpad, st));
+  cleanup();
+  return RIFE_OK;
+#undef RIFE_SC_TRY
+#undef RIFE_SC
+}
+
+static int fetch_host(const float* dev, size_t n, std::vector<float>* h) {
+  h->resize(n);
+  RIFE_CUDA_TRY(cudaMemcpy(h->data(), dev, n * 4, cudaMemcpyDeviceToHost));
+  return RIFE_OK;
+}
+
+int rife_conv3x3(const float* x, const float* w, const float* bias, const float* beta, const float* residual, float* y,
+                 int B, int Cin, int H, int W, int Cout, int stride, int act, int precision, void* stream) {
+  if (!x || !w || !y) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_conv3x3: null argument");
+  if (stride != 1 && stride != 2) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_conv3x3: stride must be 1 or 2");
+  if (stride == 2 && (H % 2 || W % 2)) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_conv3x3: stride 2 needs even H, W");
+  if ((beta == nullptr) != (residual == nullptr)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_conv3x3: beta and residual go together");
+  if (!is_device_ptr(x) || !is_device_ptr(w) || !is_device_ptr(y)) RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_conv3x3: device memory required");
+  RIFE_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  std::vector<float> hw, hb, hbeta;
+  RIFE_TRY(fetch_host(w, (size_t)Cout * Cin * 9, &hw));
+  if (bias) RIFE_TRY(fetch_host(bias, Cout, &hb));
+  const int cs = round_up(Cin, 16);
+  HostLayer L = stride == 2 ? pack_conv3x3_s2d(hw.data(), bias ? hb.data() : nullptr, Cout, Cin, cs, 4 * cs)
+                            : pack_conv3x3(hw.data(), bias ? hb.data() : nullptr, Cout, Cin, cs);
+  int epi = act ? EPI_LRELU : EPI_LINEAR;
+  if (beta) {
+    if (stride != 1 || !act) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_conv3x3: the residual form is stride 1 + LeakyReLU");
+    RIFE_TRY(fetch_host(beta, Cout, &hbeta));
+    L.beta.assign(L.npad, 0.f);
+    for (int k = 0; k < Cout; ++k) L.beta[k] = hbeta[k];
+    epi = EPI_RES;
+  }
+  const int oh = H / stride, ow = W / stride;
+  return run_single_conv(L, precision, x, B, Cin, H, W, stride == 2, residual, y, epi, L.npad, 0, Cout, oh, ow, L.npad,
+                         (cudaStream_t)stream);
+}
+
+int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
+                             int Cout, int pixel_shuffle, int precision, void* stream) {
+  if (!x || !w || !y) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_conv_transpose4x4s2: null argument");
+  if (pixel_shuffle && Cout != kLastCo) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_conv_transpose4x4s2: the fused PixelShuffle form is the 52-channel lastconv");
+  if (Cout % 4) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_conv_transpose4x4s2: Cout must be a multiple of 4");
+  if (!is_device_ptr(x) || !is_device_ptr(w) || !is_device_ptr(y)) RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_conv_transpose4x4s2: device memory required");
+  RIFE_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  std::vector<float> hw, hb;
+  RIFE_TRY(fetch_host(w, (size_t)Cin * Cout * 16, &hw));
+  if (bias) RIFE_TRY(fetch_host(bias, Cout, &hb));
+  HostLayer L = pack_convT(hw.data(), bias ? hb.data() : nullptr, Cin, Cout, round_up(Cin, 16));
+  if (pixel_shuffle)
+    return run_single_conv(L, precision, x, B, Cin, H, W, false, nullptr, y, EPI_PS, TMP_C, Cout, Cout / 4, 4 * H, 4 * W,
+                           TMP_C, (cudaStream_t)stream);
+  const int cpad = round_up(Cout, 4);
+  return run_single_conv(L, precision, x, B, Cin, H, W, false, nullptr, y, EPI_CONVT, cpad, Cout, Cout, 2 * H, 2 * W, cpad,
+                         (cudaStream_t)stream);
+}
+
+}  // extern "C"

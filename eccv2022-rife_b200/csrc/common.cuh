@@ -1,0 +1,188 @@
+// Shared declarations for the RIFE B200 kernels (device helpers, layer descriptors, launch API).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/rife_b200.h"
+
+namespace rife {
+
+// ------------------------------------------------------------------ error plumbing (api.cu)
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launch_count;
+#define RIFE_CUDA_TRY(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      rife::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                        \
+      return RIFE_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+#define RIFE_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != RIFE_OK) return _s; \
+  } while (0)
+#define RIFE_FAIL(code, msg)  \
+  do {                        \
+    rife::set_error(msg);     \
+    return (code);            \
+  } while (0)
+// after a kernel launch: count it and pick up launch-configuration errors
+#define RIFE_LAUNCH_CHECK()                              \
+  do {                                                   \
+    rife::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+    RIFE_CUDA_TRY(cudaGetLastError());                   \
+  } while (0)
+
+// ------------------------------------------------------------------ layouts
+// Full-resolution "source" tensor per frame: [B][H][W][8]: ch 0..3 = Head feature f, 4..6 = image
+// channels 0..2, 7 = image channel 3 (alpha; 0 when C == 3).  One 16 B (fp16) / 32 B (fp32) vector
+// per bilinear tap of warp().
+constexpr int SRC_C = 8;
+// Low-resolution block output ("tmp" of IFBlock.forward before the final upsample):
+// [B][H/s][W/s][16]: ch 0..3 flow (un-scaled), 4 mask, 5..12 feat, 13..15 zero.
+constexpr int TMP_C = 16;
+// Block input after the 1/s resize, channel-padded 28 -> 32 and stored space-to-depth (s2d) so that
+// the stride-2 conv0.0 becomes a stride-1 2x2-tap conv: [B][H/2s][W/2s][4 * 32], ch = (py*2+px)*32 + c.
+constexpr int XIN_C = 32;
+
+// ------------------------------------------------------------------ vector load/store helpers
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  float4 a = reinterpret_cast<const float4*>(p)[0];
+  float4 b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const __half* p, float (&v)[4]) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__half* p, const float (&v)[4]) {
+  uint2 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+  h[0] = __floats2half2_rn(v[0], v[1]);
+  h[1] = __floats2half2_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+__device__ __forceinline__ float lrelu02(float x) { return x >= 0.f ? x : x * 0.2f; }
+
+// ------------------------------------------------------------------ conv layer descriptor
+enum ConvKind : int {
+  CONV_3x3 = 0,   // taps (dy,dx) in {-1,0,1}^2, tap index = (dy+1)*3 + (dx+1)
+  CONV_S2D = 1,   // stride-2 3x3 conv expressed on the space-to-depth input: taps in {-1,0}^2, index (dy+1)*2+(dx+1)
+};
+enum ConvEpi : int {
+  EPI_LRELU = 0,      // y = lrelu(acc + bias)                         -> NHWC [.., N]
+  EPI_LRELU_S2D = 1,  // same, stored space-to-depth for a following stride-2 conv
+  EPI_RES = 2,        // y = lrelu((acc + bias) * beta + res)           (ResConv, IFNet_HDv3.py:53-54)
+  EPI_PS = 3,         // ConvTranspose(4,2,1)+PixelShuffle(2) scatter into the TMP_C-channel tmp tensor
+  EPI_HEADT = 4,      // Head.cnn3 ConvTranspose scatter into channels 0..3 of the SRC tensor
+  EPI_LINEAR = 5,     // y = acc + bias (no activation)                 -> NHWC [.., N]
+  EPI_CONVT = 6,      // generic ConvTranspose(4,2,1) parity scatter to NHWC [B][2H][2W][N/4] (op-level entry)
+};
+
+// Device-side view of one packed conv layer (fp32 FMA path).
+struct ConvLayerF32 {
+  const float* w = nullptr;     // [taps][Cin][Npad]
+  const float* bias = nullptr;  // [Npad] (ConvT: bias replicated per parity)
+  const float* beta = nullptr;  // [Npad] or null
+  int kind = CONV_3x3;
+  int cin = 0;    // padded input channels as stored in the activation tensor
+  int n = 0;      // valid output columns of the implicit GEMM
+  int npad = 0;   // multiple of 4
+};
+
+struct ConvIO {
+  const void* in = nullptr;   // [B][H][W][cin]
+  const void* res = nullptr;  // [B][H][W][n] (EPI_RES)
+  void* out = nullptr;
+  int B = 0, H = 0, W = 0;    // spatial size of the conv *input* (= GEMM rows grid)
+  int epi = EPI_LRELU;
+  int out_c = 0;              // channel count of the destination pixel (NHWC pitch)
+  int co_per_par = 0;         // EPI_PS / EPI_CONVT / EPI_HEADT: output channels per parity
+};
+
+int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);
+
+// ------------------------------------------------------------------ pixel kernels (pixel_kernels.cu)
+struct TmpLevel {
+  const void* ptr;  // [B][h][w][TMP_C]
+  int h, w;
+  int s;            // up-sampling factor to full resolution (power of two >= 1)
+};
+
+struct PixelCtx {
+  int B, C, H, W;
+  const float* gridx;  // device, W entries (model/warplayer.py:11)
+  const float* gridy;  // device, H entries (model/warplayer.py:13)
+  const float* tstep;  // device, B entries
+  const void* src0;    // [B][H][W][SRC_C]
+  const void* src1;
+  bool half_act;       // activation / src / tmp storage type: false = float, true = __half
+};
+
+// NCHW image (io dtype) -> SRC tensor channels 4..7 (+ zeros in 0..3) and the s2d Head input [2B][H/2][W/2][16]
+int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
+                void* head_in, cudaStream_t st);
+// builds the s2d block input of block `level` from the lazily-accumulated tmp levels [0, level)
+int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, cudaStream_t st);
+// evaluates flow / mask / warped images / merged at full resolution after `nlev` blocks
+struct EvalOut {
+  void* flow = nullptr;     // (B,4,H,W)
+  void* mask = nullptr;     // (B,1,H,W)
+  void* warped0 = nullptr;  // (B,C,H,W)
+  void* warped1 = nullptr;
+  void* merged = nullptr;   // (B,C,H,W): w0*sigmoid(mask) + w1*(1-sigmoid(mask))
+};
+int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, cudaStream_t st);
+
+int launch_warp_op(const void* input, const void* flow, void* out, int B, int C, int H, int W, int dtype,
+                   const float* gridx, const float* gridy, cudaStream_t st);
+int launch_resize_op(const float* x, float* out, int B, int C, int H, int W, int num, int den, float post_mul,
+                     cudaStream_t st);
+int launch_fill_grid(float* g, int n, cudaStream_t st);
+// layout converters for the op-level entry points
+int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, bool s2d, cudaStream_t st);
+int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st);
+
+}  // namespace rife

@@ -1,0 +1,543 @@
+// HBM-bound pixel kernels of the RIFE HDv3 hot path: input packing, the fused
+// {flow accumulate + warp + concat + 1/s bilinear resize} block-input gather, and the fused
+// {flow accumulate + warp + sigmoid-merge} output kernel.  Reference semantics:
+//   train_log/IFNet_HDv3.py:79-82,86-89 (F.interpolate sites), :141-159 (concat / warp / merge),
+//   model/warplayer.py:8-22 (warp).
+//
+// Design note ("lazy flow"): the reference materialises flow/mask/feat (13 channels) at full resolution
+// after every block (IFNet_HDv3.py:86-89,152).  Here each block only writes its low-resolution 13-channel
+// `tmp` tensor; every consumer re-evaluates   flow(p) = sum_j s_j * bilerp(tmp_j[0:4], p)   (same
+// left-to-right summation order as the reference's `flow = flow + fd`) for exactly the pixels it needs.
+// For s >= 4 the 1/s resize only touches the centre 2x2 of each s x s cell, so the full-resolution
+// tensors are never needed.
+#include "common.cuh"
+
+namespace rife {
+
+namespace {
+
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+
+// ATen area_pixel_compute_source_index(align_corners=False, scale given) + compute_source_index_and_lambda
+// for an up-sampling by integer factor s (rs = 1/s).
+__device__ __forceinline__ Lerp make_lerp(int d, int in_size, float rs) {
+  float src = rs * ((float)d + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  int i0 = (int)src;
+  i0 = min(i0, in_size - 1);
+  Lerp L;
+  L.i0 = i0;
+  L.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  L.l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+  L.l0 = 1.f - L.l1;
+  return L;
+}
+
+// bilinear up-sample read of channels [c0, c0+N) of a tmp level at full-resolution pixel (y, x)
+template <typename Tt, int N>
+__device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, int w, int s, int c0, int y, int x,
+                                           float (&out)[N]) {
+  static_assert(N == 4 || N == 16, "N");
+  if (s == 1) {
+    const Tt* p = base + ((size_t)y * w + x) * TMP_C + c0;
+    if constexpr (N == 4) {
+      ld4(p, out);
+    } else {
+      float a[8], b[8];
+      ld8(p, a);
+      ld8(p + 8, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { out[i] = a[i]; out[8 + i] = b[i]; }
+    }
+    return;
+  }
+  const float rs = 1.f / (float)s;
+  const Lerp ly = make_lerp(y, h, rs), lx = make_lerp(x, w, rs);
+  const Tt* p00 = base + ((size_t)ly.i0 * w + lx.i0) * TMP_C + c0;
+  const Tt* p01 = base + ((size_t)ly.i0 * w + lx.i1) * TMP_C + c0;
+  const Tt* p10 = base + ((size_t)ly.i1 * w + lx.i0) * TMP_C + c0;
+  const Tt* p11 = base + ((size_t)ly.i1 * w + lx.i1) * TMP_C + c0;
+  float v00[N], v01[N], v10[N], v11[N];
+  if constexpr (N == 4) {
+    ld4(p00, v00); ld4(p01, v01); ld4(p10, v10); ld4(p11, v11);
+  } else {
+    float a[8];
+#define RIFE_LD16(P, V)                                   \
+  ld8(P, a);                                              \
+  _Pragma("unroll") for (int i = 0; i < 8; ++i) V[i] = a[i]; \
+  ld8(P + 8, a);                                          \
+  _Pragma("unroll") for (int i = 0; i < 8; ++i) V[8 + i] = a[i];
+    RIFE_LD16(p00, v00) RIFE_LD16(p01, v01) RIFE_LD16(p10, v10) RIFE_LD16(p11, v11)
+#undef RIFE_LD16
+  }
+#pragma unroll
+  for (int c = 0; c < N; ++c)
+    out[c] = ly.l0 * (lx.l0 * v00[c] + lx.l1 * v01[c]) + ly.l1 * (lx.l0 * v10[c] + lx.l1 * v11[c]);
+}
+
+struct WarpGeom {
+  float halfw, halfh;  // (W-1)/2, (H-1)/2   (model/warplayer.py:18-19)
+  float wm1, hm1;      // W-1, H-1
+};
+
+// One bilinear tap set of warp() on the 8-channel SRC layout.  Follows the reference's arithmetic order:
+// g = base + flow / ((dim-1)/2); ix = ((g+1)/2)*(dim-1); clamp; 4 taps with zero weight beyond the edge.
+template <typename T>
+__device__ __forceinline__ void warp8(const T* __restrict__ src, int H, int W, const WarpGeom& g, float gx, float gy,
+                                      float fx, float fy, float (&out)[8]) {
+  const float nx = gx + __fdiv_rn(fx, g.halfw);
+  const float ny = gy + __fdiv_rn(fy, g.halfh);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
+  ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float x1f = x0f + 1.f, y1f = y0f + 1.f;
+  const float wnw = (x1f - ix) * (y1f - iy), wne = (ix - x0f) * (y1f - iy);
+  const float wsw = (x1f - ix) * (iy - y0f), wse = (ix - x0f) * (iy - y0f);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const bool xin = (x0 + 1) < W, yin = (y0 + 1) < H;
+  const T* p = src + ((size_t)y0 * W + x0) * SRC_C;
+  float v[8];
+  ld8(p, v);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) out[c] = v[c] * wnw;
+  if (xin) {
+    ld8(p + SRC_C, v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] += v[c] * wne;
+  }
+  if (yin) {
+    ld8(p + (size_t)W * SRC_C, v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] += v[c] * wsw;
+    if (xin) {
+      ld8(p + (size_t)W * SRC_C + SRC_C, v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[c] += v[c] * wse;
+    }
+  }
+}
+
+constexpr int MAXLEV = 5;
+struct LevelsArg {
+  const void* ptr[MAXLEV];
+  int h[MAXLEV], w[MAXLEV], s[MAXLEV];
+};
+
+// flow(p) after `nlev` blocks, plus all 16 channels of the newest level (mask = ch 4, feat = ch 5..12)
+template <typename Tt>
+__device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int b, int y, int x, float (&flow)[4],
+                                           float (&last)[16]) {
+#pragma unroll 1
+  for (int j = 0; j < nlev - 1; ++j) {
+    float f[4];
+    const Tt* base = reinterpret_cast<const Tt*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
+    sample_tmp<Tt, 4>(base, L.h[j], L.w[j], L.s[j], 0, y, x, f);
+    const float sc = (float)L.s[j];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) flow[c] = (j == 0) ? f[c] * sc : flow[c] + f[c] * sc;  // flow = flow + fd (IFNet_HDv3.py:152)
+  }
+  const int j = nlev - 1;
+  const Tt* base = reinterpret_cast<const Tt*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
+  sample_tmp<Tt, 16>(base, L.h[j], L.w[j], L.s[j], 0, y, x, last);
+  const float sc = (float)L.s[j];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) flow[c] = (j == 0) ? last[c] * sc : flow[c] + last[c] * sc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prep: NCHW images -> SRC tensors (ch 4..7; ch 0..3 zero until Head writes them) + s2d Head input
+template <typename Tio, typename T>
+__global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
+                                                   T* __restrict__ src0, T* __restrict__ src1,
+                                                   T* __restrict__ head_in, int B, int C, int H, int W) {
+  const int W2 = W >> 1, H2 = H >> 1;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nq = (size_t)B * H2 * W2;
+  const int frame = blockIdx.y;
+  if (q >= nq) return;
+  const int x2 = (int)(q % W2);
+  const int y2 = (int)((q / W2) % H2);
+  const int b = (int)(q / ((size_t)W2 * H2));
+  const Tio* img = frame ? img1 : img0;
+  T* src = frame ? src1 : src0;
+  const size_t plane = (size_t)H * W;
+  float hv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hv[i] = 0.f;
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int y = 2 * y2 + py, x = 2 * x2 + px;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      const Tio* p = img + (size_t)b * C * plane + (size_t)y * W + x;
+      for (int c = 0; c < C; ++c) v[4 + c] = to_f(p[c * plane]);
+      st8(src + (((size_t)b * H + y) * W + x) * SRC_C, v);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hv[(py * 2 + px) * 3 + c] = v[4 + c];
+    }
+  }
+  T* hp = head_in + ((((size_t)frame * B + b) * H2 + y2) * W2 + x2) * 16;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = hv[i];
+  st8(hp, a);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = hv[8 + i];
+  st8(hp + 8, a);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block input: one thread per low-resolution pixel of the (H/s, W/s) block input.
+template <typename T, typename Tt>
+__global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level, int s, const T* __restrict__ src0,
+                                                          const T* __restrict__ src1, const float* __restrict__ gridx,
+                                                          const float* __restrict__ gridy,
+                                                          const float* __restrict__ tstep, T* __restrict__ xin, int B,
+                                                          int H, int W, WarpGeom geom) {
+  const int Hs = H / s, Ws = W / s;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Hs * Ws) return;
+  const int X = (int)(idx % Ws);
+  const int Y = (int)((idx / Ws) % Hs);
+  const int b = (int)(idx / ((size_t)Ws * Hs));
+  const T* s0 = src0 + (size_t)b * H * W * SRC_C;
+  const T* s1 = src1 + (size_t)b * H * W * SRC_C;
+  const float t = tstep[b];
+  const int ns = (s == 1) ? 1 : 2;            // samples per axis: F.interpolate(1/s) reads the centre 2x2 (lambda = 0.5)
+  const int off = (s == 1) ? 0 : (s / 2 - 1);
+  float acc[28];
+  float row[28];
+#pragma unroll 1
+  for (int sy = 0; sy < ns; ++sy) {
+#pragma unroll 1
+    for (int sx = 0; sx < ns; ++sx) {
+      const int y = Y * s + off + sy, x = X * s + off + sx;
+      float v[28];
+      if (level == 0) {
+        // IFNet_HDv3.py:141: cat(img0[:, :3], img1[:, :3], f0, f1, timestep)
+        float a[8], c[8];
+        ld8(s0 + ((size_t)y * W + x) * SRC_C, a);
+        ld8(s1 + ((size_t)y * W + x) * SRC_C, c);
+        v[0] = a[4]; v[1] = a[5]; v[2] = a[6];
+        v[3] = c[4]; v[4] = c[5]; v[5] = c[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[6 + i] = a[i]; v[10 + i] = c[i]; }
+        v[14] = t;
+#pragma unroll
+        for (int i = 15; i < 28; ++i) v[i] = 0.f;
+      } else {
+        // IFNet_HDv3.py:145-147: cat(warped_img0, warped_img1, wf0, wf1, timestep, mask, feat) ++ flow (:82)
+        float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
+        eval_state<Tt>(L, level, b, y, x, flow, last);
+        const float gx = gridx[x], gy = gridy[y];
+        float a[8], c[8];
+        warp8<T>(s0, H, W, geom, gx, gy, flow[0], flow[1], a);
+        warp8<T>(s1, H, W, geom, gx, gy, flow[2], flow[3], c);
+        v[0] = a[4]; v[1] = a[5]; v[2] = a[6];
+        v[3] = c[4]; v[4] = c[5]; v[5] = c[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[6 + i] = a[i]; v[10 + i] = c[i]; }
+        v[14] = t;
+        v[15] = last[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[16 + i] = last[5 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[24 + i] = flow[i];
+      }
+      if (ns == 1) {
+#pragma unroll
+        for (int i = 0; i < 28; ++i) acc[i] = v[i];
+      } else if (sx == 0) {
+#pragma unroll
+        for (int i = 0; i < 28; ++i) row[i] = 0.5f * v[i];
+      } else {
+        // upsample_bilinear2d: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11) with all lambdas = 0.5
+#pragma unroll
+        for (int i = 0; i < 28; ++i) {
+          const float r = row[i] + 0.5f * v[i];
+          acc[i] = (sy == 0) ? 0.5f * r : acc[i] + 0.5f * r;
+        }
+      }
+    }
+  }
+  // flow channels: interpolate(flow, 1/s) * 1. / s   (IFNet_HDv3.py:81)
+  const float inv_s = 1.f / (float)s;
+#pragma unroll
+  for (int i = 24; i < 28; ++i) acc[i] = acc[i] * inv_s;
+  // s2d store: [b][Y/2][X/2][(py*2+px)*32 + c]
+  T* dst = xin + ((((size_t)b * (Hs >> 1) + (Y >> 1)) * (Ws >> 1) + (X >> 1)) * 4 + ((Y & 1) * 2 + (X & 1))) * XIN_C;
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[k * 8 + i];
+    st8(dst + k * 8, o);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = acc[24 + i];
+#pragma unroll
+  for (int i = 4; i < 8; ++i) o[i] = 0.f;
+  st8(dst + 24, o);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// eval: full-resolution flow / mask / warped images / merged after `nlev` blocks (one thread per pixel)
+template <typename T, typename Tt, typename Tio>
+__global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const T* __restrict__ src0,
+                                                   const T* __restrict__ src1, const float* __restrict__ gridx,
+                                                   const float* __restrict__ gridy, Tio* __restrict__ oflow,
+                                                   Tio* __restrict__ omask, Tio* __restrict__ ow0,
+                                                   Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
+                                                   int H, int W, WarpGeom geom) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)H * W;
+  if (idx >= (size_t)B * plane) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const int b = (int)(idx / plane);
+  float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
+  eval_state<Tt>(L, nlev, b, y, x, flow, last);
+  const size_t pix = (size_t)y * W + x;
+  if (oflow) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) oflow[((size_t)b * 4 + c) * plane + pix] = from_f<Tio>(flow[c]);
+  }
+  if (omask) omask[(size_t)b * plane + pix] = from_f<Tio>(last[4]);
+  if (ow0 || ow1 || omerged) {
+    const float gx = gridx[x], gy = gridy[y];
+    float a[8], c[8];
+    warp8<T>(src0 + (size_t)b * plane * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);  // IFNet_HDv3.py:155
+    warp8<T>(src1 + (size_t)b * plane * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);  // IFNet_HDv3.py:156
+    const float m = 1.f / (1.f + expf(-last[4]));                                         // IFNet_HDv3.py:158
+    for (int ch = 0; ch < C; ++ch) {
+      const float w0 = a[4 + ch], w1 = c[4 + ch];
+      const size_t o = ((size_t)b * C + ch) * plane + pix;
+      if (ow0) ow0[o] = from_f<Tio>(w0);
+      if (ow1) ow1[o] = from_f<Tio>(w1);
+      if (omerged) omerged[o] = from_f<Tio>(w0 * m + w1 * (1.f - m));                     // IFNet_HDv3.py:159
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone operators (NCHW, op-level API)
+template <typename Tio>
+__global__ void __launch_bounds__(256) warp_op_kernel(const Tio* __restrict__ in, const Tio* __restrict__ flow,
+                                                      Tio* __restrict__ out, const float* __restrict__ gridx,
+                                                      const float* __restrict__ gridy, int B, int C, int H, int W,
+                                                      WarpGeom g) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)H * W;
+  if (idx >= (size_t)B * plane) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const int b = (int)(idx / plane);
+  const size_t pix = (size_t)y * W + x;
+  const float fx = to_f(flow[((size_t)b * 2 + 0) * plane + pix]);
+  const float fy = to_f(flow[((size_t)b * 2 + 1) * plane + pix]);
+  const float nx = gridx[x] + __fdiv_rn(fx, g.halfw);
+  const float ny = gridy[y] + __fdiv_rn(fy, g.halfh);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
+  ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float x1f = x0f + 1.f, y1f = y0f + 1.f;
+  const float wnw = (x1f - ix) * (y1f - iy), wne = (ix - x0f) * (y1f - iy);
+  const float wsw = (x1f - ix) * (iy - y0f), wse = (ix - x0f) * (iy - y0f);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const bool xin = (x0 + 1) < W, yin = (y0 + 1) < H;
+  for (int c = 0; c < C; ++c) {
+    const Tio* p = in + ((size_t)b * C + c) * plane + (size_t)y0 * W + x0;
+    float r = to_f(p[0]) * wnw;
+    if (xin) r += to_f(p[1]) * wne;
+    if (yin) {
+      r += to_f(p[W]) * wsw;
+      if (xin) r += to_f(p[W + 1]) * wse;
+    }
+    out[((size_t)b * C + c) * plane + pix] = from_f<Tio>(r);
+  }
+}
+
+// F.interpolate(bilinear, align_corners=False) with scale_factor = num/den (power-of-two ratio), NCHW fp32
+__global__ void __launch_bounds__(256) resize_op_kernel(const float* __restrict__ x, float* __restrict__ out, int BC,
+                                                        int H, int W, int Ho, int Wo, float ratio, float post_mul) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)BC * Ho * Wo) return;
+  const int ox = (int)(idx % Wo);
+  const int oy = (int)((idx / Wo) % Ho);
+  const int bc = (int)(idx / ((size_t)Wo * Ho));
+  const Lerp ly = make_lerp(oy, H, ratio), lx = make_lerp(ox, W, ratio);
+  const float* p = x + (size_t)bc * H * W;
+  const float v00 = p[(size_t)ly.i0 * W + lx.i0], v01 = p[(size_t)ly.i0 * W + lx.i1];
+  const float v10 = p[(size_t)ly.i1 * W + lx.i0], v11 = p[(size_t)ly.i1 * W + lx.i1];
+  out[idx] = (ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11)) * post_mul;
+}
+
+// torch.linspace(-1, 1, n) scalar formula (fallback when the caller passes no host grid)
+__global__ void fill_grid_kernel(float* g, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (n == 1) { g[0] = -1.f; return; }
+  const float step = 2.f / (float)(n - 1);
+  g[i] = (i < n / 2) ? __fadd_rn(-1.f, __fmul_rn(step, (float)i)) : __fsub_rn(1.f, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                           int C, int H, int W, int Cpad, int s2d) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * H * W * Cpad) return;
+  const int c = (int)(idx % Cpad);
+  const int xx = (int)((idx / Cpad) % W);
+  const int yy = (int)((idx / ((size_t)Cpad * W)) % H);
+  const int b = (int)(idx / ((size_t)Cpad * W * H));
+  const float v = c < C ? x[(((size_t)b * C + c) * H + yy) * W + xx] : 0.f;
+  if (!s2d) {
+    y[idx] = v;
+  } else {
+    y[((((size_t)b * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * 4 + ((yy & 1) * 2 + (xx & 1))) * Cpad + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                           int C, int H, int W, int Cpad) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * C * H * W) return;
+  const int xx = (int)(idx % W);
+  const int yy = (int)((idx / W) % H);
+  const int c = (int)((idx / ((size_t)W * H)) % C);
+  const int b = (int)(idx / ((size_t)W * H * C));
+  y[idx] = x[(((size_t)b * H + yy) * W + xx) * Cpad + c];
+}
+
+inline WarpGeom make_geom(int H, int W) {
+  WarpGeom g;
+  g.halfw = (float)((W - 1.0) / 2.0);
+  g.halfh = (float)((H - 1.0) / 2.0);
+  g.wm1 = (float)(W - 1);
+  g.hm1 = (float)(H - 1);
+  return g;
+}
+
+inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
+                void* head_in, cudaStream_t st) {
+  const size_t nq = (size_t)c.B * (c.H / 2) * (c.W / 2);
+  dim3 grid(nblk(nq, 256), 2);
+#define RIFE_PREP(TIO, T)                                                                                        \
+  prep_kernel<TIO, T><<<grid, 256, 0, st>>>((const TIO*)img0, (const TIO*)img1, (T*)src0, (T*)src1, (T*)head_in, \
+                                            c.B, c.C, c.H, c.W)
+  if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
+  else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
+  else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
+  else if (io_dtype == RIFE_F16 && c.half_act) RIFE_PREP(__half, __half);
+  else RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
+#undef RIFE_PREP
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+static LevelsArg pack_levels(const TmpLevel* levels, int n) {
+  LevelsArg L{};
+  for (int i = 0; i < n && i < MAXLEV; ++i) {
+    L.ptr[i] = levels[i].ptr;
+    L.h[i] = levels[i].h;
+    L.w[i] = levels[i].w;
+    L.s[i] = levels[i].s;
+  }
+  return L;
+}
+
+int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, cudaStream_t st) {
+  const size_t n = (size_t)c.B * (c.H / s) * (c.W / s);
+  LevelsArg L = pack_levels(levels, level);
+  WarpGeom g = make_geom(c.H, c.W);
+  if (c.half_act)
+    block_input_kernel<__half, __half><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const __half*)c.src0,
+                                                                      (const __half*)c.src1, c.gridx, c.gridy, c.tstep,
+                                                                      (__half*)xin, c.B, c.H, c.W, g);
+  else
+    block_input_kernel<float, float><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const float*)c.src0,
+                                                                    (const float*)c.src1, c.gridx, c.gridy, c.tstep,
+                                                                    (float*)xin, c.B, c.H, c.W, g);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, cudaStream_t st) {
+  const size_t n = (size_t)c.B * c.H * c.W;
+  LevelsArg L = pack_levels(levels, nlev);
+  WarpGeom g = make_geom(c.H, c.W);
+#define RIFE_EVAL(T, TIO)                                                                                         \
+  eval_kernel<T, T, TIO><<<nblk(n, 256), 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
+                                                       c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
+                                                       (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g)
+  if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
+  else if (!c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(float, __half);
+  else if (c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(__half, float);
+  else if (c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(__half, __half);
+  else RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: bad io dtype");
+#undef RIFE_EVAL
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_warp_op(const void* input, const void* flow, void* out, int B, int C, int H, int W, int dtype,
+                   const float* gridx, const float* gridy, cudaStream_t st) {
+  const size_t n = (size_t)B * H * W;
+  WarpGeom g = make_geom(H, W);
+  if (dtype == RIFE_F32)
+    warp_op_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float*)input, (const float*)flow, (float*)out, gridx,
+                                                         gridy, B, C, H, W, g);
+  else if (dtype == RIFE_F16)
+    warp_op_kernel<__half><<<nblk(n, 256), 256, 0, st>>>((const __half*)input, (const __half*)flow, (__half*)out,
+                                                          gridx, gridy, B, C, H, W, g);
+  else
+    RIFE_FAIL(RIFE_ERR_DTYPE, "rife_warp: dtype must be RIFE_F32 or RIFE_F16");
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_resize_op(const float* x, float* out, int B, int C, int H, int W, int num, int den, float post_mul,
+                     cudaStream_t st) {
+  const int Ho = (int)((long long)H * num / den), Wo = (int)((long long)W * num / den);
+  const size_t n = (size_t)B * C * Ho * Wo;
+  const float ratio = (float)den / (float)num;  // 1 / scale_factor
+  resize_op_kernel<<<nblk(n, 256), 256, 0, st>>>(x, out, B * C, H, W, Ho, Wo, ratio, post_mul);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_fill_grid(float* g, int n, cudaStream_t st) {
+  fill_grid_kernel<<<nblk(n, 128), 128, 0, st>>>(g, n);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, bool s2d,
+                            cudaStream_t st) {
+  const size_t n = (size_t)B * H * W * Cpad;
+  nchw_to_nhwc_kernel<<<nblk(n, 256), 256, 0, st>>>(x, y, B, C, H, W, Cpad, s2d ? 1 : 0);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st) {
+  const size_t n = (size_t)B * C * H * W;
+  nhwc_to_nchw_kernel<<<nblk(n, 256), 256, 0, st>>>(x, y, B, C, H, W, Cpad);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+}  // namespace rife

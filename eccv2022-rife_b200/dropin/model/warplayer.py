@@ -1,0 +1,8 @@
+"""Drop-in replacement for the reference module `model/warplayer.py` (same import path and name)."""
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from _pkg import pkg as _pkg  # noqa: E402
+
+warp = _pkg.warp
+device = _pkg.model.device

@@ -1,0 +1,10 @@
+"""Drop-in replacement for the reference module `train_log/RIFE_HDv3.py` (same import path and names)."""
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from _pkg import pkg as _pkg  # noqa: E402
+
+Model = _pkg.Model
+IFNet = _pkg.IFNet
+warp = _pkg.warp
+device = _pkg.model.device

@@ -1,0 +1,249 @@
+"""Host-side mirror of the reference's `train_log/IFNet_HDv3.py` (RIFE v4.25 HDv3 IFNet).
+
+The nn.Modules here are *parameter containers*: they register exactly the reference's 158
+state-dict tensors (same keys, shapes and construction order, so the default init under a given
+torch seed and `load_state_dict` of `train_log/flownet.pkl` behave identically) but never run a
+PyTorch conv.  `IFNet.forward` hands raw device pointers to librife_b200.so, which runs the whole
+pipeline with hand-written sm_100a kernels (see csrc/ and DESIGN.md).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .warplayer import base_grids
+
+_BLOCK_C = (192, 128, 96, 64, 32)     # IFNet_HDv3.py:95-99
+_BLOCK_IN = (7 + 8, 8 + 4 + 8 + 8, 8 + 4 + 8 + 8, 8 + 4 + 8 + 8, 8 + 4 + 8 + 8)
+
+
+def _conv_lrelu(cin, cout, stride):
+    # key layout "<name>.0.{weight,bias}" of the reference's conv() helper (IFNet_HDv3.py:9-14)
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride, 1, bias=True), nn.LeakyReLU(0.2, True))
+
+
+class Head(nn.Module):
+    """Parameters of IFNet_HDv3.py:24-31 (cnn0..cnn3)."""
+
+    def __init__(self):
+        super().__init__()
+        self.cnn0 = nn.Conv2d(3, 16, 3, 2, 1)
+        self.cnn1 = nn.Conv2d(16, 16, 3, 1, 1)
+        self.cnn2 = nn.Conv2d(16, 16, 3, 1, 1)
+        self.cnn3 = nn.ConvTranspose2d(16, 4, 4, 2, 1)
+
+
+class ResConv(nn.Module):
+    """Parameters of IFNet_HDv3.py:45-51 (conv, beta)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, 1, 1)
+        self.beta = nn.Parameter(torch.ones((1, c, 1, 1)), requires_grad=True)
+
+
+class IFBlock(nn.Module):
+    """Parameters of IFNet_HDv3.py:57-76 (conv0, convblock, lastconv)."""
+
+    def __init__(self, in_planes, c=64):
+        super().__init__()
+        self.conv0 = nn.Sequential(_conv_lrelu(in_planes, c // 2, 2), _conv_lrelu(c // 2, c, 2))
+        self.convblock = nn.Sequential(*[ResConv(c) for _ in range(8)])
+        self.lastconv = nn.Sequential(nn.ConvTranspose2d(c, 4 * 13, 4, 2, 1), nn.PixelShuffle(2))
+
+
+def _precision_from_env(default):
+    v = os.environ.get("RIFE_B200_PRECISION", default).lower()
+    if v not in ("fp32", "fp16", "auto"):
+        raise ValueError("RIFE_B200_PRECISION must be fp32, fp16 or auto")
+    return v
+
+
+class _Plan:
+    __slots__ = ("handle", "workspace", "key")
+
+
+class IFNet(nn.Module):
+    """Drop-in for `train_log.IFNet_HDv3.IFNet`.
+
+    precision: "fp32" (fp32 storage + FMA convs, <=1e-4 vs the reference), "fp16" (fp16 NHWC
+    activations, tcgen05 tensor-core convs, fp32 accumulate/coordinates) or "auto" (follows the input
+    dtype: float16 inputs -> fp16 mode, float32 inputs -> fp32 mode).  Env override: RIFE_B200_PRECISION.
+    """
+
+    def __init__(self, precision="auto"):
+        super().__init__()
+        for i in range(5):                                    # same order as IFNet_HDv3.py:95-100
+            setattr(self, f"block{i}", IFBlock(_BLOCK_IN[i], c=_BLOCK_C[i]))
+        self.encode = Head()
+        self.precision = _precision_from_env(precision)
+        self._weights = {}    # (device index, precision) -> (handle, generation)
+        self._plans = {}
+        self._generation = 0
+
+    # ------------------------------------------------------------------ cache invalidation
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._generation += 1
+        return r
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._generation += 1
+        return r
+
+    def invalidate(self):
+        """Call after mutating parameters in place (the packed device copy is rebuilt on next use)."""
+        self._generation += 1
+
+    def _param_stamp(self):
+        return self._generation, sum(p._version for p in self.parameters())
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def release(self):
+        lib = _lib._lib
+        if lib is None:
+            return
+        for pl in self._plans.values():
+            lib.rife_plan_destroy(pl.handle)
+        self._plans.clear()
+        for h, _ in self._weights.values():
+            lib.rife_weights_destroy(h)
+        self._weights.clear()
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _resolve_precision(self, dtype):
+        p = self.precision
+        if p == "auto":
+            p = "fp16" if dtype == torch.float16 else "fp32"
+        return _lib.PRECISION_FP16 if p == "fp16" else _lib.PRECISION_FP32
+
+    def _get_weights(self, device, prec):
+        lib = _lib.load()
+        key = (device.index, prec)
+        stamp = self._param_stamp()
+        ent = self._weights.get(key)
+        if ent is not None and ent[1] == stamp:
+            return ent[0]
+        if ent is not None:   # stale: plans bound to it go too
+            for k in [k for k in self._plans if k[0] == key]:
+                lib.rife_plan_destroy(self._plans.pop(k).handle)
+            lib.rife_weights_destroy(ent[0])
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self.state_dict().items()}
+        n = len(sd)
+        names = (C.c_char_p * n)(*[k.encode() for k in sd])
+        ptrs = (C.c_void_p * n)(*[v.data_ptr() for v in sd.values()])
+        numel = (C.c_int64 * n)(*[v.numel() for v in sd.values()])
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.rife_weights_create(C.byref(h), n, names, ptrs, numel, prec))
+        self._weights[key] = (h, stamp)
+        return h
+
+    def _get_plan(self, device, prec, b, c, h, w, scale):
+        lib = _lib.load()
+        wh = self._get_weights(device, prec)
+        key = ((device.index, prec), b, c, h, w, float(scale))
+        pl = self._plans.get(key)
+        if pl is not None:
+            return pl
+        with torch.cuda.device(device):
+            nbytes = lib.rife_plan_workspace_bytes(b, c, h, w, float(scale), prec)
+            if nbytes == 0:
+                _lib.check(-2)
+            pl = _Plan()
+            pl.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            gx, gy, _, _ = base_grids(h, w, device)
+            hd = C.c_void_p()
+            _lib.check(lib.rife_plan_create(C.byref(hd), wh, b, c, h, w, float(scale), pl.workspace.data_ptr(), nbytes,
+                                            gx.data_ptr(), gy.data_ptr()))
+            pl.handle = hd
+        self._plans[key] = pl
+        return pl
+
+    @staticmethod
+    def _scale_from_list(scale_list):
+        if len(scale_list) < 5:
+            raise ValueError("IFNet.forward indexes scale_list[0..4] (IFNet_HDv3.py:139-148): pass 5 entries")
+        s4 = float(scale_list[4])
+        want = [16 * s4, 8 * s4, 4 * s4, 2 * s4, s4]
+        if [float(s) for s in scale_list[:5]] != want or s4 not in (1.0, 2.0, 4.0):
+            raise NotImplementedError(
+                f"eccv2022-rife_b200 builds the scale_list=[16,8,4,2,1]/scale pyramid of RIFE_HDv3.py:58 with scale in "
+                f"{{1, 0.5, 0.25}}; got {list(scale_list)}")
+        return 1.0 / s4
+
+    @staticmethod
+    def _timesteps(timestep, b):
+        if torch.is_tensor(timestep):
+            t = timestep.detach().to("cpu", torch.float32).reshape(-1)
+            if t.numel() == 1:
+                t = t.repeat(b)
+            if t.numel() != b:
+                raise ValueError("tensor timestep must have shape (B,1,1,1) (IFNet_HDv3.py:127)")
+            vals = t.tolist()
+        else:
+            vals = [float(timestep)] * b
+        return (C.c_float * b)(*vals)
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
+        if x.dtype not in (torch.float32, torch.float16):
+            raise TypeError("eccv2022-rife_b200: float32 or float16 frames required")
+
+    def run(self, img0, img1, timestep, scale, want_all):
+        """Shared engine call.  Returns merged[-1] (want_all=False) or the full forward structure."""
+        self._check_input(img0)
+        lib = _lib.load()
+        b, c, h, w = img0.shape
+        img0 = img0.contiguous()
+        img1 = img1.contiguous()
+        dev = img0.device
+        prec = self._resolve_precision(img0.dtype)
+        pl = self._get_plan(dev, prec, b, c, h, w, scale)
+        io = _lib.RIFE_F32 if img0.dtype == torch.float32 else _lib.RIFE_F16
+        ts = self._timesteps(timestep, b)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            if not want_all:
+                out = torch.empty_like(img0)
+                _lib.check(lib.rife_inference(pl.handle, img0.data_ptr(), img1.data_ptr(), ts, out.data_ptr(), io, stream))
+                return out
+            o = _lib.IFNetOutputs()
+            flows = [torch.empty((b, 4, h, w), dtype=img0.dtype, device=dev) for _ in range(5)]
+            w0 = [torch.empty_like(img0) for _ in range(5)]
+            w1 = [torch.empty_like(img0) for _ in range(5)]
+            mask = torch.empty((b, 1, h, w), dtype=img0.dtype, device=dev)
+            merged = torch.empty_like(img0)
+            for i in range(5):
+                o.flow[i] = flows[i].data_ptr()
+                o.warped0[i] = w0[i].data_ptr()
+                o.warped1[i] = w1[i].data_ptr()
+            o.mask = mask.data_ptr()
+            o.merged = merged.data_ptr()
+            _lib.check(lib.rife_ifnet_forward(pl.handle, img0.data_ptr(), img1.data_ptr(), ts, C.byref(o), io, stream))
+        merged_list = [(w0[i], w1[i]) for i in range(4)] + [merged]
+        return flows, mask, merged_list
+
+    def forward(self, x, timestep=0.5, scale_list=[8, 4, 2, 1], training=False, fastmode=True, ensemble=False):
+        """Same signature / return structure as IFNet_HDv3.py:119-169 (inference branch):
+        (flow_list[5], mask logits of the last block, merged = 4 (warped0, warped1) tuples + blended tensor)."""
+        if training:
+            raise NotImplementedError("training=True is broken in the reference (img0 undefined) and out of scope")
+        if ensemble:
+            print("warning: ensemble is not supported since RIFEv4.21")
+        if not fastmode:
+            print("contextnet is removed")
+        channel = x.shape[1] // 2
+        scale = self._scale_from_list(scale_list)
+        return self.run(x[:, :channel], x[:, channel:], timestep, scale, want_all=True)

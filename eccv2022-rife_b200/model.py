@@ -1,0 +1,69 @@
+"""Drop-in for the reference's `train_log/RIFE_HDv3.py` `Model` facade (inference side)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ifnet import IFNet
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+class Model:
+    """Same surface as RIFE_HDv3.py:15-60: Model(), .flownet, .version, .train/.eval/.device/.load_model/
+    .save_model/.inference.  `update` (training, broken in the reference) is out of scope."""
+
+    def __init__(self, local_rank=-1, precision="auto"):
+        self.flownet = IFNet(precision=precision)
+        self.device()
+        self.version = 4.25
+        if local_rank != -1:
+            raise NotImplementedError("DDP training wrapper (RIFE_HDv3.py:24-25) is out of scope: inference only")
+
+    def train(self):
+        self.flownet.train()
+
+    def eval(self):
+        self.flownet.eval()
+
+    def device(self):
+        self.flownet.to(device)
+
+    def load_model(self, path, rank=0):
+        """RIFE_HDv3.py:36-50: rank -1 keeps only 'module.'-prefixed keys and strips the prefix; non-strict."""
+        def convert(param):
+            if rank == -1:
+                return {k.replace("module.", ""): v for k, v in param.items() if "module." in k}
+            return param
+
+        if rank <= 0:
+            sd = torch.load("{}/flownet.pkl".format(path), map_location="cpu" if not torch.cuda.is_available() else None)
+            self.flownet.load_state_dict(convert(sd), False)
+
+    def save_model(self, path, rank=0):
+        if rank == 0:
+            torch.save(self.flownet.state_dict(), "{}/flownet.pkl".format(path))
+
+    def inference(self, img0, img1, timestep=0.5, scale=1.0):
+        """RIFE_HDv3.py:56-60.  Positional order (img0, img1, timestep, scale) is the reference's."""
+        return self.flownet.run(img0, img1, timestep, scale, want_all=False)
+
+    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None):
+        """End-to-end call on HOST (ideally pinned) NCHW tensors: H2D copies, inference and the D2H copy of the
+        result are enqueued on `stream` (default: current) by rife_inference_host; returns without syncing."""
+        net = self.flownet
+        if img0_host.is_cuda or out_host.is_cuda:
+            raise ValueError("inference_host takes host tensors")
+        lib = _lib.load()
+        b, c, h, w = img0_host.shape
+        prec = net._resolve_precision(img0_host.dtype)
+        pl = net._get_plan(device, prec, b, c, h, w, scale)
+        io = _lib.RIFE_F32 if img0_host.dtype == torch.float32 else _lib.RIFE_F16
+        ts = net._timesteps(timestep, b)
+        with torch.cuda.device(device):
+            st = (stream or torch.cuda.current_stream()).cuda_stream
+            _lib.check(lib.rife_inference_host(pl.handle, img0_host.data_ptr(), img1_host.data_ptr(), ts,
+                                               out_host.data_ptr(), io, st))
+        return out_host

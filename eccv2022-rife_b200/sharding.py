@@ -1,0 +1,46 @@
+"""Frame-pair sharding across GPUs (one process per GPU, no collective on the data path).
+
+The reference has no multi-GPU inference; BASELINE.json's north_star shards independent frame pairs
+across the GPUs of one box.  Each rank gets a contiguous range of pair indices; results are concatenated in index
+order.  torch.distributed is only used for the final (optional) ordered gather and for timing barriers."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous [lo, hi) range of `rank`: sizes differ by at most one, earlier ranks take the remainder."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world_size")
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def run_sharded(infer, frames, timesteps=(0.5,), gather=True):
+    """Interpolate every adjacent pair of `frames` (a list/tensor of (C,H,W) or (1,C,H,W) frames) at each timestep.
+
+    `infer(img0, img1, t)` is Model.inference-like.  Pairs are sharded contiguously over the ranks of the default
+    process group (or run locally when torch.distributed is not initialised).  Returns, on every rank when
+    `gather` is set, the list of outputs ordered by (pair index, timestep index); otherwise the local slice."""
+    n_pairs = len(frames) - 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(n_pairs, rank, world)
+    local = []
+    for i in range(lo, hi):
+        a, b = frames[i], frames[i + 1]
+        if a.dim() == 3:
+            a, b = a.unsqueeze(0), b.unsqueeze(0)
+        for t in timesteps:
+            local.append(infer(a, b, t))
+    if not gather or world == 1:
+        return local
+    payload = [x.cpu() for x in local]
+    buckets = [None] * world
+    dist.all_gather_object(buckets, payload)
+    out = []
+    for bkt in buckets:
+        out.extend(bkt)
+    return out

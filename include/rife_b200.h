@@ -1,0 +1,138 @@
+/*
+ * rife_b200.h -- C ABI of the B200-native RIFE HDv3 (v4.25) IFNet inference hot path.
+ *
+ * One shared library (librife_b200.so), plain pointers and sizes, no torch / C++ types.
+ * Every entry point is asynchronous on the given CUDA stream (no device sync inside)
+ * unless stated otherwise, returns 0 on success or a negative rife_status, and leaves a
+ * human-readable message retrievable with rife_last_error() (thread-local).
+ * There is NO CPU fallback: host pointers where device pointers are expected are an error.
+ *
+ * The reference (Dk0071942/ECCV2022-RIFE) is pure Python on PyTorch and has no native
+ * interface; each function below names the reference call site (file:line, relative to
+ * the reference repo) whose work it replaces.  A maintainer of the reference binds these
+ * with ctypes.
+ *
+ * Tensor conventions at the boundary: NCHW contiguous, float32 or float16 (rife_dtype),
+ * device pointers (tensor.data_ptr()), stream = torch.cuda.current_stream().cuda_stream.
+ */
+#ifndef RIFE_B200_H
+#define RIFE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIFE_B200_ABI_VERSION 1
+
+typedef enum rife_status {
+  RIFE_OK = 0,
+  RIFE_ERR_INVALID_ARG = -1,   /* null pointer, bad enum, bad handle                     */
+  RIFE_ERR_SHAPE = -2,         /* H or W not a multiple of 64/scale, unsupported C/scale */
+  RIFE_ERR_DTYPE = -3,         /* unsupported dtype / precision combination              */
+  RIFE_ERR_CUDA = -4,          /* a CUDA runtime / driver call failed                    */
+  RIFE_ERR_WEIGHTS = -5,       /* missing / mis-shaped tensor in the state dict          */
+  RIFE_ERR_WORKSPACE = -6,     /* workspace too small or misaligned                      */
+  RIFE_ERR_NOT_DEVICE_PTR = -7 /* a pointer that must be device memory is not            */
+} rife_status;
+
+typedef enum rife_dtype { RIFE_F32 = 0, RIFE_F16 = 1 } rife_dtype;
+
+/* Arithmetic mode of the whole pipeline.
+ *  RIFE_PRECISION_FP32: fp32 storage, fp32 FMA convs        (<= 1e-4 max-abs vs reference fp32)
+ *  RIFE_PRECISION_FP16: fp16 NHWC activations, tcgen05 tensor-core convs with fp32
+ *                       accumulation in TMEM, fp32 coordinates (<= 2e-2 max-abs, >= 45 dB PSNR) */
+typedef enum rife_precision { RIFE_PRECISION_FP32 = 0, RIFE_PRECISION_FP16 = 1 } rife_precision;
+
+typedef struct rife_weights rife_weights; /* immutable packed weights on one device          */
+typedef struct rife_plan rife_plan;       /* shape-specialised launch plan bound to a workspace */
+
+/* ---- library ------------------------------------------------------------------------- */
+int rife_abi_version(void);
+const char* rife_last_error(void);
+/* Number of kernels this library has launched on this process since load (all threads). */
+uint64_t rife_launch_count(void);
+
+/* ---- weights: replaces Model.load_model's load_state_dict (train_log/RIFE_HDv3.py:36-50) */
+/* `names[i]` are state-dict keys WITHOUT the "module." prefix (e.g. "block0.conv0.0.0.weight",
+ * "encode.cnn3.bias"); `data[i]` are HOST float32 pointers in the reference's own layouts
+ * (Conv2d OIHW, ConvTranspose2d IOHW, beta (1,c,1,1)); `numel[i]` element counts.  All 158
+ * tensors of SURVEY Appendix A must be present.  Repacks into kernel layouts on the current
+ * device (synchronous). */
+int rife_weights_create(rife_weights** out, int n, const char* const* names,
+                        const float* const* data, const int64_t* numel, int precision);
+int rife_weights_destroy(rife_weights* w);
+
+/* ---- plan ------------------------------------------------------------------------------ */
+/* Bytes of device workspace a plan for this problem needs (0 on error, see rife_last_error). */
+size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int precision);
+/* B frames-pairs per call, C image channels (3, or 4 for RGBA), H and W multiples of 64/scale,
+ * scale in {1, 0.5, 0.25} (scale_list = [16,8,4,2,1]/scale, train_log/RIFE_HDv3.py:58).
+ * `workspace` is caller-owned device memory (256-byte aligned) that must outlive the plan.
+ * `gridx_host` (W floats) / `gridy_host` (H floats) are the warp base grids
+ * torch.linspace(-1,1,W) / (-1,1,H) of model/warplayer.py:11-14 computed by the caller on the
+ * host (so that they are bit-identical to the reference's); NULL = computed by the library.
+ * Synchronous (uploads small tables, encodes TMA descriptors). */
+int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H, int W,
+                     float scale, void* workspace, size_t workspace_bytes,
+                     const float* gridx_host, const float* gridy_host);
+int rife_plan_destroy(rife_plan* p);
+
+/* ---- Model.inference (train_log/RIFE_HDv3.py:56-60) ------------------------------------ */
+/* img0, img1, out: device, NCHW (B,C,H,W) of `io_dtype`.  timestep_host: B floats (a Python
+ * float timestep is broadcast by the caller; a (B,1,1,1) tensor is passed element-wise,
+ * train_log/IFNet_HDv3.py:124-127).  out = merged[-1]. */
+int rife_inference(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
+                   void* out, int io_dtype, void* stream);
+
+/* ---- IFNet.forward (train_log/IFNet_HDv3.py:119-169), full return structure ------------- */
+/* Any pointer may be NULL (not materialised).  flow[i]: (B,4,H,W); mask: (B,1,H,W) pre-sigmoid
+ * logits of the last block; warped0/1[i]: (B,C,H,W) = merged[i] tuples; merged: (B,C,H,W). */
+typedef struct rife_ifnet_outputs {
+  void* flow[5];
+  void* mask;
+  void* warped0[5];
+  void* warped1[5];
+  void* merged;
+} rife_ifnet_outputs;
+int rife_ifnet_forward(rife_plan* p, const void* img0, const void* img1,
+                       const float* timestep_host, const rife_ifnet_outputs* outs, int io_dtype,
+                       void* stream);
+
+/* ---- end-to-end with HOST buffers (the caller side of inference_img.py:57-60,105-111) ---- */
+/* img0_host/img1_host/out_host: host NCHW buffers of io_dtype (pinned memory recommended).
+ * Enqueues H2D copies into plan-owned staging, the inference, and the D2H copy of the result
+ * on `stream`; returns without synchronising. */
+int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host,
+                        const float* timestep_host, void* out_host, int io_dtype, void* stream);
+
+/* ---- single operators (op-level parity tests; drop-in for the reference's helpers) ------ */
+/* warp(tenInput, tenFlow), model/warplayer.py:8-22.  input (B,C,H,W), flow (B,2,H,W) in pixels,
+ * out (B,C,H,W); all device, NCHW, `dtype`.  gridx/gridy: DEVICE float tables (W / H entries)
+ * or NULL (library formula). */
+int rife_warp(const void* input, const void* flow, void* out, int B, int C, int H, int W,
+              int dtype, const float* gridx_dev, const float* gridy_dev, void* stream);
+/* F.interpolate(x, scale_factor=num/den, mode="bilinear", align_corners=False) for power-of-two
+ * factors (train_log/IFNet_HDv3.py:79,81,86); out = result * post_mul.  NCHW float32, device. */
+int rife_resize_bilinear(const void* x, void* out, int B, int C, int H, int W, int num, int den,
+                         float post_mul, void* stream);
+/* conv() / ResConv of train_log/IFNet_HDv3.py:9-14,45-54 on NCHW float32 device tensors:
+ * y = leaky_relu((conv3x3(x, w, stride, pad=1) + bias) * beta + residual, 0.2)
+ * (beta / residual may be NULL => plain conv + bias + LeakyReLU; act=0 skips the LeakyReLU).
+ * w: device OIHW float32.  `precision` selects the fp32 FMA kernel or the fp16 tcgen05 kernel.
+ * Synchronous (repacks on the fly; test entry point, not the product path). */
+int rife_conv3x3(const float* x, const float* w, const float* bias, const float* beta,
+                 const float* residual, float* y, int B, int Cin, int H, int W, int Cout,
+                 int stride, int act, int precision, void* stream);
+/* ConvTranspose2d(Cin,Cout,4,2,1) (+ optional PixelShuffle(2)) of train_log/IFNet_HDv3.py:30,73-76.
+ * w: device IOHW float32; y: (B,Cout,2H,2W) or, with pixel_shuffle=1, (B,Cout/4,4H,4W). */
+int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, float* y, int B,
+                             int Cin, int H, int W, int Cout, int pixel_shuffle, int precision,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIFE_B200_H */

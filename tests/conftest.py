@@ -1,0 +1,69 @@
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+AMP = 4.0  # tests/golden/make_golden.py
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return importlib.import_module("eccv2022-rife_b200")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+_models = {}
+
+
+def seeded_model(pkg, amp=1.0, precision="auto"):
+    """The host mirror under torch.manual_seed(1234): regenerates the reference's default-init weights
+    (checked against tests/golden/weights_seed1234.json); `amp` scales every lastconv weight."""
+    import torch
+    key = (amp, precision)
+    if key not in _models:
+        torch.manual_seed(1234)
+        m = pkg.Model(precision=precision)
+        m.eval()
+        if amp != 1.0:
+            with torch.no_grad():
+                for i in range(5):
+                    getattr(m.flownet, f"block{i}").lastconv[0].weight.mul_(amp)
+            m.flownet.invalidate()
+        _models[key] = m
+    return _models[key]
+
+
+def numpy_state_dict(model):
+    return {k: v.detach().cpu().numpy().astype(np.float32) for k, v in model.flownet.state_dict().items()}
+
+
+def torch_state_dict(model):
+    return {k: v.detach().cpu().float() for k, v in model.flownet.state_dict().items()}
+
+
+def psnr(a, b):
+    mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)

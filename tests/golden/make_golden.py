@@ -1,0 +1,192 @@
+#!/usr/bin/env python3
+"""Generate golden vectors by running the UNMODIFIED reference on CPU (fp32).
+
+Run in the build container only (the reference lives at /root/reference, read-only,
+and does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests / golden vectors of its own, so these
+fixtures -- outputs of the reference's own `train_log/RIFE_HDv3.Model.inference`,
+`train_log/IFNet_HDv3.IFNet.forward` and `model/warplayer.warp` on seeded inputs -- are
+what pins the oracle (`oracle/`) and, through it, the CUDA path.
+
+Weights: `train_log/flownet.pkl` is absent from the container (.MISSING_LARGE_BLOBS), so
+weights are the reference's default init under `torch.manual_seed(1234)`.  They are NOT
+stored (22.7 MB); instead `weights_seed1234.json` stores per-tensor float64 sums and a
+sha256 so that a test can prove that the host-side mirror module regenerates them
+bit-exactly from the same seed.  `amp` cases multiply every `block{i}.lastconv.0.weight`
+by AMP to push |flow| to tens of pixels and exercise the border clamp of warp().
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("RIFE_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.set_num_threads(os.cpu_count() or 1)
+
+from train_log.RIFE_HDv3 import Model  # noqa: E402  (the reference)
+from model import warplayer as ref_warplayer  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+AMP = 4.0
+
+
+def build_model(seed=1234, amp=1.0):
+    torch.manual_seed(seed)
+    m = Model()
+    m.eval()
+    if amp != 1.0:
+        for i in range(5):
+            getattr(m.flownet, f"block{i}").lastconv[0].weight.mul_(amp)
+    return m
+
+
+def rand_frames(seed, b, c, h, w, smooth=False):
+    g = torch.Generator().manual_seed(seed)
+    if not smooth:
+        return torch.rand(b, c, h, w, generator=g), torch.rand(b, c, h, w, generator=g)
+    # smooth frames: low-res noise upsampled bicubically, second frame shifted by a few px
+    lo = torch.rand(b, c, h // 8 + 2, w // 8 + 2, generator=g)
+    big = torch.nn.functional.interpolate(lo, size=(h + 16, w + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+    return big[:, :, 8:8 + h, 8:8 + w].contiguous(), big[:, :, 5:5 + h, 11:11 + w].contiguous()
+
+
+def f32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def weights_manifest():
+    m = build_model(1234)
+    sd = m.flownet.state_dict()
+    h = hashlib.sha256()
+    sums = {}
+    for k, v in sd.items():
+        a = v.detach().cpu().numpy().astype(np.float32)
+        h.update(k.encode())
+        h.update(a.tobytes())
+        sums[k] = {"shape": list(a.shape), "sum": float(a.astype(np.float64).sum())}
+    man = {"seed": 1234, "torch": torch.__version__, "sha256": h.hexdigest(), "n_tensors": len(sd),
+           "n_params": int(sum(v.numel() for v in sd.values())), "tensors": sums}
+    with open(os.path.join(OUT, "weights_seed1234.json"), "w") as f:
+        json.dump(man, f, indent=1)
+    print("weights manifest:", man["sha256"], man["n_tensors"], man["n_params"])
+
+
+def case_demo():
+    """Config 1: inference_img.py on demo/I0_0.png + I0_1.png, exp=1 (inference_img.py:57-60, 99)."""
+    import cv2
+    i0 = cv2.imread(os.path.join(REF, "demo/I0_0.png"), cv2.IMREAD_UNCHANGED)
+    i1 = cv2.imread(os.path.join(REF, "demo/I0_1.png"), cv2.IMREAD_UNCHANGED)
+    img0 = (torch.tensor(i0.transpose(2, 0, 1)) / 255.).unsqueeze(0)
+    img1 = (torch.tensor(i1.transpose(2, 0, 1)) / 255.).unsqueeze(0)
+    m = build_model(1234)
+    out = m.inference(img0, img1)
+    print("demo mean", float(out.mean()), out[0, :, 100, 200].tolist())
+    flow_list, mask, merged = m.flownet(torch.cat((img0, img1), 1), 0.5, [16, 8, 4, 2, 1])
+    # the amplified-flow variant on the same smooth natural images
+    ma = build_model(1234, AMP)
+    out_amp = ma.inference(img0, img1)
+    fl_amp, _, _ = ma.flownet(torch.cat((img0, img1), 1), 0.5, [16, 8, 4, 2, 1])
+    print("demo amp |flow|max", float(fl_amp[-1].abs().max()))
+    save("demo_256x448", img0_u8=i0, img1_u8=i1, out=f32(out), flow=f32(flow_list[-1]).astype(np.float16),
+         mask=f32(mask).astype(np.float16), out_amp=f32(out_amp), flow_amp=f32(fl_amp[-1]).astype(np.float16))
+
+
+def case_full_structure():
+    """IFNet.forward full return structure on a small random input (IFNet_HDv3.py:119-169)."""
+    img0, img1 = rand_frames(7, 1, 3, 64, 128)
+    m = build_model(1234, AMP)
+    flow_list, mask, merged = m.flownet(torch.cat((img0, img1), 1), 0.5, [16, 8, 4, 2, 1])
+    arrs = {"img0": f32(img0), "img1": f32(img1), "mask": f32(mask), "merged4": f32(merged[4])}
+    for i in range(5):
+        arrs[f"flow{i}"] = f32(flow_list[i])
+    for i in range(4):
+        arrs[f"merged{i}_0"] = f32(merged[i][0])
+        arrs[f"merged{i}_1"] = f32(merged[i][1])
+    save("ifnet_full_64x128_amp", **arrs)
+
+
+def case_inference_variants():
+    arrs = {}
+    # (a) batch 2, arbitrary timestep, amplified flow, random noise (worst case for warp parity)
+    img0, img1 = rand_frames(11, 2, 3, 128, 192)
+    arrs["a_img0"], arrs["a_img1"] = f32(img0), f32(img1)
+    arrs["a_out"] = f32(build_model(1234, AMP).inference(img0, img1, timestep=0.3))
+    # (b) scale=0.5 (H, W multiples of 128), smooth frames
+    img0, img1 = rand_frames(12, 1, 3, 128, 256, smooth=True)
+    arrs["b_img0"], arrs["b_img1"] = f32(img0), f32(img1)
+    arrs["b_out"] = f32(build_model(1234, AMP).inference(img0, img1, 0.5, 0.5))
+    # (c) RGBA input (4 channels: IFNet_HDv3.py:121-123 splits C/2, Head sees [:, :3])
+    img0, img1 = rand_frames(13, 1, 4, 64, 64)
+    arrs["c_img0"], arrs["c_img1"] = f32(img0), f32(img1)
+    arrs["c_out"] = f32(build_model(1234).inference(img0, img1))
+    # (d) tensor timestep of shape (B,1,1,1) (IFNet_HDv3.py:126-127)
+    img0, img1 = rand_frames(14, 2, 3, 64, 64)
+    ts = torch.tensor([0.25, 0.75]).view(2, 1, 1, 1)
+    arrs["d_img0"], arrs["d_img1"], arrs["d_t"] = f32(img0), f32(img1), f32(ts)
+    arrs["d_out"] = f32(build_model(1234, AMP).inference(img0, img1, ts))
+    # (e) default-init, smooth, 128x128
+    img0, img1 = rand_frames(15, 1, 3, 128, 128, smooth=True)
+    arrs["e_img0"], arrs["e_img1"] = f32(img0), f32(img1)
+    arrs["e_out"] = f32(build_model(1234).inference(img0, img1))
+    save("inference_variants", **arrs)
+
+
+def case_warp():
+    """model/warplayer.py:8-22 on random data, small and large flows, C=3 and C=4."""
+    arrs = {}
+    g = torch.Generator().manual_seed(21)
+    for name, (b, c, h, w, mag) in {"small": (2, 3, 48, 80, 2.0), "large": (1, 4, 64, 96, 40.0),
+                                    "huge": (1, 3, 32, 32, 200.0)}.items():
+        x = torch.rand(b, c, h, w, generator=g)
+        fl = (torch.rand(b, 2, h, w, generator=g) * 2 - 1) * mag
+        ref_warplayer.backwarp_tenGrid.clear()
+        y = ref_warplayer.warp(x, fl)
+        arrs[f"{name}_x"], arrs[f"{name}_flow"], arrs[f"{name}_y"] = f32(x), f32(fl), f32(y)
+    save("warp_cases", **arrs)
+
+
+def case_ops():
+    """Intermediate ops of IFBlock.forward / Head.forward on one small input, for op-level pins."""
+    m = build_model(1234)
+    net = m.flownet
+    g = torch.Generator().manual_seed(31)
+    arrs = {}
+    x = torch.rand(1, 3, 64, 64, generator=g)
+    arrs["head_x"] = f32(x)
+    arrs["head_y"] = f32(net.encode(x))
+    xb = torch.rand(1, 24, 64, 64, generator=g)
+    fl = (torch.rand(1, 4, 64, 64, generator=g) * 2 - 1) * 3
+    f, mk, ft = net.block3(xb, fl, scale=2)
+    arrs["blk3_x"], arrs["blk3_flow"] = f32(xb), f32(fl)
+    arrs["blk3_oflow"], arrs["blk3_omask"], arrs["blk3_ofeat"] = f32(f), f32(mk), f32(ft)
+    x0 = torch.rand(1, 15, 64, 64, generator=g)
+    f, mk, ft = net.block0(x0, None, scale=16)
+    arrs["blk0_x"] = f32(x0)
+    arrs["blk0_oflow"], arrs["blk0_omask"], arrs["blk0_ofeat"] = f32(f), f32(mk), f32(ft)
+    save("ops_cases", **arrs)
+
+
+if __name__ == "__main__":
+    weights_manifest()
+    case_demo()
+    case_full_structure()
+    case_inference_variants()
+    case_warp()
+    case_ops()
