@@ -14,7 +14,8 @@ PRECISION_FP32, PRECISION_FP16 = 0, 1
 # every symbol declared in include/rife_b200.h
 SYMBOLS = [
     "rife_abi_version", "rife_last_error", "rife_launch_count", "rife_weights_create", "rife_weights_destroy",
-    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_inference", "rife_ifnet_forward",
+    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_plan_set_profiling",
+    "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
 ]
 
@@ -52,6 +53,8 @@ def load():
     lib.rife_plan_workspace_bytes.restype = sz
     lib.rife_plan_create.argtypes = [C.POINTER(vp), vp, i, i, i, i, f, vp, sz, vp, vp]
     lib.rife_plan_destroy.argtypes = [vp]
+    lib.rife_plan_set_profiling.argtypes = [vp, i]
+    lib.rife_plan_get_profile.argtypes = [vp, C.POINTER(C.c_char_p), fp, i]
     lib.rife_inference.argtypes = [vp, vp, vp, fp, vp, i, vp]
     lib.rife_ifnet_forward.argtypes = [vp, vp, vp, fp, C.POINTER(IFNetOutputs), i, vp]
     lib.rife_inference_host.argtypes = [vp, vp, vp, fp, vp, i, vp]

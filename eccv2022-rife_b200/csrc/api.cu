@@ -294,7 +294,47 @@ struct rife_plan {
   PlanLayout L{};
   char* ws = nullptr;
   void* at(size_t off) const { return ws + off; }
+  // optional per-stage CUDA-event timing (rife_plan_set_profiling)
+  bool profile = false;
+  struct Stage {
+    std::string name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+  };
+  std::vector<Stage> stages;
+  size_t n_stage = 0;  // stages recorded by the last run
+  ~rife_plan() {
+    for (auto& s : stages) {
+      if (s.e0) cudaEventDestroy(s.e0);
+      if (s.e1) cudaEventDestroy(s.e1);
+    }
+  }
 };
+
+// brackets one launch with events when profiling is on
+struct StageTimer {
+  rife_plan* p;
+  cudaStream_t st;
+  rife_plan::Stage* s = nullptr;
+  StageTimer(rife_plan* p_, cudaStream_t st_, const std::string& name) : p(p_), st(st_) {
+    if (!p->profile) return;
+    if (p->n_stage == p->stages.size()) {
+      p->stages.emplace_back();
+      cudaEventCreate(&p->stages.back().e0);
+      cudaEventCreate(&p->stages.back().e1);
+    }
+    s = &p->stages[p->n_stage++];
+    s->name = name;
+    cudaEventRecord(s->e0, st);
+  }
+  ~StageTimer() {
+    if (s) cudaEventRecord(s->e1, st);
+  }
+};
+#define RIFE_STAGE(name, expr)          \
+  do {                                  \
+    StageTimer _t(p, st, name);         \
+    RIFE_TRY(expr);                     \
+  } while (0)
 
 extern "C" {
 
@@ -346,6 +386,26 @@ int rife_plan_destroy(rife_plan* p) {
   return RIFE_OK;
 }
 
+int rife_plan_set_profiling(rife_plan* p, int enable) {
+  if (!p) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_profiling: null plan");
+  p->profile = enable != 0;
+  p->n_stage = 0;
+  return RIFE_OK;
+}
+
+int rife_plan_get_profile(rife_plan* p, const char** names, float* ms, int cap) {
+  if (!p || !names || !ms) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_get_profile: null argument");
+  int n = 0;
+  for (size_t i = 0; i < p->n_stage && n < cap; ++i, ++n) {
+    names[n] = p->stages[i].name.c_str();
+    if (cudaEventElapsedTime(&ms[n], p->stages[i].e0, p->stages[i].e1) != cudaSuccess) {
+      cudaGetLastError();
+      ms[n] = -1.f;
+    }
+  }
+  return n;
+}
+
 }  // extern "C"
 
 // --------------------------------------------------------------------------------------------------
@@ -381,18 +441,19 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.half_act = half_act;
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
-  RIFE_TRY(launch_prep(c, img0, img1, io_dtype, (void*)c.src0, (void*)c.src1, p->at(L.head_in), st));
+  p->n_stage = 0;
+  RIFE_STAGE("prep", launch_prep(c, img0, img1, io_dtype, (void*)c.src0, (void*)c.src1, p->at(L.head_in), st));
   {
     ConvIO io;
     io.B = 2 * B; io.H = H / 2; io.W = W / 2;
     io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;
-    RIFE_TRY(run_conv(p, w->head[0], io, st));
+    RIFE_STAGE("head.cnn0", run_conv(p, w->head[0], io, st));
     io.in = p->at(L.head_a); io.out = p->at(L.head_b);
-    RIFE_TRY(run_conv(p, w->head[1], io, st));
+    RIFE_STAGE("head.cnn1", run_conv(p, w->head[1], io, st));
     io.in = p->at(L.head_b); io.out = p->at(L.head_a);
-    RIFE_TRY(run_conv(p, w->head[2], io, st));
+    RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, st));
     io.in = p->at(L.head_a); io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
-    RIFE_TRY(run_conv(p, w->head[3], io, st));
+    RIFE_STAGE("head.cnn3", run_conv(p, w->head[3], io, st));
   }
 
   // ---- 5 IFBlocks (IFNet_HDv3.py:139-157)
@@ -400,25 +461,26 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   for (int i = 0; i < 5; ++i) {
     const int s = L.s[i], c_ = kBlockC[i];
     const int hs = H / s, wsz = W / s;
-    RIFE_TRY(launch_block_input(c, i, lev, s, p->at(L.xin), st));
+    const std::string bn = "b" + std::to_string(i);
+    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), st));
     ConvIO io;
     io.B = B;
     // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
     io.H = hs / 2; io.W = wsz / 2; io.in = p->at(L.xin); io.out = p->at(L.c0); io.epi = EPI_LRELU_S2D; io.out_c = c_ / 2;
-    RIFE_TRY(run_conv(p, w->blk[i].conv00, io, st));
+    RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, st));
     // conv0.1: stride 2 on (hs/2, wsz/2) == 2x2 taps on (hs/4, wsz/4)
     io.H = hs / 4; io.W = wsz / 4; io.in = p->at(L.c0); io.out = p->at(L.act_a); io.epi = EPI_LRELU; io.out_c = c_;
-    RIFE_TRY(run_conv(p, w->blk[i].conv01, io, st));
+    RIFE_STAGE(bn + ".conv0.1", run_conv(p, w->blk[i].conv01, io, st));
     void* cur = p->at(L.act_a);
     void* nxt = p->at(L.act_b);
     for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
       io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
-      RIFE_TRY(run_conv(p, w->blk[i].res[j], io, st));
+      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, st));
       void* t = cur; cur = nxt; nxt = t;
     }
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
     io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
-    RIFE_TRY(run_conv(p, w->blk[i].last, io, st));
+    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, st));
     lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = s;
 
     EvalOut eo;
@@ -429,7 +491,8 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
       eo.mask = outs->mask;
       eo.merged = outs->merged;
     }
-    if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged) RIFE_TRY(launch_eval(c, i + 1, lev, eo, io_dtype, st));
+    if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged)
+      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(c, i + 1, lev, eo, io_dtype, st));
   }
   return RIFE_OK;
 }

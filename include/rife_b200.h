@@ -79,6 +79,11 @@ int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H
                      float scale, void* workspace, size_t workspace_bytes,
                      const float* gridx_host, const float* gridy_host);
 int rife_plan_destroy(rife_plan* p);
+/* Per-kernel timing: when enabled, every launch of the pipeline is bracketed by CUDA events on the launch
+ * stream.  After the stream has been synchronised, rife_plan_get_profile returns (up to `cap`) the stage names
+ * (pointers valid until the next run) and durations in ms of the LAST run; return value = number of stages. */
+int rife_plan_set_profiling(rife_plan* p, int enable);
+int rife_plan_get_profile(rife_plan* p, const char** names, float* ms, int cap);
 
 /* ---- Model.inference (train_log/RIFE_HDv3.py:56-60) ------------------------------------ */
 /* img0, img1, out: device, NCHW (B,C,H,W) of `io_dtype`.  timestep_host: B floats (a Python

@@ -1,0 +1,147 @@
+"""End-to-end parity of the CUDA pipeline (through the C ABI and the drop-in Python surface) against the golden
+vectors of the unmodified reference, the numpy oracle and the torch-CPU restatement.
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4 max-abs; fp16 mode <= 2e-2 max-abs and >= 45 dB PSNR."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import AMP, load_golden, numpy_state_dict, psnr, seeded_model, torch_state_dict
+from oracle import rife_oracle as O
+from oracle import torch_ref as T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL32 = 1e-4
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_golden_variants_fp32(pkg):
+    g = load_golden("inference_variants")
+    m, ma = seeded_model(pkg, 1.0, "fp32"), seeded_model(pkg, AMP, "fp32")
+    out = ma.inference(cu(g["a_img0"]), cu(g["a_img1"]), timestep=0.3).cpu().numpy()
+    assert np.abs(out - g["a_out"]).max() < TOL32                     # batch 2, arbitrary timestep, noise, |flow|~10px
+    out = ma.inference(cu(g["b_img0"]), cu(g["b_img1"]), 0.5, 0.5).cpu().numpy()
+    assert np.abs(out - g["b_out"]).max() < TOL32                     # scale=0.5 (positional, RIFE_HDv3.py:56)
+    out = m.inference(cu(g["c_img0"]), cu(g["c_img1"])).cpu().numpy()
+    assert out.shape == (1, 4, 64, 64) and np.abs(out - g["c_out"]).max() < TOL32      # RGBA
+    out = ma.inference(cu(g["d_img0"]), cu(g["d_img1"]), cu(g["d_t"])).cpu().numpy()
+    assert np.abs(out - g["d_out"]).max() < TOL32                     # tensor timestep (B,1,1,1)
+    out = m.inference(cu(g["e_img0"]), cu(g["e_img1"])).cpu().numpy()
+    assert np.abs(out - g["e_out"]).max() < TOL32
+
+
+def test_demo_config1_fp32(pkg):
+    """BASELINE config 1 (inference_img.py on demo/I0_0.png + I0_1.png, exp=1, scale=1.0, fp32)."""
+    g = load_golden("demo_256x448")
+    img0 = cu(g["img0_u8"].transpose(2, 0, 1)[None]).float() / 255.
+    img1 = cu(g["img1_u8"].transpose(2, 0, 1)[None]).float() / 255.
+    out = seeded_model(pkg, 1.0, "fp32").inference(img0, img1).cpu().numpy()
+    assert np.abs(out - g["out"]).max() < TOL32
+    assert abs(float(out.mean()) - 0.34859153) < 1e-5
+    out_amp = seeded_model(pkg, AMP, "fp32").inference(img0, img1).cpu().numpy()
+    assert np.abs(out_amp - g["out_amp"]).max() < TOL32
+
+
+def test_ifnet_forward_structure_fp32(pkg):
+    """IFNet.forward returns (flow_list[5], mask logits, merged[4 tuples + tensor]) (IFNet_HDv3.py:169)."""
+    g = load_golden("ifnet_full_64x128_amp")
+    net = seeded_model(pkg, AMP, "fp32").flownet
+    x = torch.cat((cu(g["img0"]), cu(g["img1"])), 1)
+    flows, mask, merged = net(x, 0.5, [16, 8, 4, 2, 1])
+    assert len(flows) == 5 and len(merged) == 5 and isinstance(merged[0], tuple) and torch.is_tensor(merged[4])
+    for i in range(5):
+        assert np.abs(flows[i].cpu().numpy() - g[f"flow{i}"]).max() < 5e-4, i
+    for i in range(4):
+        assert np.abs(merged[i][0].cpu().numpy() - g[f"merged{i}_0"]).max() < TOL32
+        assert np.abs(merged[i][1].cpu().numpy() - g[f"merged{i}_1"]).max() < TOL32
+    assert np.abs(mask.cpu().numpy() - g["mask"]).max() < TOL32
+    assert np.abs(merged[4].cpu().numpy() - g["merged4"]).max() < TOL32
+
+
+def test_against_numpy_oracle_fp32(pkg):
+    rng = np.random.default_rng(3)
+    a = rng.random((1, 3, 64, 192), dtype=np.float32)
+    b = rng.random((1, 3, 64, 192), dtype=np.float32)
+    m = seeded_model(pkg, AMP, "fp32")
+    ref = O.model_inference(numpy_state_dict(m), a, b, 0.7)
+    out = m.inference(cu(a), cu(b), 0.7).cpu().numpy()
+    assert np.abs(out - ref).max() < TOL32
+
+
+def test_batch_consistency_and_determinism(pkg):
+    """Size-independent properties: a batch equals its items run one by one; repeated calls are bit-identical."""
+    rng = np.random.default_rng(4)
+    a = cu(rng.random((3, 3, 128, 128), dtype=np.float32))
+    b = cu(rng.random((3, 3, 128, 128), dtype=np.float32))
+    m = seeded_model(pkg, AMP, "fp32")
+    full = m.inference(a, b)
+    assert torch.equal(full, m.inference(a, b))
+    for i in range(3):
+        assert torch.equal(full[i:i + 1], m.inference(a[i:i + 1], b[i:i + 1]))
+
+
+def test_range_property(pkg):
+    """warp (bilinear, border) and the sigmoid blend are convex combinations: frames in [0,1] stay in [0,1]."""
+    m = seeded_model(pkg, AMP, "fp32")
+    rng = np.random.default_rng(5)
+    a, b = cu(rng.random((2, 3, 128, 192), dtype=np.float32)), cu(rng.random((2, 3, 128, 192), dtype=np.float32))
+    out = m.inference(a, b, 0.25)
+    assert out.shape == a.shape and torch.isfinite(out).all()
+    assert float(out.min()) >= -1e-6 and float(out.max()) <= 1 + 1e-6
+
+
+def test_1080p_against_torch_cpu_fp32(pkg):
+    """BASELINE's headline shape (1088x1920 padded 1080p) against the torch-CPU restatement, smooth frames."""
+    g = torch.Generator().manual_seed(9)
+    lo = torch.rand(1, 3, 1088 // 8 + 2, 1920 // 8 + 2, generator=g)
+    big = torch.nn.functional.interpolate(lo, size=(1088 + 16, 1920 + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+    a, b = big[:, :, 8:8 + 1088, 8:8 + 1920].contiguous(), big[:, :, 5:5 + 1088, 11:11 + 1920].contiguous()
+    m = seeded_model(pkg, AMP, "fp32")
+    ref = T.model_inference(torch_state_dict(m), a, b).numpy()
+    out = m.inference(a.to(DEV), b.to(DEV)).cpu().numpy()
+    assert np.abs(out - ref).max() < TOL32
+
+
+def test_shape_and_device_errors(pkg):
+    m = seeded_model(pkg, 1.0, "fp32")
+    with pytest.raises(RuntimeError):
+        m.inference(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))            # CPU tensors: no fallback
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        m.inference(torch.zeros(1, 3, 96, 64, device=DEV), torch.zeros(1, 3, 96, 64, device=DEV))
+    with pytest.raises(RuntimeError, match="multiples of 64/scale = 128"):
+        m.inference(torch.zeros(1, 3, 64, 64, device=DEV), torch.zeros(1, 3, 64, 64, device=DEV), 0.5, 0.5)
+    with pytest.raises(NotImplementedError):
+        m.flownet(torch.zeros(1, 6, 64, 64, device=DEV), 0.5, [8, 4, 2, 1, 0.5])
+
+
+def test_inference_host_e2e(pkg):
+    """rife_inference_host: pinned host buffers in, pinned host buffer out."""
+    g = load_golden("inference_variants")
+    m = seeded_model(pkg, 1.0, "fp32")
+    a = torch.from_numpy(g["e_img0"]).pin_memory()
+    b = torch.from_numpy(g["e_img1"]).pin_memory()
+    out = torch.empty_like(a).pin_memory()
+    m.inference_host(a, b, out)
+    torch.cuda.synchronize()
+    assert np.abs(out.numpy() - g["e_out"]).max() < TOL32
+
+
+def test_dropin_import_paths(pkg):
+    """`from train_log.RIFE_HDv3 import Model` / `from model.warplayer import warp` resolve to this package when
+    eccv2022-rife_b200/dropin precedes the reference on sys.path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import torch;"
+            "from train_log.RIFE_HDv3 import Model; from train_log.IFNet_HDv3 import IFNet; from model.warplayer import warp;"
+            "torch.manual_seed(1234); m = Model(); m.eval(); m.device();"
+            "x = torch.rand(1, 3, 64, 64, device='cuda'); y = m.inference(x, x.flip(3)); print(tuple(y.shape), m.version)"
+            ) % os.path.join(root, "eccv2022-rife_b200", "dropin")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "(1, 3, 64, 64) 4.25" in r.stdout
