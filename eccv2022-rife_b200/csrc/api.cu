@@ -33,11 +33,6 @@ static bool is_device_ptr(const void* p) {
 
 // --------------------------------------------------------------------------------------------------
 // host-side repacking into the implicit-GEMM layouts [tap][cin_pad][npad]
-struct HostLayer {
-  int kind = CONV_3x3, cin = 0, n = 0, npad = 0, taps = 9;
-  std::vector<float> w, bias, beta;
-};
-
 // Conv2d OIHW (co, ci, 3, 3), stride 1
 static HostLayer pack_conv3x3(const float* W, const float* b, int co, int ci, int cin_pad) {
   HostLayer L;
@@ -83,6 +78,7 @@ static HostLayer pack_conv3x3_s2d(const float* W, const float* b, int co, int ci
 static HostLayer pack_convT(const float* W, const float* b, int ci, int co, int cin_pad) {
   HostLayer L;
   L.kind = CONV_3x3; L.taps = 9; L.cin = cin_pad; L.n = 4 * co; L.npad = round_up(4 * co, 16);
+  L.convt_co = co;
   L.w.assign((size_t)9 * cin_pad * L.npad, 0.f);
   L.bias.assign(L.npad, 0.f);
   for (int par = 0; par < 4; ++par) {
@@ -129,7 +125,7 @@ static int upload(rife_weights* w, const void* host, size_t bytes, void** dev) {
   return RIFE_OK;
 }
 
-static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d) {
+static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool ps_layout = false) {
   void *pw, *pb, *pbeta = nullptr;
   RIFE_TRY(upload(w, h.w.data(), h.w.size() * 4, &pw));
   RIFE_TRY(upload(w, h.bias.data(), h.bias.size() * 4, &pb));
@@ -139,14 +135,16 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d) {
   d->f32.beta = (const float*)pbeta;
   d->f32.kind = h.kind; d->f32.cin = h.cin; d->f32.n = h.n; d->f32.npad = h.npad;
   if (w->precision == RIFE_PRECISION_FP16) {
-    void* ph = nullptr;
+    void *ph = nullptr, *phb = nullptr, *phbeta = nullptr;
     std::vector<__half> packed;
-    RIFE_TRY(umma_pack_weights(h.w.data(), h.taps, h.cin, h.npad, &packed, &d->h16));
+    std::vector<float> hb, hbeta;
+    RIFE_TRY(umma_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->h16));
     RIFE_TRY(upload(w, packed.data(), packed.size() * sizeof(__half), &ph));
+    RIFE_TRY(upload(w, hb.data(), hb.size() * 4, &phb));
+    if (!hbeta.empty()) RIFE_TRY(upload(w, hbeta.data(), hbeta.size() * 4, &phbeta));
     d->h16.w = (const __half*)ph;
-    d->h16.bias = d->f32.bias;
-    d->h16.beta = d->f32.beta;
-    d->h16.kind = h.kind; d->h16.n = h.n;
+    d->h16.bias = (const float*)phb;
+    d->h16.beta = (const float*)phbeta;
   }
   return RIFE_OK;
 }
@@ -217,7 +215,7 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
       for (int k = 0; k < c; ++k) L.beta[k] = be[k];
       if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
     }
-    if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last))) return fail(st);
+    if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last, /*ps_layout=*/true))) return fail(st);
   }
   *out = w;
   return RIFE_OK;
@@ -567,7 +565,7 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
   tmpw.precision = precision;
   cudaGetDevice(&tmpw.device);
   DevLayer d;
-  int rc = upload_layer(&tmpw, h, &d);
+  int rc = upload_layer(&tmpw, h, &d, epi == EPI_PS);
   const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
   (void)E;
   float *xin = nullptr, *res = nullptr, *yout = nullptr;

@@ -1,6 +1,486 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a, fp16 operands / fp32 TMEM accumulators.
+//
+//   out[p][n] = sum_{tap} sum_{ci} act[p + off(tap)][ci] * w[tap][ci][n]        (p = pixel of an NHWC tensor)
+//
+// One CTA per 128-pixel tile (TH x TW output pixels = the 128 rows of one UMMA M=128 accumulator).
+//   warp 0   : TMA producer.  Per (tap, K chunk): one 4-D tiled TMA load of the activation box
+//              {KC ch, TW, TH, 1} at (x0+dx, y0+dy) -- out-of-image coordinates (the conv's zero padding and the
+//              ragged last tiles) are zero-filled by the TMA unit -- plus one 2-D load of the weight tile
+//              {KC, Npad}.  Both land K-major with the hardware swizzle that matches KC*2 bytes (128B/64B/32B).
+//   warp 1   : allocates TMEM, then one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Npad,
+//              K=16) straight from the swizzled smem tiles; tcgen05.commit releases each smem stage back to the
+//              producer and finally signals the epilogue.
+//   warps 2-5: epilogue.  tcgen05.ld (32 lanes x 16 columns) -> registers -> fused tail of the layer
+//              (bias, LeakyReLU, beta*x + residual, space-to-depth store, ConvTranspose parity scatter +
+//              PixelShuffle) -> 16/32-byte vector stores of fp16 NHWC.
+// Reference semantics: train_log/IFNet_HDv3.py:9-14 (conv), :24-43 (Head), :45-54 (ResConv), :73-76 (lastconv).
+#include <cuda.h>
+
 #include "conv_umma.cuh"
+
 namespace rife {
-int umma_pack_weights(const float*, int, int, int, std::vector<__half>*, UmmaLayer*) { RIFE_FAIL(RIFE_ERR_DTYPE, "fp16 tcgen05 path not built yet"); }
-int launch_conv_umma(const UmmaLayer&, const ConvIO&, cudaStream_t) { RIFE_FAIL(RIFE_ERR_DTYPE, "fp16 tcgen05 path not built yet"); }
-int launch_conv_umma_f32io(const UmmaLayer&, const ConvIO&, cudaStream_t) { RIFE_FAIL(RIFE_ERR_DTYPE, "fp16 tcgen05 path not built yet"); }
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_TAPS = 9;
+
+struct UmmaParams {
+  int B, H, W;
+  int tw, th, tiles_x, tiles_y;
+  int ntaps, nchunks, kc, stages;
+  int npad, n_valid, tmem_cols;
+  int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
+  int epi, out_c, cpp;
+  const float* bias;
+  const float* beta;
+  const __half* res;
+  __half* out;
+  signed char dy[MAX_TAPS], dx[MAX_TAPS];
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, rows of `kc` fp16 (= swizzle span), 8-row swizzle atoms stacked every 8*kc*2 bytes
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address       [0,14)
+  d |= (uint64_t)1 << 16;                            // LBO (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version 1 (sm_100)     [46,48)
+  d |= (uint64_t)layout_type << 61;                  // swizzle mode        [61,64)
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = v[i];
+  st8(dst, a);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
+  st8(dst + 8, a);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                const __grid_constant__ CUtensorMap tm_b,
+                                                                const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
+
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int b = tile / p.tiles_y;
+  const int x0 = tx * p.tw, y0 = ty * p.th;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int ksteps = p.ntaps * p.nchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int tap = ks / p.nchunks, chunk = ks - tap * p.nchunks;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, (uint32_t)(p.a_bytes + p.npad * p.kc * 2));
+        const uint32_t sa = tiles_base + stage * stage_bytes;
+        tma_load_4d(sa, &tm_a, fb, chunk * p.kc, x0 + p.dx[tap], y0 + p.dy[tap], b);
+        tma_load_2d(sa + p.a_bytes, &tm_b, fb, 0, (tap * p.nchunks + chunk) * p.npad);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t sbo = 8u * (uint32_t)p.kc * 2u;
+      const uint32_t layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+      const int ksub = p.kc >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = tiles_base + stage * stage_bytes;
+        const uint64_t da = make_smem_desc(sa, sbo, layout);
+        const uint64_t db = make_smem_desc(sa + p.a_bytes, sbo, layout);
+        for (int k = 0; k < ksub; ++k)  // advance 16 fp16 = 32 bytes along K inside the swizzle span
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    // ---------------- epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (accumulator row = pixel of the tile)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int py_ = m / p.tw, px_ = m - py_ * p.tw;
+    const int y = y0 + py_, x = x0 + px_;
+    const bool valid = (y < p.H) && (x < p.W);
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nchunk16 = p.npad >> 4;
+    for (int j = 0; j < nchunk16; ++j) {
+      float v[16];
+      __syncwarp();
+      tmem_ld16(trow + (uint32_t)(j * 16), v);
+      if (!valid) continue;
+      const int n0 = j * 16;
+      {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = __ldg(bp + i);
+          v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+        }
+      }
+      switch (p.epi) {
+        case EPI_LRELU:
+        case EPI_LINEAR: {
+          if (p.epi == EPI_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
+          }
+          if (n0 < p.n_valid) store16h(p.out + (((size_t)b * p.H + y) * p.W + x) * p.out_c + n0, v);
+        } break;
+        case EPI_LRELU_S2D: {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
+          const size_t o = ((((size_t)b * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1)));
+          if (n0 < p.n_valid) store16h(p.out + o * p.out_c + n0, v);
+        } break;
+        case EPI_RES: {
+          const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.out_c + n0;
+          float r[8], be[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ld8(p.res + o + 8 * h, r);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h + 4 * g));
+              be[0] = bb.x; be[1] = bb.y; be[2] = bb.z; be[3] = bb.w;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = 8 * h + 4 * g + i;
+                v[k] = lrelu02(v[k] * be[i] + r[4 * g + i]);
+              }
+            }
+          }
+          store16h(p.out + o, v);
+        } break;
+        case EPI_PS: {
+          // permuted columns: chunk j = par*4 + (dy*2+dx) holds the 13 (+3 zero) channels of one output pixel
+          const int par = j >> 2, sub = j & 3;
+          const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * x + 2 * (par & 1) + (sub & 1);
+          store16h(p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
+        } break;
+        case EPI_HEADT: {
+#pragma unroll
+          for (int par = 0; par < 4; ++par) {
+            const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+            float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
+            st4(p.out + (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
+          }
+        } break;
+        case EPI_CONVT: {
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + i;
+            if (n >= p.n_valid) break;
+            const int par = n / p.cpp, co = n - par * p.cpp;
+            const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+            p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
+          }
+        } break;
+        default: break;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ casts for the f32io wrapper
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(x[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __half2float(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+}  // namespace
+
+int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
+                      std::vector<float>* beta, UmmaLayer* L) {
+  if (h.cin % 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: cin must be a multiple of 16");
+  const int kc = (h.cin % 64 == 0) ? 64 : ((h.cin % 32 == 0) ? 32 : 16);
+  const int nchunks = h.cin / kc;
+  std::vector<int> colmap;  // new column -> old column (or -1 = zero column)
+  if (ps_layout) {
+    if (h.convt_co != 52) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: PixelShuffle layout is the 52-channel lastconv");
+    colmap.assign(256, -1);
+    for (int par = 0; par < 4; ++par)
+      for (int sub = 0; sub < 4; ++sub)
+        for (int k = 0; k < 13; ++k) colmap[(par * 4 + sub) * 16 + k] = par * 52 + 4 * k + sub;  // co = 4k + 2dy + dx
+  } else {
+    colmap.resize(h.npad);
+    for (int i = 0; i < h.npad; ++i) colmap[i] = i;
+  }
+  const int np = (int)colmap.size();
+  if (np % 16 || np > 256) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: N must be a multiple of 16 and <= 256");
+  packed->assign((size_t)h.taps * nchunks * np * kc, __float2half_rn(0.f));
+  for (int t = 0; t < h.taps; ++t)
+    for (int ch = 0; ch < nchunks; ++ch)
+      for (int n = 0; n < np; ++n) {
+        const int on = colmap[n];
+        if (on < 0) continue;
+        for (int k = 0; k < kc; ++k)
+          (*packed)[(((size_t)t * nchunks + ch) * np + n) * kc + k] =
+              __float2half_rn(h.w[((size_t)t * h.cin + ch * kc + k) * h.npad + on]);
+      }
+  bias->assign(np, 0.f);
+  beta->clear();
+  if (!h.beta.empty()) beta->assign(np, 0.f);
+  for (int n = 0; n < np; ++n) {
+    if (colmap[n] < 0) continue;
+    (*bias)[n] = h.bias[colmap[n]];
+    if (!h.beta.empty()) (*beta)[n] = h.beta[colmap[n]];
+  }
+  L->kind = h.kind; L->taps = h.taps; L->cin = h.cin; L->kc = kc;
+  L->n = ps_layout ? 256 : h.n;
+  L->npad = np;
+  L->ps_cols = ps_layout ? 1 : 0;
+  return RIFE_OK;
+}
+
+int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_PS needs the PixelShuffle column layout");
+  if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_RES needs beta and res");
+  if (io.epi == EPI_HEADT && L.npad != 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_HEADT expects N = 16");
+
+  UmmaParams p{};
+  p.B = io.B; p.H = io.H; p.W = io.W;
+  p.tw = 16; p.th = 8;
+  p.tiles_x = (io.W + p.tw - 1) / p.tw;
+  p.tiles_y = (io.H + p.th - 1) / p.th;
+  p.ntaps = L.taps; p.kc = L.kc; p.nchunks = L.cin / L.kc;
+  p.npad = L.npad; p.n_valid = L.n;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < L.npad) p.tmem_cols <<= 1;
+  p.a_bytes = TILE_M * L.kc * 2;
+  p.b_bytes = ((L.npad * L.kc * 2) + 1023) / 1024 * 1024;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = 98304 / stage_bytes;
+  if (stages < 2) stages = 2;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int ksteps = p.ntaps * p.nchunks;
+  if (stages > ksteps) stages = ksteps;
+  p.stages = stages;
+  p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par;
+  p.bias = L.bias; p.beta = L.beta;
+  p.res = (const __half*)io.res; p.out = (__half*)io.out;
+  if (L.kind == CONV_3x3) {
+    for (int t = 0; t < 9; ++t) { p.dy[t] = (signed char)(t / 3 - 1); p.dx[t] = (signed char)(t % 3 - 1); }
+  } else {
+    for (int t = 0; t < 4; ++t) { p.dy[t] = (signed char)(t / 2 - 1); p.dx[t] = (signed char)(t % 2 - 1); }
+  }
+
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)io.W, (cuuint64_t)io.H, (cuuint64_t)io.B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)io.W * L.cin * 2, (cuuint64_t)io.H * io.W * L.cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)L.kc, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(io.in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(L.kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.kc, (cuuint64_t)L.taps * p.nchunks * L.npad};
+    cuuint64_t strides[1] = {(cuuint64_t)L.kc * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)L.npad};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(L.w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(L.kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+  }
+  const int smem = stages * stage_bytes + 1024;
+  {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+      RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[dev] = true;
+    }
+  }
+  const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y * io.B);
+  conv_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a, tm_b, p);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_conv_umma_f32io(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
+  size_t nin = (size_t)io.B * io.H * io.W * L.cin, nout = 0, nres = 0;
+  switch (io.epi) {
+    case EPI_PS: nout = (size_t)io.B * 16 * io.H * io.W * TMP_C; break;
+    case EPI_HEADT:
+    case EPI_CONVT: nout = (size_t)io.B * 4 * io.H * io.W * io.out_c; break;
+    default: nout = (size_t)io.B * io.H * io.W * io.out_c; break;
+  }
+  if (io.res) nres = (size_t)io.B * io.H * io.W * io.out_c;
+  __half *hin = nullptr, *hout = nullptr, *hres = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    cudaFree(hin); cudaFree(hout); cudaFree(hres);
+  };
+  cudaError_t e = cudaMalloc((void**)&hin, nin * 2);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&hout, nout * 2);
+  if (e == cudaSuccess && nres) e = cudaMalloc((void**)&hres, nres * 2);
+  if (e == cudaSuccess) e = cudaMemsetAsync(hout, 0, nout * 2, st);
+  if (e != cudaSuccess) {
+    cleanup();
+    RIFE_FAIL(RIFE_ERR_CUDA, std::string("conv_umma_f32io: ") + cudaGetErrorString(e));
+  }
+  f32_to_f16_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, nin);
+  if (nres) f32_to_f16_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, nres);
+  ConvIO h = io;
+  h.in = hin; h.res = hres; h.out = hout;
+  int rc = launch_conv_umma(L, h, st);
+  if (rc == RIFE_OK) {
+    f16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, nout);
+    if (cudaGetLastError() != cudaSuccess) rc = RIFE_ERR_CUDA;
+  }
+  cleanup();
+  return rc;
+}
+
+}  // namespace rife

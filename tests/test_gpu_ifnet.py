@@ -145,3 +145,58 @@ def test_dropin_import_paths(pkg):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "(1, 3, 64, 64) 4.25" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------- fp16 / tcgen05 mode
+TOL16, PSNR16 = 2e-2, 45.0
+
+
+def _check16(out, ref, what):
+    err = float(np.abs(out - ref).max())
+    p = psnr(out, ref)
+    assert err < TOL16 and p >= PSNR16, f"{what}: max-abs {err:.4f}, PSNR {p:.1f} dB"
+
+
+def test_golden_variants_fp16(pkg):
+    g = load_golden("inference_variants")
+    m, ma = seeded_model(pkg, 1.0, "fp16"), seeded_model(pkg, AMP, "fp16")
+    _check16(ma.inference(cu(g["a_img0"]), cu(g["a_img1"]), timestep=0.3).cpu().numpy(), g["a_out"], "a")
+    _check16(ma.inference(cu(g["b_img0"]), cu(g["b_img1"]), 0.5, 0.5).cpu().numpy(), g["b_out"], "b")
+    _check16(m.inference(cu(g["c_img0"]), cu(g["c_img1"])).cpu().numpy(), g["c_out"], "c")
+    _check16(ma.inference(cu(g["d_img0"]), cu(g["d_img1"]), cu(g["d_t"])).cpu().numpy(), g["d_out"], "d")
+    _check16(m.inference(cu(g["e_img0"]), cu(g["e_img1"])).cpu().numpy(), g["e_out"], "e")
+    # fp16 tensors in / out (the reference's --fp16 mode, inference_video.py:85-86,190-194)
+    out = m.inference(cu(g["e_img0"]).half(), cu(g["e_img1"]).half())
+    assert out.dtype == torch.float16
+    _check16(out.float().cpu().numpy(), g["e_out"], "e/half-io")
+
+
+def test_demo_config1_fp16(pkg):
+    g = load_golden("demo_256x448")
+    img0 = cu(g["img0_u8"].transpose(2, 0, 1)[None]).float() / 255.
+    img1 = cu(g["img1_u8"].transpose(2, 0, 1)[None]).float() / 255.
+    _check16(seeded_model(pkg, 1.0, "fp16").inference(img0, img1).cpu().numpy(), g["out"], "demo")
+    _check16(seeded_model(pkg, AMP, "fp16").inference(img0, img1).cpu().numpy(), g["out_amp"], "demo-amp")
+
+
+def test_720p_config2_fp16(pkg):
+    """BASELINE config 2: 720p (padded 768x1280) 2X, fp16, against the torch-CPU fp32 restatement."""
+    g = torch.Generator().manual_seed(10)
+    lo = torch.rand(1, 3, 768 // 8 + 2, 1280 // 8 + 2, generator=g)
+    big = torch.nn.functional.interpolate(lo, size=(768 + 16, 1280 + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+    a, b = big[:, :, 8:8 + 768, 8:8 + 1280].contiguous(), big[:, :, 5:5 + 768, 11:11 + 1280].contiguous()
+    m = seeded_model(pkg, AMP, "fp16")
+    ref = T.model_inference(torch_state_dict(m), a, b).numpy()
+    out = m.inference(a.to(DEV).half(), b.to(DEV).half()).float().cpu().numpy()
+    _check16(out, ref, "720p")
+
+
+def test_batch_consistency_fp16(pkg):
+    rng = np.random.default_rng(4)
+    a = cu(rng.random((3, 3, 128, 128), dtype=np.float32)).half()
+    b = cu(rng.random((3, 3, 128, 128), dtype=np.float32)).half()
+    m = seeded_model(pkg, AMP, "fp16")
+    full = m.inference(a, b)
+    assert torch.equal(full, m.inference(a, b))
+    for i in range(3):
+        assert torch.equal(full[i:i + 1], m.inference(a[i:i + 1], b[i:i + 1]))
