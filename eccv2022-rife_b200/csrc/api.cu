@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_halo.cuh"
 #include "conv_umma.cuh"
 
 namespace rife {
@@ -100,7 +101,9 @@ static HostLayer pack_convT(const float* W, const float* b, int ci, int co, int 
 
 struct DevLayer {
   ConvLayerF32 f32;   // always present (fp32 FMA path)
-  UmmaLayer h16;      // present when precision == FP16
+  UmmaLayer h16;      // present when precision == FP16: NHWC tcgen05 kernel (conv_umma.cu)
+  HaloLayer hk;       // present when precision == FP16 and the layer fits the halo kernel (conv_halo.cu)
+  bool use_hk = false;
 };
 
 }  // namespace rife
@@ -110,6 +113,9 @@ using namespace rife;
 struct rife_weights {
   int device = 0;
   int precision = RIFE_PRECISION_FP32;
+  bool force_nhwc = false;  // test hook: never pick the halo kernel
+  bool head_hk = false;     // Head / block i run on the halo kernel with planar-8 activations
+  bool blk_hk[5] = {false, false, false, false, false};
   std::vector<void*> allocs;
   DevLayer head[4];
   struct Block {
@@ -145,6 +151,17 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool p
     d->h16.w = (const __half*)ph;
     d->h16.bias = (const float*)phb;
     d->h16.beta = (const float*)phbeta;
+    if (!w->force_nhwc && halo_fits(h, ps_layout)) {
+      void *pk = nullptr, *pkb = nullptr, *pkbeta = nullptr;
+      RIFE_TRY(halo_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->hk));
+      RIFE_TRY(upload(w, packed.data(), packed.size() * sizeof(__half), &pk));
+      RIFE_TRY(upload(w, hb.data(), hb.size() * 4, &pkb));
+      if (!hbeta.empty()) RIFE_TRY(upload(w, hbeta.data(), hbeta.size() * 4, &pkbeta));
+      d->hk.w = (const __half*)pk;
+      d->hk.bias = (const float*)pkb;
+      d->hk.beta = (const float*)pkbeta;
+      d->use_hk = true;
+    }
   }
   return RIFE_OK;
 }
@@ -216,7 +233,11 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
       if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
     }
     if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last, /*ps_layout=*/true))) return fail(st);
+    bool all = B.conv00.use_hk && B.conv01.use_hk && B.last.use_hk;
+    for (int j = 0; j < 8; ++j) all = all && B.res[j].use_hk;
+    w->blk_hk[i] = all;
   }
+  w->head_hk = w->head[0].use_hk && w->head[1].use_hk && w->head[2].use_hk && w->head[3].use_hk;
   *out = w;
   return RIFE_OK;
 }
@@ -408,8 +429,8 @@ int rife_plan_get_profile(rife_plan* p, const char** names, float* ms, int cap) 
 
 // --------------------------------------------------------------------------------------------------
 // pipeline
-static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, cudaStream_t st) {
-  if (p->precision == RIFE_PRECISION_FP16) return launch_conv_umma(L.h16, io, st);
+static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
+  if (p->precision == RIFE_PRECISION_FP16) return hk ? launch_conv_halo(L.hk, io, st) : launch_conv_umma(L.h16, io, st);
   return launch_conv_f32(L.f32, io, st);
 }
 
@@ -437,6 +458,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.src0 = p->at(L.src);
   c.src1 = (char*)p->at(L.src) + N * SRC_C * E;
   c.half_act = half_act;
+  c.planar_head = half_act && w->head_hk;
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
   p->n_stage = 0;
@@ -445,13 +467,13 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     ConvIO io;
     io.B = 2 * B; io.H = H / 2; io.W = W / 2;
     io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;
-    RIFE_STAGE("head.cnn0", run_conv(p, w->head[0], io, st));
+    RIFE_STAGE("head.cnn0", run_conv(p, w->head[0], io, c.planar_head, st));
     io.in = p->at(L.head_a); io.out = p->at(L.head_b);
-    RIFE_STAGE("head.cnn1", run_conv(p, w->head[1], io, st));
+    RIFE_STAGE("head.cnn1", run_conv(p, w->head[1], io, c.planar_head, st));
     io.in = p->at(L.head_b); io.out = p->at(L.head_a);
-    RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, st));
+    RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, c.planar_head, st));
     io.in = p->at(L.head_a); io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
-    RIFE_STAGE("head.cnn3", run_conv(p, w->head[3], io, st));
+    RIFE_STAGE("head.cnn3", run_conv(p, w->head[3], io, c.planar_head, st));
   }
 
   // ---- 5 IFBlocks (IFNet_HDv3.py:139-157)
@@ -460,25 +482,26 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     const int s = L.s[i], c_ = kBlockC[i];
     const int hs = H / s, wsz = W / s;
     const std::string bn = "b" + std::to_string(i);
-    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), st));
+    const bool hk = half_act && w->blk_hk[i];
+    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, st));
     ConvIO io;
     io.B = B;
     // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
     io.H = hs / 2; io.W = wsz / 2; io.in = p->at(L.xin); io.out = p->at(L.c0); io.epi = EPI_LRELU_S2D; io.out_c = c_ / 2;
-    RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, st));
+    RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, hk, st));
     // conv0.1: stride 2 on (hs/2, wsz/2) == 2x2 taps on (hs/4, wsz/4)
     io.H = hs / 4; io.W = wsz / 4; io.in = p->at(L.c0); io.out = p->at(L.act_a); io.epi = EPI_LRELU; io.out_c = c_;
-    RIFE_STAGE(bn + ".conv0.1", run_conv(p, w->blk[i].conv01, io, st));
+    RIFE_STAGE(bn + ".conv0.1", run_conv(p, w->blk[i].conv01, io, hk, st));
     void* cur = p->at(L.act_a);
     void* nxt = p->at(L.act_b);
     for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
       io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
-      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, st));
+      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk, st));
       void* t = cur; cur = nxt; nxt = t;
     }
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
     io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
-    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, st));
+    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk, st));
     lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = s;
 
     EvalOut eo;
@@ -562,6 +585,8 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
                            const float* residual_nchw, float* y_nchw, int epi, int out_c_store, int cpp, int out_C,
                            int out_H, int out_W, int out_Cpad, cudaStream_t st) {
   rife_weights tmpw;
+  tmpw.force_nhwc = precision == 3;  // test hook: RIFE_PRECISION_FP16 through the NHWC tcgen05 kernel only
+  if (precision == 3) precision = RIFE_PRECISION_FP16;
   tmpw.precision = precision;
   cudaGetDevice(&tmpw.device);
   DevLayer d;
@@ -596,7 +621,8 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
   io.B = B; io.H = gh; io.W = gw; io.in = xin; io.res = res; io.out = yout; io.epi = epi; io.out_c = out_c_store;
   io.co_per_par = cpp;
   if (precision == RIFE_PRECISION_FP16) {
-    RIFE_SC(launch_conv_umma_f32io(d.h16, io, st));
+    if (d.use_hk) RIFE_SC(launch_conv_halo_f32io(d.hk, io, st));
+    else RIFE_SC(launch_conv_umma_f32io(d.h16, io, st));
   } else {
     RIFE_SC(launch_conv_f32(d.f32, io, st));
   }

@@ -18,6 +18,7 @@ extern std::atomic<uint64_t> g_launch_count;
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
     if (_e != cudaSuccess) {                                                                  \
+      cudaGetLastError(); /* clear the sticky last-error so later launches are not blamed */   \
       rife::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
                       std::to_string(__LINE__) + ")");                                        \
       return RIFE_ERR_CUDA;                                                                   \
@@ -159,13 +160,15 @@ struct PixelCtx {
   const void* src0;    // [B][H][W][SRC_C]
   const void* src1;
   bool half_act;       // activation / src / tmp storage type: false = float, true = __half
+  bool planar_head = false;  // Head input stored planar-8 (conv_halo.cu) instead of pixel-major
 };
 
 // NCHW image (io dtype) -> SRC tensor channels 4..7 (+ zeros in 0..3) and the s2d Head input [2B][H/2][W/2][16]
 int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
                 void* head_in, cudaStream_t st);
 // builds the s2d block input of block `level` from the lazily-accumulated tmp levels [0, level)
-int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, cudaStream_t st);
+int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
+                       cudaStream_t st);
 // evaluates flow / mask / warped images / merged at full resolution after `nlev` blocks
 struct EvalOut {
   void* flow = nullptr;     // (B,4,H,W)

@@ -1,0 +1,566 @@
+// Persistent halo-tile tcgen05 convolution for the thin layers (C <= 64: Head, IFBlock 3 and 4 -- 75% of the
+// network's FLOPs and nearly all of its conv bytes; train_log/IFNet_HDv3.py:24-43, 57-76).
+//
+// Why a second conv kernel: with C <= 64 the per-tap operand tiles are tiny, so a kernel that re-loads the
+// activation tile once per tap (conv_umma.cu) moves 9x the activation bytes L2->SM and exposes a TMA->MMA->epilogue
+// latency chain per 128-pixel tile.  Here
+//   * activations live in HBM as [B][C/8][H][W][8] fp16 ("planar-8"); ONE TMA box {(TW+R)*8, TH+R, C/8, 1} brings
+//     the whole (TH+R) x (TW+R) halo of a 16 x 8 pixel tile into smem as C/8 planes of [rows][cols][8ch];
+//   * that layout is exactly the tcgen05 no-swizzle K-major canonical layout when the tile is 8 pixels wide
+//     (8 consecutive pixels = one 8x16B core matrix, SBO = halo row pitch, LBO = plane pitch), so every tap of the
+//     3x3 / 2x2 stencil is the SAME smem tile read through a descriptor whose start address is shifted by
+//     (dy * pitch + dx) * 16 bytes -- no im2col, no re-load;
+//   * the layer's weights stay resident in smem for the CTA's lifetime; CTAs are persistent (one or two per SM)
+//     and walk tiles with a TMA ring several tiles deep and two TMEM accumulator buffers, so the epilogue of tile
+//     i overlaps the MMAs of tile i+1 and the loads of tiles i+2..;
+//   * ConvTranspose2d(4,2,1)+PixelShuffle (lastconv) runs as 4 output parities x 4 taps (16 MMAs groups of N=64)
+//     instead of 9 dense taps of N=208/256.
+#include <cuda.h>
+
+#include "conv_halo.cuh"
+
+namespace rife {
+namespace {
+
+constexpr int TW = 8, TH = 16;  // tile: 16 rows x 8 pixels = 128 GEMM rows, row m = ty*8 + tx
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_ENTRIES = 16;
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+struct HaloParams {
+  int B, H, W, tiles_x, tiles_y, ntiles;
+  int kgroups, ksteps, R;
+  int plane_bytes, a_stage_bytes, a_tx_bytes, stages;
+  int nentries, ne, ncols, tmem_cols, n_valid, w_bytes, wtile_bytes;
+  int epi, out_c, cpp;
+  const __half* w;
+  const float* bias;
+  const float* beta;
+  const __half* res;
+  __half* out;
+  signed char e_dy[MAX_ENTRIES], e_dx[MAX_ENTRIES];
+  unsigned char e_col16[MAX_ENTRIES], e_first[MAX_ENTRIES];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();  // a mis-programmed pipeline traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// no-swizzle K-major descriptor: 8 rows x 16 B core matrices; LBO = byte stride between the two 8-element K chunks
+// of one MMA, SBO = byte stride between consecutive 8-row groups
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout type 0 = SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = v[i];
+  st8(dst, a);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
+  st8(dst + 8, a);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ __align__(8) uint64_t t_full[2];
+  __shared__ __align__(8) uint64_t t_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = w_smem + (((uint32_t)p.w_bytes + 1023u) & ~1023u);
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&w_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&t_full[i]), 1);
+      mbar_init(smem_u32(&t_empty[i]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int pitch = TW + p.R;  // halo row pitch in pixels
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: resident weights once, then one halo box per tile
+      const uint32_t wb = smem_u32(&w_full);
+      mbar_expect_tx(wb, (uint32_t)p.w_bytes);
+      for (int off = 0; off < p.w_bytes; off += 32768) {
+        const int n = min(32768, p.w_bytes - off);
+        bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wb);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x;
+        const int r = tile / p.tiles_x;
+        const int ty = r % p.tiles_y, b = r / p.tiles_y;
+        mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&a_full[stage]);
+        mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
+        tma_load_4d(a_smem + stage * p.a_stage_bytes, &tm_a, fb, (tx * TW - 1) * 8, ty * TH - 1, 0, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ne >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)p.plane_bytes, a_sbo = (uint32_t)pitch * 16u;
+      const uint32_t b_lbo = (uint32_t)p.ne * 16u, b_sbo = 128u;
+      mbar_wait(smem_u32(&w_full), 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_wait(smem_u32(&a_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = a_smem + stage * p.a_stage_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.ncols);
+        for (int e = 0; e < p.nentries; ++e) {
+          const uint32_t a_off = (uint32_t)(((p.e_dy[e] + 1) * pitch + (p.e_dx[e] + 1)) * 16);
+          const uint32_t wa = w_smem + (uint32_t)(e * p.wtile_bytes);
+          const uint32_t d_col = acc + (uint32_t)p.e_col16[e] * 16u;
+          for (int kk = 0; kk < p.ksteps; ++kk) {
+            const uint64_t da = make_desc_noswz(sa + (uint32_t)(2 * kk) * a_lbo + a_off, a_lbo, a_sbo);
+            const uint64_t db = make_desc_noswz(wa + (uint32_t)(2 * kk) * b_lbo, b_lbo, b_sbo);
+            umma_f16(d_col, da, db, idesc, (p.e_first[e] && kk == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(smem_u32(&a_empty[stage]));
+        umma_commit(smem_u32(&t_full[buf]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: TMEM lanes 32*(warp%4)..+31
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty_ = m >> 3, tx_ = m & 7;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nchunk16 = p.ncols >> 4;
+    const size_t plane = (size_t)p.H * p.W * 8;  // elements per planar-8 channel group
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int tx = tile % p.tiles_x;
+      const int r = tile / p.tiles_x;
+      const int ty = r % p.tiles_y, b = r / p.tiles_y;
+      const int y = ty * TH + ty_, x = tx * TW + tx_;
+      const bool valid = (y < p.H) && (x < p.W);
+      const int buf = it & 1;
+      mbar_wait(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      for (int j = 0; j < nchunk16; ++j) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(trow + (uint32_t)(buf * p.ncols + j * 16), v);
+        if (!valid) continue;
+        const int n0 = j * 16;
+        {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(bp + i);
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+          }
+        }
+        switch (p.epi) {
+          case EPI_LRELU:
+          case EPI_LINEAR:
+          case EPI_LRELU_S2D: {
+            if (p.epi != EPI_LINEAR) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
+            }
+            if (n0 >= p.n_valid) break;
+            __half* dst;
+            size_t pl;
+            if (p.epi == EPI_LRELU_S2D) {
+              // planar-8 on the half-resolution s2d grid, channel = par*out_c + n
+              const int H2 = p.H >> 1, W2 = p.W >> 1;
+              const int G = (4 * p.out_c) >> 3, g = (((y & 1) * 2 + (x & 1)) * p.out_c + n0) >> 3;
+              pl = (size_t)H2 * W2 * 8;
+              dst = p.out + ((size_t)b * G + g) * pl + ((size_t)(y >> 1) * W2 + (x >> 1)) * 8;
+            } else {
+              const int G = p.out_c >> 3;
+              pl = plane;
+              dst = p.out + ((size_t)b * G + (n0 >> 3)) * pl + ((size_t)y * p.W + x) * 8;
+            }
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = v[i];
+            st8(dst, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
+            st8(dst + pl, a);
+          } break;
+          case EPI_RES: {
+            const int G = p.out_c >> 3;
+            const size_t o = ((size_t)b * G + (n0 >> 3)) * plane + ((size_t)y * p.W + x) * 8;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float rr[8], a[8];
+              ld8(p.res + o + h * plane, rr);
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h + 4));
+              const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
+              st8(p.out + o + h * plane, a);
+            }
+          } break;
+          case EPI_PS: {
+            const int par = j >> 2, sub = j & 3;
+            const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * x + 2 * (par & 1) + (sub & 1);
+            store16h(p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
+          } break;
+          case EPI_HEADT: {
+#pragma unroll
+            for (int par = 0; par < 4; ++par) {
+              const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+              float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
+              st4(p.out + (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
+            }
+          } break;
+          case EPI_CONVT: {
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + i;
+              if (n >= p.n_valid) break;
+              const int par = n / p.cpp, co = n - par * p.cpp;
+              const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+              p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
+            }
+          } break;
+          default: break;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&t_empty[buf]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------- layout converters (tests)
+__global__ void nhwc_f32_to_planar8_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * H * W * C) return;
+  const int c = (int)(i % C);
+  const size_t pix = i / C;
+  const size_t hw = (size_t)H * W;
+  const size_t b = pix / hw, p = pix % hw;
+  y[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)] = __float2half_rn(x[i]);
+}
+__global__ void planar8_to_nhwc_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * H * W * C) return;
+  const int c = (int)(i % C);
+  const size_t pix = i / C;
+  const size_t hw = (size_t)H * W;
+  const size_t b = pix / hw, p = pix % hw;
+  y[i] = __half2float(x[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)]);
+}
+__global__ void f16_to_f32_k(const __half* __restrict__ x, float* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __half2float(x[i]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+bool halo_fits(const HostLayer& h, bool ps_layout) {
+  if (h.cin % 16 || h.cin > 128) return false;
+  const int R = h.kind == CONV_3x3 ? 2 : 1;
+  const int a_stage = (h.cin / 8) * (TH + R) * (TW + R) * 16;
+  const int w_bytes = ps_layout ? 16 * (h.cin / 8) * 64 * 16 : h.taps * (h.cin / 8) * h.npad * 16;
+  if (!ps_layout && h.npad > 128) return false;
+  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET;
+}
+
+int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
+                      std::vector<float>* beta, HaloLayer* L) {
+  if (!halo_fits(h, ps_layout)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "halo_pack_weights: layer does not fit the halo kernel");
+  const int kg = h.cin / 8;
+  *L = HaloLayer();
+  L->kind = h.kind; L->cin = h.cin;
+  beta->clear();
+  if (ps_layout) {
+    if (h.convt_co != 52 || h.kind != CONV_3x3) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "halo_pack_weights: PS layout is the 52-channel lastconv");
+    L->nentries = 16; L->ne = 64; L->ncols = 256; L->n_valid = 256; L->ps_cols = 1;
+    packed->assign((size_t)16 * kg * 64 * 8, __float2half_rn(0.f));
+    bias->assign(256, 0.f);
+    int e = 0;
+    for (int par = 0; par < 4; ++par) {
+      const int py = par >> 1, px = par & 1;
+      for (int sub = 0; sub < 4; ++sub)
+        for (int k = 0; k < 13; ++k) (*bias)[par * 64 + sub * 16 + k] = h.bias[par * 52 + 4 * k + sub];
+      for (int dyi = 0; dyi < 2; ++dyi)
+        for (int dxi = 0; dxi < 2; ++dxi, ++e) {
+          const int dy = py ? dyi : dyi - 1, dx = px ? dxi : dxi - 1;  // taps that feed this output parity
+          const int t = (dy + 1) * 3 + (dx + 1);
+          L->e_dy[e] = (signed char)dy; L->e_dx[e] = (signed char)dx;
+          L->e_col16[e] = (unsigned char)(par * 4);
+          L->e_first[e] = (dyi == 0 && dxi == 0) ? 1 : 0;
+          for (int g = 0; g < kg; ++g)
+            for (int sub = 0; sub < 4; ++sub)
+              for (int k = 0; k < 13; ++k) {
+                const int n = sub * 16 + k, on = par * 52 + 4 * k + sub;
+                for (int c = 0; c < 8; ++c)
+                  (*packed)[(((size_t)e * kg + g) * 64 + n) * 8 + c] =
+                      __float2half_rn(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + on]);
+              }
+        }
+    }
+  } else {
+    L->nentries = h.taps; L->ne = h.npad; L->ncols = h.npad; L->n_valid = h.n;
+    packed->assign((size_t)h.taps * kg * h.npad * 8, __float2half_rn(0.f));
+    bias->assign(h.bias.begin(), h.bias.end());
+    if (!h.beta.empty()) beta->assign(h.beta.begin(), h.beta.end());
+    const int side = h.kind == CONV_3x3 ? 3 : 2;
+    for (int t = 0; t < h.taps; ++t) {
+      L->e_dy[t] = (signed char)(t / side - 1); L->e_dx[t] = (signed char)(t % side - 1);
+      L->e_col16[t] = 0; L->e_first[t] = t == 0;
+      for (int g = 0; g < kg; ++g)
+        for (int n = 0; n < h.npad; ++n)
+          for (int c = 0; c < 8; ++c)
+            (*packed)[(((size_t)t * kg + g) * h.npad + n) * 8 + c] =
+                __float2half_rn(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + n]);
+    }
+  }
+  L->w_bytes = (int)(packed->size() * sizeof(__half));
+  return RIFE_OK;
+}
+
+int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
+  if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES needs beta and res");
+  if (io.epi == EPI_HEADT && L.ncols != 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_HEADT expects N = 16");
+  HaloParams p{};
+  p.B = io.B; p.H = io.H; p.W = io.W;
+  p.tiles_x = (io.W + TW - 1) / TW;
+  p.tiles_y = (io.H + TH - 1) / TH;
+  p.ntiles = p.tiles_x * p.tiles_y * io.B;
+  p.kgroups = L.cin / 8; p.ksteps = L.cin / 16;
+  p.R = L.kind == CONV_3x3 ? 2 : 1;
+  p.plane_bytes = (TH + p.R) * (TW + p.R) * 16;
+  p.a_tx_bytes = p.kgroups * p.plane_bytes;
+  p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
+  p.nentries = L.nentries; p.ne = L.ne; p.ncols = L.ncols; p.n_valid = L.n_valid;
+  p.w_bytes = L.w_bytes;
+  p.wtile_bytes = p.kgroups * L.ne * 16;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * L.ncols) p.tmem_cols <<= 1;
+  const int w_al = (L.w_bytes + 1023) / 1024 * 1024;
+  int stages = (SMEM_BUDGET - w_al - 2048) / p.a_stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
+  int smem = w_al + stages * p.a_stage_bytes + 1024;
+  // two co-resident CTAs per SM hide the per-tile latency chain of very thin layers when smem and TMEM allow
+  int per_sm = 1;
+  if (2 * p.tmem_cols <= 512) {
+    int s2 = stages;
+    while (s2 > 3 && 2 * (w_al + s2 * p.a_stage_bytes + 2048) > 224 * 1024) --s2;
+    if (2 * (w_al + s2 * p.a_stage_bytes + 2048) <= 224 * 1024) {
+      per_sm = 2;
+      stages = s2;
+      smem = w_al + stages * p.a_stage_bytes + 1024;
+    }
+  }
+  p.stages = stages;
+  p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par;
+  p.w = L.w; p.bias = L.bias; p.beta = L.beta;
+  p.res = (const __half*)io.res; p.out = (__half*)io.out;
+  for (int e = 0; e < L.nentries; ++e) {
+    p.e_dy[e] = L.e_dy[e]; p.e_dx[e] = L.e_dx[e]; p.e_col16[e] = L.e_col16[e]; p.e_first[e] = L.e_first[e];
+  }
+  CUtensorMap tm_a;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)io.W * 8, (cuuint64_t)io.H, (cuuint64_t)p.kgroups, (cuuint64_t)io.B};
+    cuuint64_t strides[3] = {(cuuint64_t)io.W * 16, (cuuint64_t)io.H * io.W * 16, (cuuint64_t)p.kgroups * io.H * io.W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)((TW + p.R) * 8), (cuuint32_t)(TH + p.R), (cuuint32_t)p.kgroups, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(io.in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed: " + std::to_string((int)r));
+  }
+  {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+      RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr_set[dev] = true;
+    }
+  }
+  int grid = num_sms() * per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  conv_halo_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
+  // NHWC fp32 in (cin channels) -> planar-8 fp16; planar / pixel-major fp16 out -> NHWC fp32
+  const size_t nin = (size_t)io.B * io.H * io.W * L.cin;
+  size_t nout = 0;
+  bool planar_out = false;
+  int oh = io.H, ow = io.W, oc = io.out_c;
+  switch (io.epi) {
+    case EPI_PS: nout = (size_t)io.B * 16 * io.H * io.W * TMP_C; break;
+    case EPI_HEADT:
+    case EPI_CONVT: nout = (size_t)io.B * 4 * io.H * io.W * io.out_c; break;
+    case EPI_LRELU_S2D: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo_f32io: s2d store is pipeline-only");
+    default: nout = (size_t)io.B * io.H * io.W * io.out_c; planar_out = true; break;
+  }
+  const size_t nres = io.res ? (size_t)io.B * io.H * io.W * io.out_c : 0;
+  __half *hin = nullptr, *hout = nullptr, *hres = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    cudaFree(hin); cudaFree(hout); cudaFree(hres);
+  };
+  cudaError_t e = cudaMalloc((void**)&hin, nin * 2);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&hout, nout * 2);
+  if (e == cudaSuccess && nres) e = cudaMalloc((void**)&hres, nres * 2);
+  if (e == cudaSuccess) e = cudaMemsetAsync(hout, 0, nout * 2, st);
+  if (e != cudaSuccess) {
+    cleanup();
+    RIFE_FAIL(RIFE_ERR_CUDA, std::string("conv_halo_f32io: ") + cudaGetErrorString(e));
+  }
+  nhwc_f32_to_planar8_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, io.B, io.H, io.W, L.cin);
+  if (nres)
+    nhwc_f32_to_planar8_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, io.B, io.H, io.W, io.out_c);
+  ConvIO h = io;
+  h.in = hin; h.res = hres; h.out = hout;
+  int rc = launch_conv_halo(L, h, st);
+  if (rc == RIFE_OK) {
+    if (planar_out)
+      planar8_to_nhwc_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, io.B, oh, ow, oc);
+    else
+      f16_to_f32_k<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, nout);
+    if (cudaGetLastError() != cudaSuccess) rc = RIFE_ERR_CUDA;
+  }
+  cleanup();
+  return rc;
+}
+
+}  // namespace rife

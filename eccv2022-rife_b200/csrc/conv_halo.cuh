@@ -1,0 +1,33 @@
+// Persistent halo-tile tcgen05 convolution (thin layers, planar-8 activations) -- interface.  See conv_halo.cu.
+#pragma once
+#include <vector>
+
+#include "conv_umma.cuh"
+
+namespace rife {
+
+struct HaloLayer {
+  const __half* w = nullptr;    // smem image: [entry][cin/8][ne][8] fp16 (no-swizzle K-major B tiles)
+  const float* bias = nullptr;  // [ncols]
+  const float* beta = nullptr;  // [ncols] or null
+  int kind = CONV_3x3;
+  int cin = 0;        // multiple of 16, <= 128
+  int nentries = 0;   // MMA schedule: taps (9 / 4) or ConvTranspose (parity, tap) pairs (16)
+  int ne = 0;         // GEMM N of each MMA
+  int ncols = 0;      // accumulator columns per tile (ne, or 4 * 64 for the parity schedule)
+  int n_valid = 0;
+  int w_bytes = 0;
+  int ps_cols = 0;
+  signed char e_dy[16] = {}, e_dx[16] = {};
+  unsigned char e_col16[16] = {}, e_first[16] = {};
+};
+
+bool halo_fits(const HostLayer& h, bool ps_layout);
+int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
+                      std::vector<float>* beta, HaloLayer* L);
+// planar-8 fp16 activations [B][C/8][H][W][8] in; planar-8 (LRELU / LINEAR / RES / LRELU_S2D) or pixel-major
+// (PS / HEADT / CONVT) fp16 out
+int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st);
+int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st);
+
+}  // namespace rife

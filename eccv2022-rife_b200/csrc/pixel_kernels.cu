@@ -154,7 +154,8 @@ __device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int b, 
 template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                    T* __restrict__ src0, T* __restrict__ src1,
-                                                   T* __restrict__ head_in, int B, int C, int H, int W) {
+                                                   T* __restrict__ head_in, int B, int C, int H, int W,
+                                                   int planar) {
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)B * H2 * W2;
@@ -184,14 +185,17 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
       for (int c = 0; c < 3; ++c) hv[(py * 2 + px) * 3 + c] = v[4 + c];
     }
   }
-  T* hp = head_in + ((((size_t)frame * B + b) * H2 + y2) * W2 + x2) * 16;
+  // pixel-major [2B][H/2][W/2][16] or planar-8 [2B][2][H/2][W/2][8] (conv_halo.cu)
+  T* hp = planar ? head_in + ((((size_t)frame * B + b) * 2 * H2 + y2) * W2 + x2) * 8
+                 : head_in + ((((size_t)frame * B + b) * H2 + y2) * W2 + x2) * 16;
+  const size_t gstride = planar ? (size_t)H2 * W2 * 8 : 8;
   float a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = hv[i];
   st8(hp, a);
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = hv[8 + i];
-  st8(hp + 8, a);
+  st8(hp + gstride, a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
                                                           const T* __restrict__ src1, const float* __restrict__ gridx,
                                                           const float* __restrict__ gridy,
                                                           const float* __restrict__ tstep, T* __restrict__ xin, int B,
-                                                          int H, int W, WarpGeom geom) {
+                                                          int H, int W, WarpGeom geom, int planar) {
   const int Hs = H / s, Ws = W / s;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * Hs * Ws) return;
@@ -272,20 +276,24 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
   const float inv_s = 1.f / (float)s;
 #pragma unroll
   for (int i = 24; i < 28; ++i) acc[i] = acc[i] * inv_s;
-  // s2d store: [b][Y/2][X/2][(py*2+px)*32 + c]
-  T* dst = xin + ((((size_t)b * (Hs >> 1) + (Y >> 1)) * (Ws >> 1) + (X >> 1)) * 4 + ((Y & 1) * 2 + (X & 1))) * XIN_C;
+  // s2d store, channel = (py*2+px)*32 + c: pixel-major [b][Y/2][X/2][128] or planar-8 [b][16][Y/2][X/2][8]
+  const int par = (Y & 1) * 2 + (X & 1);
+  const size_t hw2 = (size_t)(Hs >> 1) * (Ws >> 1), pix2 = (size_t)(Y >> 1) * (Ws >> 1) + (X >> 1);
+  T* dst = planar ? xin + (((size_t)b * 16 + par * 4) * hw2 + pix2) * 8
+                  : xin + (((size_t)b * hw2 + pix2) * 4 + par) * XIN_C;
+  const size_t gstride = planar ? hw2 * 8 : 8;
   float o[8];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = acc[k * 8 + i];
-    st8(dst + k * 8, o);
+    st8(dst + k * gstride, o);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i] = acc[24 + i];
 #pragma unroll
   for (int i = 4; i < 8; ++i) o[i] = 0.f;
-  st8(dst + 24, o);
+  st8(dst + 3 * gstride, o);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -437,7 +445,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   dim3 grid(nblk(nq, 256), 2);
 #define RIFE_PREP(TIO, T)                                                                                        \
   prep_kernel<TIO, T><<<grid, 256, 0, st>>>((const TIO*)img0, (const TIO*)img1, (T*)src0, (T*)src1, (T*)head_in, \
-                                            c.B, c.C, c.H, c.W)
+                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0)
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
@@ -459,18 +467,19 @@ static LevelsArg pack_levels(const TmpLevel* levels, int n) {
   return L;
 }
 
-int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, cudaStream_t st) {
+int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
+                       cudaStream_t st) {
   const size_t n = (size_t)c.B * (c.H / s) * (c.W / s);
   LevelsArg L = pack_levels(levels, level);
   WarpGeom g = make_geom(c.H, c.W);
   if (c.half_act)
     block_input_kernel<__half, __half><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const __half*)c.src0,
                                                                       (const __half*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                      (__half*)xin, c.B, c.H, c.W, g);
+                                                                      (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
   else
     block_input_kernel<float, float><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const float*)c.src0,
                                                                     (const float*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                    (float*)xin, c.B, c.H, c.W, g);
+                                                                    (float*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }

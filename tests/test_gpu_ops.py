@@ -120,31 +120,33 @@ def _h(a):
                                               (96, 96, 20, 36, 1), (128, 128, 12, 20, 1), (192, 192, 9, 15, 1),
                                               (28, 16, 32, 48, 2), (15, 96, 16, 16, 2), (3, 16, 32, 32, 2),
                                               (64, 128, 16, 32, 2), (32, 64, 8, 8, 2), (16, 32, 64, 96, 2)])
-def test_conv3x3_fp16_tcgen05(pkg, ci, co, h, w, stride):
+@pytest.mark.parametrize("prec", [1, 3])   # 1 = pipeline policy (halo kernel when the layer fits), 3 = NHWC kernel only
+def test_conv3x3_fp16_tcgen05(pkg, ci, co, h, w, stride, prec):
     rng = np.random.default_rng(ci * 7 + co)
     x = _h(rng.standard_normal((2, ci, h, w)).astype(np.float32))
     wt = _h((rng.standard_normal((co, ci, 3, 3)) / np.sqrt(9 * ci)).astype(np.float32))
     b = rng.standard_normal(co).astype(np.float32)
-    y = _conv(pkg, x, wt, b, stride, 1, precision=1)
+    y = _conv(pkg, x, wt, b, stride, 1, precision=prec)
     ref = O.leaky_relu(O.conv2d(x, wt, b, stride, 1))
     assert y.shape == ref.shape
     assert np.abs(y - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))   # fp16 output rounding (2^-11 relative)
 
 
-def test_resconv_fp16_tcgen05(pkg):
+@pytest.mark.parametrize("prec,c", [(1, 64), (3, 64), (1, 32), (1, 96)])
+def test_resconv_fp16_tcgen05(pkg, prec, c):
     rng = np.random.default_rng(5)
-    c = 64
     x = _h(rng.standard_normal((1, c, 20, 28)).astype(np.float32))
     wt = _h((rng.standard_normal((c, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
     b = rng.standard_normal(c).astype(np.float32)
     beta = rng.standard_normal(c).astype(np.float32)
-    y = _conv(pkg, x, wt, b, 1, 1, beta=beta, res=x, precision=1)
+    y = _conv(pkg, x, wt, b, 1, 1, beta=beta, res=x, precision=prec)
     ref = O.leaky_relu(O.conv2d(x, wt, b, 1, 1) * beta[None, :, None, None] + x)
     assert np.abs(y - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("prec", [1, 3])
 @pytest.mark.parametrize("ci,co,ps", [(32, 52, 1), (16, 4, 0), (192, 52, 1), (64, 52, 1)])
-def test_conv_transpose_fp16_tcgen05(pkg, ci, co, ps):
+def test_conv_transpose_fp16_tcgen05(pkg, ci, co, ps, prec):
     lib = pkg._lib.load()
     rng = np.random.default_rng(ci + co)
     x = _h(rng.standard_normal((2, ci, 10, 14)).astype(np.float32))
@@ -154,7 +156,7 @@ def test_conv_transpose_fp16_tcgen05(pkg, ci, co, ps):
     shape = (2, co // 4, 40, 56) if ps else (2, co, 20, 28)
     y = torch.empty(shape, device=DEV)
     pkg._lib.check(lib.rife_conv_transpose4x4s2(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 2, ci, 10, 14,
-                                                co, ps, 1, _stream()))
+                                                co, ps, prec, _stream()))
     ref = O.conv_transpose2d_k4s2p1(x, wt, b)
     if ps:
         ref = O.pixel_shuffle2(ref)
