@@ -16,13 +16,15 @@
 //   * ConvTranspose2d(4,2,1)+PixelShuffle (lastconv) runs as 4 output parities x 4 taps (16 MMAs groups of N=64)
 //     instead of 9 dense taps of N=208/256.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "conv_halo.cuh"
 
 namespace rife {
 namespace {
 
-constexpr int TW = 8, TH = 16;  // tile: 16 rows x 8 pixels = 128 GEMM rows, row m = ty*8 + tx
+constexpr int TW = 8, TH = 16;  // M-tile: 16 rows x 8 pixels = 128 GEMM rows, row m = ty*8 + tx
+constexpr int MAX_MMA = 128;    // (schedule entries) x (K steps) per M-tile
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ENTRIES = 16;
@@ -30,7 +32,7 @@ constexpr int SMEM_BUDGET = 220 * 1024;
 
 struct HaloParams {
   int B, H, W, tiles_x, tiles_y, ntiles;
-  int kgroups, ksteps, R;
+  int kgroups, ksteps, R, mt;  // mt = vertically stacked M-tiles per pipeline step (they share one halo load)
   int plane_bytes, a_stage_bytes, a_tx_bytes, stages;
   int nentries, ne, ncols, tmem_cols, n_valid, w_bytes, wtile_bytes;
   int epi, out_c, cpp;
@@ -134,6 +136,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
   __shared__ __align__(8) uint64_t t_full[2];
   __shared__ __align__(8) uint64_t t_empty[2];
   __shared__ uint32_t tmem_slot;
+  // per-MMA operand tables, built once: the issuing thread then spends ~5 instructions per tcgen05.mma
+  __shared__ __align__(8) uint64_t tab_b[MAX_MMA];  // complete B (weights) descriptor
+  __shared__ uint32_t tab_a[MAX_MMA];               // A start-address field relative to the stage base (16-byte units)
+  __shared__ uint32_t tab_d[MAX_MMA];               // accumulator column offset | (accumulate << 31)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,7 +149,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&a_full[s]), 1);
-      mbar_init(smem_u32(&a_empty[s]), 1);
+      // ResConv epilogues read the residual (= centre tap of the input tile) from the smem stage itself, so the
+      // stage is released by the MMA commit AND the four epilogue warps
+      mbar_init(smem_u32(&a_empty[s]), p.epi == EPI_RES ? 5 : 1);
     }
     mbar_init(smem_u32(&w_full), 1);
     for (int i = 0; i < 2; ++i) {
@@ -158,11 +166,21 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 1) {
+    const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)p.ne * 16u, 128u);
+    for (int i = lane; i < p.nentries * p.ksteps; i += 32) {
+      const int e = i / p.ksteps, kk = i - e * p.ksteps;
+      tab_a[i] = (uint32_t)((2 * kk) * (p.plane_bytes >> 4) + (p.e_dy[e] + 1) * (TW + p.R) + (p.e_dx[e] + 1));
+      tab_b[i] = b_desc0 + (uint64_t)((w_smem + (uint32_t)(e * p.wtile_bytes) + (uint32_t)(2 * kk * p.ne * 16)) >> 4);
+      tab_d[i] = (uint32_t)p.e_col16[e] * 16u | ((p.e_first[e] && kk == 0) ? 0u : 0x80000000u);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const int pitch = TW + p.R;  // halo row pitch in pixels
+  const int n_mma = p.nentries * p.ksteps;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&a_full[stage]);
         mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
-        tma_load_4d(a_smem + stage * p.a_stage_bytes, &tm_a, fb, (tx * TW - 1) * 8, ty * TH - 1, 0, b);
+        tma_load_4d(a_smem + stage * p.a_stage_bytes, &tm_a, fb, (tx * TW - 1) * 8, ty * TH * p.mt - 1, 0, b);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -190,8 +208,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- MMA issuer
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ne >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)p.plane_bytes, a_sbo = (uint32_t)pitch * 16u;
-      const uint32_t b_lbo = (uint32_t)p.ne * 16u, b_sbo = 128u;
+      const uint64_t a_desc0 = make_desc_noswz(0, (uint32_t)p.plane_bytes, (uint32_t)pitch * 16u);
+      const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
       mbar_wait(smem_u32(&w_full), 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -200,16 +218,14 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         mbar_wait(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         mbar_wait(smem_u32(&a_full[stage]), phase);
         tc_fence_after();
-        const uint32_t sa = a_smem + stage * p.a_stage_bytes;
-        const uint32_t acc = tmem_base + (uint32_t)(buf * p.ncols);
-        for (int e = 0; e < p.nentries; ++e) {
-          const uint32_t a_off = (uint32_t)(((p.e_dy[e] + 1) * pitch + (p.e_dx[e] + 1)) * 16);
-          const uint32_t wa = w_smem + (uint32_t)(e * p.wtile_bytes);
-          const uint32_t d_col = acc + (uint32_t)p.e_col16[e] * 16u;
-          for (int kk = 0; kk < p.ksteps; ++kk) {
-            const uint64_t da = make_desc_noswz(sa + (uint32_t)(2 * kk) * a_lbo + a_off, a_lbo, a_sbo);
-            const uint64_t db = make_desc_noswz(wa + (uint32_t)(2 * kk) * b_lbo, b_lbo, b_sbo);
-            umma_f16(d_col, da, db, idesc, (p.e_first[e] && kk == 0) ? 0u : 1u);
+        const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
+        for (int m = 0; m < p.mt; ++m) {
+          const uint64_t a_base = a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step);
+          const uint32_t acc = tmem_base + (uint32_t)((buf * p.mt + m) * p.ncols);
+#pragma unroll 4
+          for (int i = 0; i < n_mma; ++i) {
+            const uint32_t d = tab_d[i];
+            umma_f16(acc + (d & 0xFFFFu), a_base + tab_a[i], tab_b[i], idesc, d >> 31);
           }
         }
         umma_commit(smem_u32(&a_empty[stage]));
@@ -225,20 +241,25 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nchunk16 = p.ncols >> 4;
     const size_t plane = (size_t)p.H * p.W * 8;  // elements per planar-8 channel group
-    int it = 0;
+    int it = 0, stage = 0;
+    uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int tx = tile % p.tiles_x;
       const int r = tile / p.tiles_x;
       const int ty = r % p.tiles_y, b = r / p.tiles_y;
-      const int y = ty * TH + ty_, x = tx * TW + tx_;
-      const bool valid = (y < p.H) && (x < p.W);
+      const int x = tx * TW + tx_;
       const int buf = it & 1;
+      const uint32_t res_smem = a_smem + stage * p.a_stage_bytes + (uint32_t)(((ty_ + 1) * pitch + tx_ + 1) * 16);
+      if (p.epi == EPI_RES) mbar_wait(smem_u32(&a_full[stage]), phase);  // acquire the TMA-written tile
       mbar_wait(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
-      for (int j = 0; j < nchunk16; ++j) {
+      for (int jm = 0; jm < nchunk16 * p.mt; ++jm) {
+        const int mi = jm / nchunk16, j = jm - mi * nchunk16;
+        const int y = (ty * p.mt + mi) * TH + ty_;
+        const bool valid = (y < p.H) && (x < p.W);
         float v[16];
         __syncwarp();
-        tmem_ld16(trow + (uint32_t)(buf * p.ncols + j * 16), v);
+        tmem_ld16(trow + (uint32_t)((buf * p.mt + mi) * p.ncols + j * 16), v);
         if (!valid) continue;
         const int n0 = j * 16;
         {
@@ -284,8 +305,17 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
             const size_t o = ((size_t)b * G + (n0 >> 3)) * plane + ((size_t)y * p.W + x) * 8;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+              // residual x[pixel][n0+8h .. +7] = plane (n0/8 + h) of the halo tile at (row+1, col+1)
+              uint4 u;
+              const uint32_t ra = res_smem + (uint32_t)(((n0 >> 3) + h) * p.plane_bytes + mi * TH * pitch * 16);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ra));
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
               float rr[8], a[8];
-              ld8(p.res + o + h * plane, rr);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
+              }
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h + 4));
               const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -321,7 +351,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&t_empty[buf]));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&t_empty[buf]));
+        if (p.epi == EPI_RES) mbar_arrive(smem_u32(&a_empty[stage]));
+      }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -453,36 +487,51 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
   if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES needs beta and res");
+  if (io.epi == EPI_RES && L.cin != io.out_c) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES is the c -> c ResConv (residual = input)");
   if (io.epi == EPI_HEADT && L.ncols != 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_HEADT expects N = 16");
   HaloParams p{};
   p.B = io.B; p.H = io.H; p.W = io.W;
-  p.tiles_x = (io.W + TW - 1) / TW;
-  p.tiles_y = (io.H + TH - 1) / TH;
-  p.ntiles = p.tiles_x * p.tiles_y * io.B;
   p.kgroups = L.cin / 8; p.ksteps = L.cin / 16;
   p.R = L.kind == CONV_3x3 ? 2 : 1;
-  p.plane_bytes = (TH + p.R) * (TW + p.R) * 16;
+  if (L.nentries * p.ksteps > MAX_MMA) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: MMA schedule too long");
+  // stack up to 4 M-tiles per pipeline step for thin layers: amortises the per-step barrier chain and the halo
+  {
+    const int w_al0 = (L.w_bytes + 1023) / 1024 * 1024;
+    static const int mt_max = []() { const char* e = getenv("RIFE_HK_MT"); return e ? atoi(e) : 2; }();
+    int mt = mt_max < 1 ? 1 : (mt_max > 4 ? 4 : mt_max);
+    while (mt > 1 && (2 * mt * L.ncols > 512 || io.H < TH * mt ||
+                      w_al0 + 3 * (p.kgroups * (TH * mt + p.R) * (TW + p.R) * 16 + 1024) + 2048 > SMEM_BUDGET))
+      mt >>= 1;
+    p.mt = mt;
+  }
+  p.tiles_x = (io.W + TW - 1) / TW;
+  p.tiles_y = (io.H + TH * p.mt - 1) / (TH * p.mt);
+  p.ntiles = p.tiles_x * p.tiles_y * io.B;
+  p.plane_bytes = (TH * p.mt + p.R) * (TW + p.R) * 16;
   p.a_tx_bytes = p.kgroups * p.plane_bytes;
   p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
   p.nentries = L.nentries; p.ne = L.ne; p.ncols = L.ncols; p.n_valid = L.n_valid;
   p.w_bytes = L.w_bytes;
   p.wtile_bytes = p.kgroups * L.ne * 16;
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * L.ncols) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.mt * L.ncols) p.tmem_cols <<= 1;
   const int w_al = (L.w_bytes + 1023) / 1024 * 1024;
   int stages = (SMEM_BUDGET - w_al - 2048) / p.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
   int smem = w_al + stages * p.a_stage_bytes + 1024;
-  // two co-resident CTAs per SM hide the per-tile latency chain of very thin layers when smem and TMEM allow
+  // co-resident CTAs per SM hide the per-step latency chain of thin layers when smem and TMEM allow
   int per_sm = 1;
-  if (2 * p.tmem_cols <= 512) {
+  static const int persm_max = []() { const char* e = getenv("RIFE_HK_PERSM"); return e ? atoi(e) : 4; }();
+  for (int k = persm_max; k >= 2; --k) {
+    if (k * p.tmem_cols > 512) continue;
     int s2 = stages;
-    while (s2 > 3 && 2 * (w_al + s2 * p.a_stage_bytes + 2048) > 224 * 1024) --s2;
-    if (2 * (w_al + s2 * p.a_stage_bytes + 2048) <= 224 * 1024) {
-      per_sm = 2;
+    while (s2 > 3 && k * (w_al + s2 * p.a_stage_bytes + 2048) > 224 * 1024) --s2;
+    if (k * (w_al + s2 * p.a_stage_bytes + 2048) <= 224 * 1024) {
+      per_sm = k;
       stages = s2;
       smem = w_al + stages * p.a_stage_bytes + 1024;
+      break;
     }
   }
   p.stages = stages;
@@ -496,7 +545,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)io.W * 8, (cuuint64_t)io.H, (cuuint64_t)p.kgroups, (cuuint64_t)io.B};
     cuuint64_t strides[3] = {(cuuint64_t)io.W * 16, (cuuint64_t)io.H * io.W * 16, (cuuint64_t)p.kgroups * io.H * io.W * 16};
-    cuuint32_t box[4] = {(cuuint32_t)((TW + p.R) * 8), (cuuint32_t)(TH + p.R), (cuuint32_t)p.kgroups, 1};
+    cuuint32_t box[4] = {(cuuint32_t)((TW + p.R) * 8), (cuuint32_t)(TH * p.mt + p.R), (cuuint32_t)p.kgroups, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(io.in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
