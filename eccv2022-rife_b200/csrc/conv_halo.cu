@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <utility>
+
 #include "conv_halo.cuh"
 
 namespace rife {
@@ -127,6 +129,56 @@ __device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
   st8(dst + 8, a);
 }
 
+// Compile-time MMA schedules (must match halo_pack_weights): KIND 0 = 3x3 taps, 1 = 2x2 taps on the s2d grid,
+// 2 = ConvTranspose(4,2,1)+PixelShuffle as (output parity, tap) pairs.
+template <int KIND> struct Sched;
+template <> struct Sched<0> {
+  static constexpr int NENT = 9, R = 2;
+  static constexpr int dy(int e) { return e / 3 - 1; }
+  static constexpr int dx(int e) { return e % 3 - 1; }
+  static constexpr int col16(int) { return 0; }
+  static constexpr bool first(int e) { return e == 0; }
+};
+template <> struct Sched<1> {
+  static constexpr int NENT = 4, R = 1;
+  static constexpr int dy(int e) { return e / 2 - 1; }
+  static constexpr int dx(int e) { return e % 2 - 1; }
+  static constexpr int col16(int) { return 0; }
+  static constexpr bool first(int e) { return e == 0; }
+};
+template <> struct Sched<2> {
+  static constexpr int NENT = 16, R = 2;
+  static constexpr int dy(int e) { return ((e >> 2) >> 1) ? ((e >> 1) & 1) : ((e >> 1) & 1) - 1; }
+  static constexpr int dx(int e) { return ((e >> 2) & 1) ? (e & 1) : (e & 1) - 1; }
+  static constexpr int col16(int e) { return (e >> 2) * 4; }
+  static constexpr bool first(int e) { return (e & 3) == 0; }
+};
+
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+  else
+    asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 0;" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+}
+
+// fully unrolled issue of one M-tile's MMAs: every operand offset is an immediate
+template <int KIND, int KSTEPS, int NE, int MT, int E = 0, int KK = 0>
+__device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
+  using S = Sched<KIND>;
+  if constexpr (E < S::NENT) {
+    constexpr int pitch = TW + S::R;
+    constexpr int plane16 = (TH * MT + S::R) * pitch;
+    constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
+    constexpr int b_off = E * (2 * KSTEPS) * NE + 2 * KK * NE;
+    umma_f16_c<!(S::first(E) && KK == 0)>(acc + S::col16(E) * 16, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
+    if constexpr (KK + 1 < KSTEPS) issue_tile<KIND, KSTEPS, NE, MT, E, KK + 1>(acc, a_base, b_base, idesc);
+    else issue_tile<KIND, KSTEPS, NE, MT, E + 1, 0>(acc, a_base, b_base, idesc);
+  }
+}
+
+// KIND < 0: generic table-driven schedule (any layer that fits); otherwise the compile-time schedule <KIND,KSTEPS,NE,MT>
+template <int KIND, int KSTEPS, int NE, int MT>
 __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -219,13 +271,21 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         mbar_wait(smem_u32(&a_full[stage]), phase);
         tc_fence_after();
         const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
-        for (int m = 0; m < p.mt; ++m) {
-          const uint64_t a_base = a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step);
-          const uint32_t acc = tmem_base + (uint32_t)((buf * p.mt + m) * p.ncols);
+        if constexpr (KIND >= 0) {
+          const uint64_t b_base = make_desc_noswz(w_smem, (uint32_t)NE * 16u, 128u);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            issue_tile<KIND, KSTEPS, NE, MT>(tmem_base + (uint32_t)((buf * MT + m) * p.ncols),
+                                             a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step), b_base, idesc);
+        } else {
+          for (int m = 0; m < p.mt; ++m) {
+            const uint64_t a_base = a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step);
+            const uint32_t acc = tmem_base + (uint32_t)((buf * p.mt + m) * p.ncols);
 #pragma unroll 4
-          for (int i = 0; i < n_mma; ++i) {
-            const uint32_t d = tab_d[i];
-            umma_f16(acc + (d & 0xFFFFu), a_base + tab_a[i], tab_b[i], idesc, d >> 31);
+            for (int i = 0; i < n_mma; ++i) {
+              const uint32_t d = tab_d[i];
+              umma_f16(acc + (d & 0xFFFFu), a_base + tab_a[i], tab_b[i], idesc, d >> 31);
+            }
           }
         }
         umma_commit(smem_u32(&a_empty[stage]));
@@ -482,6 +542,18 @@ int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
   return RIFE_OK;
 }
 
+static int set_smem_attr(const void* fn) {
+  // once per (function, device): opt in to > 48 KB dynamic shared memory
+  static std::vector<std::pair<const void*, int>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& s : seen)
+    if (s.first == fn && s.second == dev) return RIFE_OK;
+  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  seen.emplace_back(fn, dev);
+  return RIFE_OK;
+}
+
 int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -552,18 +624,31 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed: " + std::to_string((int)r));
   }
-  {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-      RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      attr_set[dev] = true;
-    }
-  }
   int grid = num_sms() * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
-  conv_halo_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
+  const int kind = L.ps_cols ? 2 : (L.kind == CONV_3x3 ? 0 : 1);
+  bool done = false;
+#define RIFE_HK_CASE(K, KS, N_)                                                                              \
+  if (!done && p.mt == 2 && kind == K && p.ksteps == KS && p.ne == N_) {                                     \
+    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, 2>));                                    \
+    conv_halo_kernel<K, KS, N_, 2><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);                               \
+    done = true;                                                                                             \
+  }
+  RIFE_HK_CASE(1, 1, 16)   // Head.cnn0            (s2d, cin 16 -> 16)
+  RIFE_HK_CASE(0, 1, 16)   // Head.cnn1/2/3        (3x3, 16 -> 16)
+  RIFE_HK_CASE(1, 8, 16)   // block4.conv0.0       (s2d, 128 -> 16)
+  RIFE_HK_CASE(1, 4, 32)   // block4.conv0.1       (s2d, 64 -> 32)
+  RIFE_HK_CASE(0, 2, 32)   // block4 ResConv       (3x3, 32 -> 32)
+  RIFE_HK_CASE(2, 2, 64)   // block4.lastconv      (ConvT+PS, 32 -> 4x64)
+  RIFE_HK_CASE(1, 8, 32)   // block3.conv0.0       (s2d, 128 -> 32)
+  RIFE_HK_CASE(1, 8, 64)   // block3.conv0.1       (s2d, 128 -> 64)
+  RIFE_HK_CASE(0, 4, 64)   // block3 ResConv       (3x3, 64 -> 64)
+  RIFE_HK_CASE(2, 4, 64)   // block3.lastconv      (ConvT+PS, 64 -> 4x64)
+#undef RIFE_HK_CASE
+  if (!done) {
+    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0>));
+    conv_halo_kernel<-1, 0, 0, 0><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
+  }
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }

@@ -38,11 +38,11 @@ __device__ __forceinline__ Lerp make_lerp(int d, int in_size, float rs) {
 
 // bilinear up-sample read of channels [c0, c0+N) of a tmp level at full-resolution pixel (y, x)
 template <typename Tt, int N>
-__device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, int w, int s, int c0, int y, int x,
-                                           float (&out)[N]) {
+__device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, int w, int s, float rs, int c0, int y,
+                                           int x, float (&out)[N]) {
   static_assert(N == 4 || N == 16, "N");
   if (s == 1) {
-    const Tt* p = base + ((size_t)y * w + x) * TMP_C + c0;
+    const Tt* p = base + (y * w + x) * TMP_C + c0;
     if constexpr (N == 4) {
       ld4(p, out);
     } else {
@@ -54,12 +54,13 @@ __device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, i
     }
     return;
   }
-  const float rs = 1.f / (float)s;
   const Lerp ly = make_lerp(y, h, rs), lx = make_lerp(x, w, rs);
-  const Tt* p00 = base + ((size_t)ly.i0 * w + lx.i0) * TMP_C + c0;
-  const Tt* p01 = base + ((size_t)ly.i0 * w + lx.i1) * TMP_C + c0;
-  const Tt* p10 = base + ((size_t)ly.i1 * w + lx.i0) * TMP_C + c0;
-  const Tt* p11 = base + ((size_t)ly.i1 * w + lx.i1) * TMP_C + c0;
+  const Tt* r0 = base + ly.i0 * w * TMP_C + c0;   // per-image element offsets fit in 32 bits
+  const Tt* r1 = base + ly.i1 * w * TMP_C + c0;
+  const Tt* p00 = r0 + lx.i0 * TMP_C;
+  const Tt* p01 = r0 + lx.i1 * TMP_C;
+  const Tt* p10 = r1 + lx.i0 * TMP_C;
+  const Tt* p11 = r1 + lx.i1 * TMP_C;
   float v00[N], v01[N], v10[N], v11[N];
   if constexpr (N == 4) {
     ld4(p00, v00); ld4(p01, v01); ld4(p10, v10); ld4(p11, v11);
@@ -79,17 +80,20 @@ __device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, i
 }
 
 struct WarpGeom {
-  float halfw, halfh;  // (W-1)/2, (H-1)/2   (model/warplayer.py:18-19)
-  float wm1, hm1;      // W-1, H-1
+  float halfw, halfh;          // (W-1)/2, (H-1)/2   (model/warplayer.py:18-19)
+  float inv_halfw, inv_halfh;  // reciprocals, used by the fp16-storage pipeline (1 ulp of the normalised coordinate)
+  float wm1, hm1;              // W-1, H-1
 };
+template <typename T> struct ExactDiv { static constexpr bool value = true; };
+template <> struct ExactDiv<__half> { static constexpr bool value = false; };
 
 // One bilinear tap set of warp() on the 8-channel SRC layout.  Follows the reference's arithmetic order:
 // g = base + flow / ((dim-1)/2); ix = ((g+1)/2)*(dim-1); clamp; 4 taps with zero weight beyond the edge.
 template <typename T>
 __device__ __forceinline__ void warp8(const T* __restrict__ src, int H, int W, const WarpGeom& g, float gx, float gy,
                                       float fx, float fy, float (&out)[8]) {
-  const float nx = gx + __fdiv_rn(fx, g.halfw);
-  const float ny = gy + __fdiv_rn(fy, g.halfh);
+  const float nx = gx + (ExactDiv<T>::value ? __fdiv_rn(fx, g.halfw) : __fmul_rn(fx, g.inv_halfw));
+  const float ny = gy + (ExactDiv<T>::value ? __fdiv_rn(fy, g.halfh) : __fmul_rn(fy, g.inv_halfh));
   float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
   float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
   ix = fminf(g.wm1, fmaxf(ix, 0.f));
@@ -100,7 +104,7 @@ __device__ __forceinline__ void warp8(const T* __restrict__ src, int H, int W, c
   const float wsw = (x1f - ix) * (iy - y0f), wse = (ix - x0f) * (iy - y0f);
   const int x0 = (int)x0f, y0 = (int)y0f;
   const bool xin = (x0 + 1) < W, yin = (y0 + 1) < H;
-  const T* p = src + ((size_t)y0 * W + x0) * SRC_C;
+  const T* p = src + (y0 * W + x0) * SRC_C;
   float v[8];
   ld8(p, v);
 #pragma unroll
@@ -111,11 +115,11 @@ __device__ __forceinline__ void warp8(const T* __restrict__ src, int H, int W, c
     for (int c = 0; c < 8; ++c) out[c] += v[c] * wne;
   }
   if (yin) {
-    ld8(p + (size_t)W * SRC_C, v);
+    ld8(p + W * SRC_C, v);
 #pragma unroll
     for (int c = 0; c < 8; ++c) out[c] += v[c] * wsw;
     if (xin) {
-      ld8(p + (size_t)W * SRC_C + SRC_C, v);
+      ld8(p + W * SRC_C + SRC_C, v);
 #pragma unroll
       for (int c = 0; c < 8; ++c) out[c] += v[c] * wse;
     }
@@ -126,6 +130,7 @@ constexpr int MAXLEV = 5;
 struct LevelsArg {
   const void* ptr[MAXLEV];
   int h[MAXLEV], w[MAXLEV], s[MAXLEV];
+  float rs[MAXLEV], sc[MAXLEV];  // 1/s and s as floats (both exact: s is a power of two)
 };
 
 // flow(p) after `nlev` blocks, plus all 16 channels of the newest level (mask = ch 4, feat = ch 5..12)
@@ -136,15 +141,15 @@ __device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int b, 
   for (int j = 0; j < nlev - 1; ++j) {
     float f[4];
     const Tt* base = reinterpret_cast<const Tt*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
-    sample_tmp<Tt, 4>(base, L.h[j], L.w[j], L.s[j], 0, y, x, f);
-    const float sc = (float)L.s[j];
+    sample_tmp<Tt, 4>(base, L.h[j], L.w[j], L.s[j], L.rs[j], 0, y, x, f);
+    const float sc = L.sc[j];
 #pragma unroll
     for (int c = 0; c < 4; ++c) flow[c] = (j == 0) ? f[c] * sc : flow[c] + f[c] * sc;  // flow = flow + fd (IFNet_HDv3.py:152)
   }
   const int j = nlev - 1;
   const Tt* base = reinterpret_cast<const Tt*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
-  sample_tmp<Tt, 16>(base, L.h[j], L.w[j], L.s[j], 0, y, x, last);
-  const float sc = (float)L.s[j];
+  sample_tmp<Tt, 16>(base, L.h[j], L.w[j], L.s[j], L.rs[j], 0, y, x, last);
+  const float sc = L.sc[j];
 #pragma unroll
   for (int c = 0; c < 4; ++c) flow[c] = (j == 0) ? last[c] * sc : flow[c] + last[c] * sc;
 }
@@ -207,11 +212,9 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
                                                           const float* __restrict__ tstep, T* __restrict__ xin, int B,
                                                           int H, int W, WarpGeom geom, int planar) {
   const int Hs = H / s, Ws = W / s;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Hs * Ws) return;
-  const int X = (int)(idx % Ws);
-  const int Y = (int)((idx / Ws) % Hs);
-  const int b = (int)(idx / ((size_t)Ws * Hs));
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Ws) return;
   const T* s0 = src0 + (size_t)b * H * W * SRC_C;
   const T* s1 = src1 + (size_t)b * H * W * SRC_C;
   const float t = tstep[b];
@@ -228,8 +231,8 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
       if (level == 0) {
         // IFNet_HDv3.py:141: cat(img0[:, :3], img1[:, :3], f0, f1, timestep)
         float a[8], c[8];
-        ld8(s0 + ((size_t)y * W + x) * SRC_C, a);
-        ld8(s1 + ((size_t)y * W + x) * SRC_C, c);
+        ld8(s0 + (y * W + x) * SRC_C, a);
+        ld8(s1 + (y * W + x) * SRC_C, c);
         v[0] = a[4]; v[1] = a[5]; v[2] = a[6];
         v[3] = c[4]; v[4] = c[5]; v[5] = c[6];
 #pragma unroll
@@ -305,12 +308,10 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
                                                    Tio* __restrict__ omask, Tio* __restrict__ ow0,
                                                    Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
                                                    int H, int W, WarpGeom geom) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t plane = (size_t)H * W;
-  if (idx >= (size_t)B * plane) return;
-  const int x = (int)(idx % W);
-  const int y = (int)((idx / W) % H);
-  const int b = (int)(idx / plane);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
   float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
   eval_state<Tt>(L, nlev, b, y, x, flow, last);
   const size_t pix = (size_t)y * W + x;
@@ -430,6 +431,8 @@ inline WarpGeom make_geom(int H, int W) {
   WarpGeom g;
   g.halfw = (float)((W - 1.0) / 2.0);
   g.halfh = (float)((H - 1.0) / 2.0);
+  g.inv_halfw = 1.f / g.halfw;
+  g.inv_halfh = 1.f / g.halfh;
   g.wm1 = (float)(W - 1);
   g.hm1 = (float)(H - 1);
   return g;
@@ -463,21 +466,23 @@ static LevelsArg pack_levels(const TmpLevel* levels, int n) {
     L.h[i] = levels[i].h;
     L.w[i] = levels[i].w;
     L.s[i] = levels[i].s;
+    L.rs[i] = 1.f / (float)levels[i].s;
+    L.sc[i] = (float)levels[i].s;
   }
   return L;
 }
 
 int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
                        cudaStream_t st) {
-  const size_t n = (size_t)c.B * (c.H / s) * (c.W / s);
   LevelsArg L = pack_levels(levels, level);
   WarpGeom g = make_geom(c.H, c.W);
+  const dim3 grid(nblk((size_t)(c.W / s), 128), (unsigned)(c.H / s), (unsigned)c.B);
   if (c.half_act)
-    block_input_kernel<__half, __half><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const __half*)c.src0,
+    block_input_kernel<__half, __half><<<grid, 128, 0, st>>>(L, level, s, (const __half*)c.src0,
                                                                       (const __half*)c.src1, c.gridx, c.gridy, c.tstep,
                                                                       (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
   else
-    block_input_kernel<float, float><<<nblk(n, 128), 128, 0, st>>>(L, level, s, (const float*)c.src0,
+    block_input_kernel<float, float><<<grid, 128, 0, st>>>(L, level, s, (const float*)c.src0,
                                                                     (const float*)c.src1, c.gridx, c.gridy, c.tstep,
                                                                     (float*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
   RIFE_LAUNCH_CHECK();
@@ -488,8 +493,9 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   const size_t n = (size_t)c.B * c.H * c.W;
   LevelsArg L = pack_levels(levels, nlev);
   WarpGeom g = make_geom(c.H, c.W);
+  const dim3 egrid(nblk((size_t)c.W, 256), (unsigned)c.H, (unsigned)c.B);
 #define RIFE_EVAL(T, TIO)                                                                                         \
-  eval_kernel<T, T, TIO><<<nblk(n, 256), 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
+  eval_kernel<T, T, TIO><<<egrid, 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
                                                        c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
                                                        (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g)
   if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
