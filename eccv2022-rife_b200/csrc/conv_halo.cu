@@ -16,6 +16,7 @@
 //   * ConvTranspose2d(4,2,1)+PixelShuffle (lastconv) runs as 4 output parities x 4 taps (16 MMAs groups of N=64)
 //     instead of 9 dense taps of N=208/256.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <utility>
@@ -43,6 +44,7 @@ struct HaloParams {
   const float* beta;
   const __half* res;
   __half* out;
+  long long* dbg;  // RIFE_HK_DEBUG=1: per-CTA role timers (8 x int64), else null
   signed char e_dy[MAX_ENTRIES], e_dx[MAX_ENTRIES];
   unsigned char e_col16[MAX_ENTRIES], e_first[MAX_ENTRIES];
 };
@@ -71,6 +73,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) return;
     if (clock64() - t0 > 4000000000LL) __trap();  // a mis-programmed pipeline traps instead of hanging the GPU
   }
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -177,8 +184,112 @@ __device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64
   }
 }
 
+
+// Per-tile epilogue context of one thread (= one pixel column position tx_ of the tile; rows come from (mi, ty_)).
+struct EpiCtx {
+  int b, x, y0;           // batch, pixel x, first row of this thread in the step (mi = 0)
+  uint32_t res_smem;      // smem address of the residual for (mi = 0, plane 0)
+  size_t plane;           // elements per planar-8 channel group of the destination
+};
+
+// Fused layer tail for 16 accumulator columns [16j, 16j+16) of M-tile `mi` (bias already in smem).
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, const float* s_bias, const float* s_beta,
+                                          int pitch, int mi, int j, float (&v)[16]) {
+  const int n0 = j * 16;
+  const int y = c.y0 + mi * TH;
+  if (y >= p.H || c.x >= p.W) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * i);
+    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+  }
+  if constexpr (EPI == EPI_LRELU || EPI == EPI_LINEAR || EPI == EPI_LRELU_S2D) {
+    if constexpr (EPI != EPI_LINEAR) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
+    }
+    if (n0 >= p.n_valid) return;
+    __half* dst;
+    size_t pl;
+    if constexpr (EPI == EPI_LRELU_S2D) {
+      // planar-8 on the half-resolution s2d grid, channel = par*out_c + n
+      const int H2 = p.H >> 1, W2 = p.W >> 1;
+      const int G = (4 * p.out_c) >> 3, g = (((y & 1) * 2 + (c.x & 1)) * p.out_c + n0) >> 3;
+      pl = (size_t)H2 * W2 * 8;
+      dst = p.out + ((size_t)c.b * G + g) * pl + ((size_t)(y >> 1) * W2 + (c.x >> 1)) * 8;
+    } else {
+      pl = c.plane;
+      dst = p.out + ((size_t)c.b * (p.out_c >> 3) + (n0 >> 3)) * pl + ((size_t)y * p.W + c.x) * 8;
+    }
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = v[i];
+    st8(dst, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
+    st8(dst + pl, a);
+  } else if constexpr (EPI == EPI_RES) {
+    const size_t o = ((size_t)c.b * (p.out_c >> 3) + (n0 >> 3)) * c.plane + ((size_t)y * p.W + c.x) * 8;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // residual x[pixel][n0+8h .. +7] = plane (n0/8 + h) of the halo tile at (row+1, col+1)
+      uint4 u;
+      const uint32_t ra = c.res_smem + (uint32_t)(((n0 >> 3) + h) * p.plane_bytes + mi * TH * pitch * 16);
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ra));
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+      float rr[8], a[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(hh[i]);
+        rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
+      }
+      const float4 b0 = *reinterpret_cast<const float4*>(s_beta + n0 + 8 * h);
+      const float4 b1 = *reinterpret_cast<const float4*>(s_beta + n0 + 8 * h + 4);
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
+      st8(p.out + o + h * c.plane, a);
+    }
+  } else if constexpr (EPI == EPI_PS) {
+    const int par = j >> 2, sub = j & 3;
+    const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * c.x + 2 * (par & 1) + (sub & 1);
+    store16h(p.out + (((size_t)c.b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
+  } else if constexpr (EPI == EPI_HEADT) {
+#pragma unroll
+    for (int par = 0; par < 4; ++par) {
+      const int oy = 2 * y + (par >> 1), ox = 2 * c.x + (par & 1);
+      float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
+      st4(p.out + (((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
+    }
+  } else if constexpr (EPI == EPI_CONVT) {
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      if (n >= p.n_valid) break;
+      const int par = n / p.cpp, co = n - par * p.cpp;
+      const int oy = 2 * y + (par >> 1), ox = 2 * c.x + (par & 1);
+      p.out[(((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_chunk_rt(const HaloParams& p, const EpiCtx& c, const float* s_bias,
+                                             const float* s_beta, int pitch, int mi, int j, float (&v)[16]) {
+  switch (p.epi) {
+    case EPI_LRELU: epi_chunk<EPI_LRELU>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_LINEAR: epi_chunk<EPI_LINEAR>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_LRELU_S2D: epi_chunk<EPI_LRELU_S2D>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_RES: epi_chunk<EPI_RES>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_PS: epi_chunk<EPI_PS>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_HEADT: epi_chunk<EPI_HEADT>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    case EPI_CONVT: epi_chunk<EPI_CONVT>(p, c, s_bias, s_beta, pitch, mi, j, v); break;
+    default: break;
+  }
+}
+
 // KIND < 0: generic table-driven schedule (any layer that fits); otherwise the compile-time schedule <KIND,KSTEPS,NE,MT>
-template <int KIND, int KSTEPS, int NE, int MT>
+// EPI >= 0 additionally fixes the epilogue at compile time (fully unrolled over M-tiles and 16-column chunks).
+template <int KIND, int KSTEPS, int NE, int MT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -188,6 +299,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
   __shared__ __align__(8) uint64_t t_full[2];
   __shared__ __align__(8) uint64_t t_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_beta[128];
   // per-MMA operand tables, built once: the issuing thread then spends ~5 instructions per tcgen05.mma
   __shared__ __align__(8) uint64_t tab_b[MAX_MMA];  // complete B (weights) descriptor
   __shared__ uint32_t tab_a[MAX_MMA];               // A start-address field relative to the stage base (16-byte units)
@@ -218,6 +331,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.ncols; i += NUM_THREADS - 64) {
+      s_bias[i] = p.bias[i];
+      if (p.beta && i < 128) s_beta[i] = p.beta[i];
+    }
+  }
   if (warp == 1) {
     const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)p.ne * 16u, 128u);
     for (int i = lane; i < p.nentries * p.ksteps; i += 32) {
@@ -245,16 +364,18 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       }
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int tx = tile % p.tiles_x;
         const int r = tile / p.tiles_x;
         const int ty = r % p.tiles_y, b = r / p.tiles_y;
-        mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1);
+        mbar_wait_t(smem_u32(&a_empty[stage]), phase ^ 1, t_wait);
         const uint32_t fb = smem_u32(&a_full[stage]);
         mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
         tma_load_4d(a_smem + stage * p.a_stage_bytes, &tm_a, fb, (tx * TW - 1) * 8, ty * TH * p.mt - 1, 0, b);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = t_wait;
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -262,13 +383,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ne >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_desc0 = make_desc_noswz(0, (uint32_t)p.plane_bytes, (uint32_t)pitch * 16u);
       const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
-      mbar_wait(smem_u32(&w_full), 0);
+      long long t_w = 0, t_te = 0, t_af = 0;
+      const long long t_begin = clock64();
+      mbar_wait_t(smem_u32(&w_full), 0, t_w);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        mbar_wait(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
-        mbar_wait(smem_u32(&a_full[stage]), phase);
+        mbar_wait_t(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u, t_te);
+        mbar_wait_t(smem_u32(&a_full[stage]), phase, t_af);
         tc_fence_after();
         const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
         if constexpr (KIND >= 0) {
@@ -292,6 +415,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         umma_commit(smem_u32(&t_full[buf]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 1] = t_w;
+        p.dbg[blockIdx.x * 8 + 2] = t_te;
+        p.dbg[blockIdx.x * 8 + 3] = t_af;
+        p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
     }
   } else {
     // ---------------- epilogue warps: TMEM lanes 32*(warp%4)..+31
@@ -303,119 +432,54 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
     const size_t plane = (size_t)p.H * p.W * 8;  // elements per planar-8 channel group
     int it = 0, stage = 0;
     uint32_t phase = 0;
+    long long t_tf = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int tx = tile % p.tiles_x;
       const int r = tile / p.tiles_x;
       const int ty = r % p.tiles_y, b = r / p.tiles_y;
-      const int x = tx * TW + tx_;
       const int buf = it & 1;
-      const uint32_t res_smem = a_smem + stage * p.a_stage_bytes + (uint32_t)(((ty_ + 1) * pitch + tx_ + 1) * 16);
-      if (p.epi == EPI_RES) mbar_wait(smem_u32(&a_full[stage]), phase);  // acquire the TMA-written tile
-      mbar_wait(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u);
+      EpiCtx c;
+      c.b = b; c.x = tx * TW + tx_; c.plane = plane;
+      c.res_smem = a_smem + stage * p.a_stage_bytes + (uint32_t)(((ty_ + 1) * pitch + tx_ + 1) * 16);
+      if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) mbar_wait(smem_u32(&a_full[stage]), phase);  // acquire the TMA-written tile
+      mbar_wait_t(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u, t_tf);
       tc_fence_after();
-      for (int jm = 0; jm < nchunk16 * p.mt; ++jm) {
-        const int mi = jm / nchunk16, j = jm - mi * nchunk16;
-        const int y = (ty * p.mt + mi) * TH + ty_;
-        const bool valid = (y < p.H) && (x < p.W);
-        float v[16];
-        __syncwarp();
-        tmem_ld16(trow + (uint32_t)((buf * p.mt + mi) * p.ncols + j * 16), v);
-        if (!valid) continue;
-        const int n0 = j * 16;
-        {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+      if constexpr (KIND >= 0 && EPI >= 0) {
+        constexpr int NCOLS = KIND == 2 ? 256 : NE;
+        c.y0 = ty * MT * TH + ty_;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(bp + i);
-            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+        for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+          for (int j = 0; j < NCOLS / 16; ++j) {
+            float v[16];
+            tmem_ld16(trow + (uint32_t)((buf * MT + mi) * NCOLS + j * 16), v);
+            epi_chunk<EPI>(p, c, s_bias, s_beta, pitch, mi, j, v);
+            __syncwarp();
           }
         }
-        switch (p.epi) {
-          case EPI_LRELU:
-          case EPI_LINEAR:
-          case EPI_LRELU_S2D: {
-            if (p.epi != EPI_LINEAR) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
-            }
-            if (n0 >= p.n_valid) break;
-            __half* dst;
-            size_t pl;
-            if (p.epi == EPI_LRELU_S2D) {
-              // planar-8 on the half-resolution s2d grid, channel = par*out_c + n
-              const int H2 = p.H >> 1, W2 = p.W >> 1;
-              const int G = (4 * p.out_c) >> 3, g = (((y & 1) * 2 + (x & 1)) * p.out_c + n0) >> 3;
-              pl = (size_t)H2 * W2 * 8;
-              dst = p.out + ((size_t)b * G + g) * pl + ((size_t)(y >> 1) * W2 + (x >> 1)) * 8;
-            } else {
-              const int G = p.out_c >> 3;
-              pl = plane;
-              dst = p.out + ((size_t)b * G + (n0 >> 3)) * pl + ((size_t)y * p.W + x) * 8;
-            }
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = v[i];
-            st8(dst, a);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
-            st8(dst + pl, a);
-          } break;
-          case EPI_RES: {
-            const int G = p.out_c >> 3;
-            const size_t o = ((size_t)b * G + (n0 >> 3)) * plane + ((size_t)y * p.W + x) * 8;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              // residual x[pixel][n0+8h .. +7] = plane (n0/8 + h) of the halo tile at (row+1, col+1)
-              uint4 u;
-              const uint32_t ra = res_smem + (uint32_t)(((n0 >> 3) + h) * p.plane_bytes + mi * TH * pitch * 16);
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ra));
-              const __half2* hh = reinterpret_cast<const __half2*>(&u);
-              float rr[8], a[8];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(hh[i]);
-                rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
-              }
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h + 4));
-              const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
-              st8(p.out + o + h * plane, a);
-            }
-          } break;
-          case EPI_PS: {
-            const int par = j >> 2, sub = j & 3;
-            const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * x + 2 * (par & 1) + (sub & 1);
-            store16h(p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
-          } break;
-          case EPI_HEADT: {
-#pragma unroll
-            for (int par = 0; par < 4; ++par) {
-              const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
-              float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
-              st4(p.out + (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
-            }
-          } break;
-          case EPI_CONVT: {
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + i;
-              if (n >= p.n_valid) break;
-              const int par = n / p.cpp, co = n - par * p.cpp;
-              const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
-              p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
-            }
-          } break;
-          default: break;
+      } else {
+        c.y0 = ty * p.mt * TH + ty_;
+        for (int jm = 0; jm < nchunk16 * p.mt; ++jm) {
+          const int mi = jm / nchunk16, j = jm - mi * nchunk16;
+          float v[16];
+          __syncwarp();
+          tmem_ld16(trow + (uint32_t)((buf * p.mt + mi) * p.ncols + j * 16), v);
+          epi_chunk_rt(p, c, s_bias, s_beta, pitch, mi, j, v);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(smem_u32(&t_empty[buf]));
-        if (p.epi == EPI_RES) mbar_arrive(smem_u32(&a_empty[stage]));
+        if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) mbar_arrive(smem_u32(&a_empty[stage]));
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 5] = t_tf;
+      p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 8 + 7] = it;
     }
   }
   tc_fence_before();
@@ -549,7 +613,7 @@ static int set_smem_attr(const void* fn) {
   cudaGetDevice(&dev);
   for (auto& s : seen)
     if (s.first == fn && s.second == dev) return RIFE_OK;
-  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
   seen.emplace_back(fn, dev);
   return RIFE_OK;
 }
@@ -626,30 +690,48 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   }
   int grid = num_sms() * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
+  static const bool debug = getenv("RIFE_HK_DEBUG") != nullptr;
+  p.dbg = nullptr;
+  if (debug) {
+    cudaMalloc((void**)&p.dbg, (size_t)grid * 64);
+    cudaMemsetAsync(p.dbg, 0, (size_t)grid * 64, st);
+  }
   const int kind = L.ps_cols ? 2 : (L.kind == CONV_3x3 ? 0 : 1);
   bool done = false;
-#define RIFE_HK_CASE(K, KS, N_)                                                                              \
-  if (!done && p.mt == 2 && kind == K && p.ksteps == KS && p.ne == N_) {                                     \
-    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, 2>));                                    \
-    conv_halo_kernel<K, KS, N_, 2><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);                               \
+#define RIFE_HK_CASE(K, KS, N_, MT_, E_)                                                                     \
+  if (!done && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {                   \
+    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_>));                              \
+    conv_halo_kernel<K, KS, N_, MT_, E_><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);                         \
     done = true;                                                                                             \
   }
-  RIFE_HK_CASE(1, 1, 16)   // Head.cnn0            (s2d, cin 16 -> 16)
-  RIFE_HK_CASE(0, 1, 16)   // Head.cnn1/2/3        (3x3, 16 -> 16)
-  RIFE_HK_CASE(1, 8, 16)   // block4.conv0.0       (s2d, 128 -> 16)
-  RIFE_HK_CASE(1, 4, 32)   // block4.conv0.1       (s2d, 64 -> 32)
-  RIFE_HK_CASE(0, 2, 32)   // block4 ResConv       (3x3, 32 -> 32)
-  RIFE_HK_CASE(2, 2, 64)   // block4.lastconv      (ConvT+PS, 32 -> 4x64)
-  RIFE_HK_CASE(1, 8, 32)   // block3.conv0.0       (s2d, 128 -> 32)
-  RIFE_HK_CASE(1, 8, 64)   // block3.conv0.1       (s2d, 128 -> 64)
-  RIFE_HK_CASE(0, 4, 64)   // block3 ResConv       (3x3, 64 -> 64)
-  RIFE_HK_CASE(2, 4, 64)   // block3.lastconv      (ConvT+PS, 64 -> 4x64)
+  RIFE_HK_CASE(1, 1, 16, 2, EPI_LRELU)      // Head.cnn0            (s2d, cin 16 -> 16)
+  RIFE_HK_CASE(0, 1, 16, 2, EPI_LRELU)      // Head.cnn1/2          (3x3, 16 -> 16)
+  RIFE_HK_CASE(0, 1, 16, 2, EPI_HEADT)      // Head.cnn3            (ConvT as 3x3, 16 -> 4x4)
+  RIFE_HK_CASE(1, 8, 16, 1, EPI_LRELU_S2D)  // block4.conv0.0       (s2d, 128 -> 16)
+  RIFE_HK_CASE(1, 4, 32, 2, EPI_LRELU)      // block4.conv0.1       (s2d, 64 -> 32)
+  RIFE_HK_CASE(0, 2, 32, 2, EPI_RES)        // block4 ResConv       (3x3, 32 -> 32)
+  RIFE_HK_CASE(2, 2, 64, 1, EPI_PS)         // block4.lastconv      (ConvT+PS, 32 -> 4x64)
+  RIFE_HK_CASE(1, 8, 32, 1, EPI_LRELU_S2D)  // block3.conv0.0       (s2d, 128 -> 32)
+  RIFE_HK_CASE(1, 8, 64, 1, EPI_LRELU)      // block3.conv0.1       (s2d, 128 -> 64)
+  RIFE_HK_CASE(0, 4, 64, 2, EPI_RES)        // block3 ResConv       (3x3, 64 -> 64)
+  RIFE_HK_CASE(2, 4, 64, 1, EPI_PS)         // block3.lastconv      (ConvT+PS, 64 -> 4x64)
 #undef RIFE_HK_CASE
   if (!done) {
-    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0>));
-    conv_halo_kernel<-1, 0, 0, 0><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
+    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
+    conv_halo_kernel<-1, 0, 0, 0, -1><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
   }
   RIFE_LAUNCH_CHECK();
+  if (debug) {
+    std::vector<long long> h((size_t)grid * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), p.dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    double a[8] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 8 + k] / grid;
+    fprintf(stderr, "[hk] kind=%d cin=%d ne=%d mt=%d grid=%d per_sm=%d stages=%d steps/cta=%.1f | prod wait a_empty %.0f | mma: wait w %.0f, t_empty %.0f, a_full %.0f, total %.0f | epi: wait t_full %.0f, total %.0f\n",
+            kind, L.cin, L.ne, p.mt, grid, per_sm, p.stages, a[7], a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
   return RIFE_OK;
 }
 
