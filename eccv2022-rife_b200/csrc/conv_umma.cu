@@ -30,7 +30,7 @@ struct UmmaParams {
   int B, H, W;
   int tw, th, tiles_x, tiles_y;
   int ntaps, nchunks, kc, stages;
-  int npad, n_valid, tmem_cols;
+  int npad, n_valid, tmem_cols, nw;  // nw = accumulator columns per CTA (N split over blockIdx.y)
   int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
   int epi, out_c, cpp;
   const float* bias;
@@ -125,6 +125,10 @@ __device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// grid = (pixel tiles, N splits): each CTA computes `nw` accumulator columns [blockIdx.y * nw, +nw) of one 128-pixel
+// tile.  Splitting N gives the small-spatial / wide-channel layers (IFBlock 0-2) enough CTAs to cover the machine
+// and shrinks the per-stage weight tile, so the TMA ring is deeper.
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const __grid_constant__ CUtensorMap tm_b,
                                                                 const UmmaParams p) {
@@ -133,6 +137,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_beta[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
   const int ty = tile % p.tiles_y;
   const int b = tile / p.tiles_y;
   const int x0 = tx * p.tw, y0 = ty * p.th;
+  const int n_off = blockIdx.y * p.nw;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -161,6 +168,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.nw; i += NUM_THREADS - 64) {
+      s_bias[i] = p.bias[n_off + i];
+      if (EPI == EPI_RES) s_beta[i] = p.beta[n_off + i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,14 +185,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
       // ---------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.nw * p.kc * 2);
       for (int ks = 0; ks < ksteps; ++ks) {
         const int tap = ks / p.nchunks, chunk = ks - tap * p.nchunks;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, (uint32_t)(p.a_bytes + p.npad * p.kc * 2));
+        mbar_expect_tx(fb, tx_bytes);
         const uint32_t sa = tiles_base + stage * stage_bytes;
         tma_load_4d(sa, &tm_a, fb, chunk * p.kc, x0 + p.dx[tap], y0 + p.dy[tap], b);
-        tma_load_2d(sa + p.a_bytes, &tm_b, fb, 0, (tap * p.nchunks + chunk) * p.npad);
+        tma_load_2d(sa + p.a_bytes, &tm_b, fb, 0, ks * p.npad + n_off);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -187,20 +201,32 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- MMA issuer
       // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.nw >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       const uint32_t sbo = 8u * (uint32_t)p.kc * 2u;
       const uint32_t layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+      const uint64_t desc0 = make_smem_desc(0, sbo, layout);
+      const uint32_t a16 = (uint32_t)p.a_bytes >> 4;
       const int ksub = p.kc >> 4;
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, accum = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
-        const uint32_t sa = tiles_base + stage * stage_bytes;
-        const uint64_t da = make_smem_desc(sa, sbo, layout);
-        const uint64_t db = make_smem_desc(sa + p.a_bytes, sbo, layout);
-        for (int k = 0; k < ksub; ++k)  // advance 16 fp16 = 32 bytes along K inside the swizzle span
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
+        const uint64_t da = desc0 + (uint64_t)((tiles_base + stage * stage_bytes) >> 4);
+        const uint64_t db = da + a16;
+        // advance 16 fp16 = 32 bytes along K inside the swizzle span
+        if (ksub == 4) {
+          umma_f16(tmem_base, da, db, idesc, accum);
+          umma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+          umma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
+          umma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
+        } else if (ksub == 2) {
+          umma_f16(tmem_base, da, db, idesc, accum);
+          umma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+        } else {
+          umma_f16(tmem_base, da, db, idesc, accum);
+        }
+        accum = 1u;
         umma_commit(smem_u32(&empty_bar[stage]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -213,73 +239,85 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
     const int py_ = m / p.tw, px_ = m - py_ * p.tw;
     const int y = y0 + py_, x = x0 + px_;
     const bool valid = (y < p.H) && (x < p.W);
+    const int nchunk16 = p.nw >> 4;
+    const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+    // ResConv: fetch the residual while the MMAs run (it does not depend on them)
+    constexpr int MAXRES = 6;
+    uint4 resv[2 * MAXRES];
+    if constexpr (EPI == EPI_RES) {
+      if (valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.out_c + n_off);
+#pragma unroll
+        for (int j = 0; j < MAXRES; ++j)
+          if (j < nchunk16) { resv[2 * j] = __ldg(rp + 2 * j); resv[2 * j + 1] = __ldg(rp + 2 * j + 1); }
+      }
+    }
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int nchunk16 = p.npad >> 4;
-    for (int j = 0; j < nchunk16; ++j) {
-      float v[16];
-      __syncwarp();
-      tmem_ld16(trow + (uint32_t)(j * 16), v);
-      if (!valid) continue;
-      const int n0 = j * 16;
-      {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll 1
+    for (int jb = 0; jb < nchunk16; jb += MAXRES) {
+#pragma unroll
+      for (int jj = 0; jj < MAXRES; ++jj) {
+        const int j = jb + jj;
+        if (j >= nchunk16) break;
+        float v[16];
+        __syncwarp();
+        tmem_ld16(trow + (uint32_t)(j * 16), v);
+        if (!valid) continue;
+        const int nl = j * 16;        // column inside this CTA's slice
+        const int n0 = n_off + nl;    // global GEMM column
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 bb = __ldg(bp + i);
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + nl + 4 * i);
           v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
         }
-      }
-      switch (p.epi) {
-        case EPI_LRELU:
-        case EPI_LINEAR: {
-          if (p.epi == EPI_LRELU) {
+        if constexpr (EPI == EPI_LRELU || EPI == EPI_LINEAR) {
+          if constexpr (EPI == EPI_LRELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
           }
-          if (n0 < p.n_valid) store16h(p.out + (((size_t)b * p.H + y) * p.W + x) * p.out_c + n0, v);
-        } break;
-        case EPI_LRELU_S2D: {
+          if (n0 < p.n_valid) store16h(p.out + pix * p.out_c + n0, v);
+        } else if constexpr (EPI == EPI_LRELU_S2D) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
           const size_t o = ((((size_t)b * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1)));
           if (n0 < p.n_valid) store16h(p.out + o * p.out_c + n0, v);
-        } break;
-        case EPI_RES: {
-          const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.out_c + n0;
-          float r[8], be[4];
+        } else if constexpr (EPI == EPI_RES) {
+          uint4 r2[2];
+          if (jb == 0) { r2[0] = resv[2 * jj]; r2[1] = resv[2 * jj + 1]; }
+          else {  // slices wider than 16*MAXRES columns: fetch late (not used by the network's shapes)
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.out_c + n0);
+            r2[0] = __ldg(rp); r2[1] = __ldg(rp + 1);
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ld8(p.res + o + 8 * h, r);
+            const __half2* hh = reinterpret_cast<const __half2*>(&r2[h]);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_beta + nl + 8 * h);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_beta + nl + 8 * h + 4);
+            const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + 8 * h + 4 * g));
-              be[0] = bb.x; be[1] = bb.y; be[2] = bb.z; be[3] = bb.w;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = 8 * h + 4 * g + i;
-                v[k] = lrelu02(v[k] * be[i] + r[4 * g + i]);
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(hh[i]);
+              v[8 * h + 2 * i] = lrelu02(v[8 * h + 2 * i] * be[2 * i] + f.x);
+              v[8 * h + 2 * i + 1] = lrelu02(v[8 * h + 2 * i + 1] * be[2 * i + 1] + f.y);
             }
           }
-          store16h(p.out + o, v);
-        } break;
-        case EPI_PS: {
-          // permuted columns: chunk j = par*4 + (dy*2+dx) holds the 13 (+3 zero) channels of one output pixel
-          const int par = j >> 2, sub = j & 3;
+          store16h(p.out + pix * p.out_c + n0, v);
+        } else if constexpr (EPI == EPI_PS) {
+          // permuted columns: global chunk jg = par*4 + (dy*2+dx) holds the 13 (+3 zero) channels of one output pixel
+          const int jg = n0 >> 4;
+          const int par = jg >> 2, sub = jg & 3;
           const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * x + 2 * (par & 1) + (sub & 1);
           store16h(p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
-        } break;
-        case EPI_HEADT: {
+        } else if constexpr (EPI == EPI_HEADT) {
 #pragma unroll
           for (int par = 0; par < 4; ++par) {
             const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
             float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
             st4(p.out + (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
           }
-        } break;
-        case EPI_CONVT: {
+        } else if constexpr (EPI == EPI_CONVT) {
           for (int i = 0; i < 16; ++i) {
             const int n = n0 + i;
             if (n >= p.n_valid) break;
@@ -287,8 +325,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
             const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
             p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
           }
-        } break;
-        default: break;
+        }
       }
     }
   }
@@ -391,12 +428,15 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   p.tiles_y = (io.H + p.th - 1) / p.th;
   p.ntaps = L.taps; p.kc = L.kc; p.nchunks = L.cin / L.kc;
   p.npad = L.npad; p.n_valid = L.n;
+  // N split: 64-column slices when the layer is wide and has too few pixel tiles to fill the machine
+  p.nw = L.npad;
+  if (L.npad >= 128 && L.npad % 64 == 0 && p.tiles_x * p.tiles_y * io.B <= 148 / 2 + 16 && io.epi != EPI_HEADT) p.nw = 64;
   p.tmem_cols = 32;
-  while (p.tmem_cols < L.npad) p.tmem_cols <<= 1;
+  while (p.tmem_cols < p.nw) p.tmem_cols <<= 1;
   p.a_bytes = TILE_M * L.kc * 2;
-  p.b_bytes = ((L.npad * L.kc * 2) + 1023) / 1024 * 1024;
+  p.b_bytes = ((p.nw * L.kc * 2) + 1023) / 1024 * 1024;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = 98304 / stage_bytes;
+  int stages = (104 * 1024) / stage_bytes;  // two CTAs per SM stay co-resident (no second wave, overlapped epilogues)
   if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int ksteps = p.ntaps * p.nchunks;
@@ -425,7 +465,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.kc, (cuuint64_t)L.taps * p.nchunks * L.npad};
     cuuint64_t strides[1] = {(cuuint64_t)L.kc * 2};
-    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)L.npad};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)p.nw};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(L.w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(L.kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -433,17 +473,29 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
   }
   const int smem = stages * stage_bytes + 1024;
-  {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-      RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set[dev] = true;
-    }
+  const dim3 grid((unsigned)(p.tiles_x * p.tiles_y * io.B), (unsigned)(L.npad / p.nw));
+#define RIFE_UMMA_LAUNCH(E_)                                                                                   \
+  case E_: {                                                                                                   \
+    static bool attr_set[64] = {};                                                                             \
+    int dev = 0;                                                                                               \
+    cudaGetDevice(&dev);                                                                                       \
+    if (dev < 64 && !attr_set[dev]) {                                                                          \
+      RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr_set[dev] = true;                                                                                    \
+    }                                                                                                          \
+    conv_umma_kernel<E_><<<grid, NUM_THREADS, smem, st>>>(tm_a, tm_b, p);                                      \
+  } break;
+  switch (io.epi) {
+    RIFE_UMMA_LAUNCH(EPI_LRELU)
+    RIFE_UMMA_LAUNCH(EPI_LRELU_S2D)
+    RIFE_UMMA_LAUNCH(EPI_RES)
+    RIFE_UMMA_LAUNCH(EPI_PS)
+    RIFE_UMMA_LAUNCH(EPI_HEADT)
+    RIFE_UMMA_LAUNCH(EPI_LINEAR)
+    RIFE_UMMA_LAUNCH(EPI_CONVT)
+    default: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: bad epilogue");
   }
-  const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y * io.B);
-  conv_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a, tm_b, p);
+#undef RIFE_UMMA_LAUNCH
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }
