@@ -1,0 +1,99 @@
+"""Host-side logic of the drop-in surface (runs without a GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_model_surface(pkg):
+    m = pkg.Model()
+    for attr in ("flownet", "version", "train", "eval", "device", "load_model", "save_model", "inference"):
+        assert hasattr(m, attr)
+    assert m.version == 4.25
+    sd = m.flownet.state_dict()
+    assert len(sd) == 158
+    assert sd["encode.cnn3.weight"].shape == (16, 4, 4, 4)                 # ConvTranspose2d: (Cin, Cout, kh, kw)
+    assert sd["block0.conv0.0.0.weight"].shape == (96, 15, 3, 3)
+    assert sd["block4.lastconv.0.weight"].shape == (32, 52, 4, 4)
+    assert sd["block2.convblock.7.beta"].shape == (1, 96, 1, 1)
+
+
+def test_load_model_strips_module_prefix(pkg, tmp_path):
+    """RIFE_HDv3.py:36-50: rank -1 keeps only 'module.' keys, strips the prefix, loads non-strictly."""
+    torch.manual_seed(7)
+    src = pkg.Model()
+    sd = {"module." + k: v.clone() for k, v in src.flownet.state_dict().items()}
+    sd["module.teacher.conv0.weight"] = torch.zeros(3)      # unknown key: tolerated (strict=False)
+    sd["not_prefixed"] = torch.zeros(1)                      # dropped by the rank -1 filter
+    torch.save(sd, tmp_path / "flownet.pkl")
+    dst = pkg.Model()
+    gen0 = dst.flownet._generation
+    dst.load_model(str(tmp_path), -1)
+    assert dst.flownet._generation > gen0                    # packed device weights get rebuilt
+    for k, v in src.flownet.state_dict().items():
+        assert torch.equal(v.cpu(), dst.flownet.state_dict()[k].cpu()), k
+    dst.save_model(str(tmp_path), 0)
+    assert "block0.conv0.0.0.weight" in torch.load(tmp_path / "flownet.pkl")
+
+
+def test_scale_list_and_timestep_validation(pkg):
+    f = pkg.IFNet._scale_from_list
+    assert f([16, 8, 4, 2, 1]) == 1.0 and f([32, 16, 8, 4, 2]) == 0.5 and f([64.0, 32.0, 16.0, 8.0, 4.0]) == 0.25
+    with pytest.raises(ValueError):
+        f([8, 4, 2, 1])                    # the reference's own default has 4 entries and crashes at index 4
+    with pytest.raises(NotImplementedError):
+        f([8, 4, 2, 1, 0.5])
+    with pytest.raises(NotImplementedError):
+        f([16, 8, 4, 2, 2])
+    t = pkg.IFNet._timesteps(0.25, 3)
+    assert list(t) == [0.25, 0.25, 0.25]
+    t = pkg.IFNet._timesteps(torch.tensor([0.25, 0.75]).view(2, 1, 1, 1), 2)
+    assert list(t) == [0.25, 0.75]
+    with pytest.raises(ValueError):
+        pkg.IFNet._timesteps(torch.zeros(3, 1, 1, 1), 2)
+
+
+def test_no_cpu_fallback(pkg):
+    m = pkg.Model()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.inference(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.warp(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(NotImplementedError):
+        m.flownet(torch.zeros(1, 6, 64, 64), training=True)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may import it."""
+    pk = os.path.join(ROOT, "eccv2022-rife_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU", ""), os.path.join(dirpath, f)
+
+
+def test_dropin_modules_import_on_cpu():
+    code = ("import sys; sys.path.insert(0, %r);"
+            "from train_log.RIFE_HDv3 import Model; from train_log.IFNet_HDv3 import IFNet, IFBlock, Head, ResConv;"
+            "from model.warplayer import warp; m = Model(); print(m.version, len(m.flownet.state_dict()))"
+            ) % os.path.join(ROOT, "eccv2022-rife_b200", "dropin")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "4.25 158" in r.stdout
+
+
+def test_shard_range(pkg):
+    for n in (0, 1, 7, 8, 9, 100):
+        for w in (1, 2, 3, 4, 8):
+            spans = [pkg.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        pkg.shard_range(4, 2, 2)
