@@ -254,7 +254,7 @@ int rife_weights_destroy(rife_weights* w) {
 // --------------------------------------------------------------------------------------------------
 // plan
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, c0, act_a, act_b, tmp[5], gridx, gridy, tstep, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, stage_in0, stage_in1,
       stage_out, total;
   int s[5];
 };
@@ -297,6 +297,7 @@ static int plan_layout(int B, int C, int H, int W, float scale, int precision, P
   L->act_a = take(act * E);
   L->act_b = take(act * E);
   for (int i = 0; i < 5; ++i) L->tmp[i] = take(N / ((size_t)L->s[i] * L->s[i]) * TMP_C * E);
+  L->fbuf = take(N * 4 * 4);  // full-resolution fp32 flow carried between the last stages
   L->gridx = take((size_t)W * 4);
   L->gridy = take((size_t)H * 4);
   L->tstep = take((size_t)B * 4);
@@ -478,12 +479,15 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
 
   // ---- 5 IFBlocks (IFNet_HDv3.py:139-157)
   TmpLevel lev[5];
+  float* fbuf = (float*)p->at(L.fbuf);
+  int fbuf_levels = 0;  // number of levels summed in fbuf (0 = nothing stored yet)
   for (int i = 0; i < 5; ++i) {
     const int s = L.s[i], c_ = kBlockC[i];
     const int hs = H / s, wsz = W / s;
     const std::string bn = "b" + std::to_string(i);
     const bool hk = half_act && w->blk_hk[i];
-    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, st));
+    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
+    if (i > 0 && s <= 2) fbuf_levels = i;  // every full-resolution pixel was sampled: fbuf = flow after blocks [0, i)
     ConvIO io;
     io.B = B;
     // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
@@ -513,7 +517,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
       eo.merged = outs->merged;
     }
     if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged)
-      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(c, i + 1, lev, eo, io_dtype, st));
+      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(c, i + 1, lev, eo, io_dtype, fbuf, fbuf_levels, st));
   }
   return RIFE_OK;
 }

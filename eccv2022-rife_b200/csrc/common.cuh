@@ -167,8 +167,10 @@ struct PixelCtx {
 int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
                 void* head_in, cudaStream_t st);
 // builds the s2d block input of block `level` from the lazily-accumulated tmp levels [0, level)
+// `fbuf` ([B][H][W][4] fp32): full-resolution flow summed over levels [0, fbuf_levels); read when fbuf_levels > 0,
+// (re)written with the sum over [0, level) when `fbuf_store` (only valid when every pixel is sampled: s <= 2)
 int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
-                       cudaStream_t st);
+                       float* fbuf, int fbuf_levels, bool fbuf_store, cudaStream_t st);
 // evaluates flow / mask / warped images / merged at full resolution after `nlev` blocks
 struct EvalOut {
   void* flow = nullptr;     // (B,4,H,W)
@@ -177,7 +179,8 @@ struct EvalOut {
   void* warped1 = nullptr;
   void* merged = nullptr;   // (B,C,H,W): w0*sigmoid(mask) + w1*(1-sigmoid(mask))
 };
-int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, cudaStream_t st);
+int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, const float* fbuf,
+                int fbuf_levels, cudaStream_t st);
 
 int launch_warp_op(const void* input, const void* flow, void* out, int B, int C, int H, int W, int dtype,
                    const float* gridx, const float* gridy, cudaStream_t st);

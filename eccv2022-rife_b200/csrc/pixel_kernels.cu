@@ -16,6 +16,10 @@ namespace rife {
 
 namespace {
 
+// fp32 storage => reproduce the reference's arithmetic exactly; fp16 storage => cheaper, rounding-equivalent forms
+template <typename T> struct ExactDiv { static constexpr bool value = true; };
+template <> struct ExactDiv<__half> { static constexpr bool value = false; };
+
 struct Lerp {
   int i0, i1;
   float l0, l1;
@@ -74,9 +78,17 @@ __device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, i
     RIFE_LD16(p00, v00) RIFE_LD16(p01, v01) RIFE_LD16(p10, v10) RIFE_LD16(p11, v11)
 #undef RIFE_LD16
   }
+  if constexpr (ExactDiv<Tt>::value) {
+    // ATen upsample_bilinear2d association (fp32 pipeline: bit-faithful)
 #pragma unroll
-  for (int c = 0; c < N; ++c)
-    out[c] = ly.l0 * (lx.l0 * v00[c] + lx.l1 * v01[c]) + ly.l1 * (lx.l0 * v10[c] + lx.l1 * v11[c]);
+    for (int c = 0; c < N; ++c)
+      out[c] = ly.l0 * (lx.l0 * v00[c] + lx.l1 * v01[c]) + ly.l1 * (lx.l0 * v10[c] + lx.l1 * v11[c]);
+  } else {
+    // fp16-storage pipeline: four tap weights, 4 instead of 6 operations per channel (differs by rounding only)
+    const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+#pragma unroll
+    for (int c = 0; c < N; ++c) out[c] = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
+  }
 }
 
 struct WarpGeom {
@@ -84,8 +96,7 @@ struct WarpGeom {
   float inv_halfw, inv_halfh;  // reciprocals, used by the fp16-storage pipeline (1 ulp of the normalised coordinate)
   float wm1, hm1;              // W-1, H-1
 };
-template <typename T> struct ExactDiv { static constexpr bool value = true; };
-template <> struct ExactDiv<__half> { static constexpr bool value = false; };
+
 
 // One bilinear tap set of warp() on the 8-channel SRC layout.  Follows the reference's arithmetic order:
 // g = base + flow / ((dim-1)/2); ix = ((g+1)/2)*(dim-1); clamp; 4 taps with zero weight beyond the edge.
@@ -134,11 +145,12 @@ struct LevelsArg {
 };
 
 // flow(p) after `nlev` blocks, plus all 16 channels of the newest level (mask = ch 4, feat = ch 5..12)
+// `j0` > 0: `flow` already holds the sum over levels [0, j0) (read from the full-resolution fp32 flow buffer).
 template <typename Tt>
-__device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int b, int y, int x, float (&flow)[4],
+__device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int j0, int b, int y, int x, float (&flow)[4],
                                            float (&last)[16]) {
 #pragma unroll 1
-  for (int j = 0; j < nlev - 1; ++j) {
+  for (int j = j0; j < nlev - 1; ++j) {
     float f[4];
     const Tt* base = reinterpret_cast<const Tt*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
     sample_tmp<Tt, 4>(base, L.h[j], L.w[j], L.s[j], L.rs[j], 0, y, x, f);
@@ -210,7 +222,8 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
                                                           const T* __restrict__ src1, const float* __restrict__ gridx,
                                                           const float* __restrict__ gridy,
                                                           const float* __restrict__ tstep, T* __restrict__ xin, int B,
-                                                          int H, int W, WarpGeom geom, int planar) {
+                                                          int H, int W, WarpGeom geom, int planar,
+                                                          float* __restrict__ fbuf, int fbuf_levels, int fbuf_store) {
   const int Hs = H / s, Ws = W / s;
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, b = blockIdx.z;
@@ -243,7 +256,10 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
       } else {
         // IFNet_HDv3.py:145-147: cat(warped_img0, warped_img1, wf0, wf1, timestep, mask, feat) ++ flow (:82)
         float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
-        eval_state<Tt>(L, level, b, y, x, flow, last);
+        float* fp = fbuf + (((size_t)b * H + y) * W + x) * 4;
+        if (fbuf_levels > 0) ld4(fp, flow);
+        eval_state<Tt>(L, level, fbuf_levels, b, y, x, flow, last);
+        if (fbuf_store) st4(fp, flow);   // full-resolution flow after `level` blocks, reused by the next stage
         const float gx = gridx[x], gy = gridy[y];
         float a[8], c[8];
         warp8<T>(s0, H, W, geom, gx, gy, flow[0], flow[1], a);
@@ -307,13 +323,15 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
                                                    const float* __restrict__ gridy, Tio* __restrict__ oflow,
                                                    Tio* __restrict__ omask, Tio* __restrict__ ow0,
                                                    Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
-                                                   int H, int W, WarpGeom geom) {
+                                                   int H, int W, WarpGeom geom, const float* __restrict__ fbuf,
+                                                   int fbuf_levels) {
   const size_t plane = (size_t)H * W;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
   float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
-  eval_state<Tt>(L, nlev, b, y, x, flow, last);
+  if (fbuf_levels > 0) ld4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow);
+  eval_state<Tt>(L, nlev, fbuf_levels, b, y, x, flow, last);
   const size_t pix = (size_t)y * W + x;
   if (oflow) {
 #pragma unroll
@@ -473,23 +491,26 @@ static LevelsArg pack_levels(const TmpLevel* levels, int n) {
 }
 
 int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
-                       cudaStream_t st) {
+                       float* fbuf, int fbuf_levels, bool fbuf_store, cudaStream_t st) {
   LevelsArg L = pack_levels(levels, level);
   WarpGeom g = make_geom(c.H, c.W);
   const dim3 grid(nblk((size_t)(c.W / s), 128), (unsigned)(c.H / s), (unsigned)c.B);
   if (c.half_act)
     block_input_kernel<__half, __half><<<grid, 128, 0, st>>>(L, level, s, (const __half*)c.src0,
                                                                       (const __half*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                      (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
+                                                                      (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,
+                                                                      fbuf, fbuf_levels, fbuf_store ? 1 : 0);
   else
     block_input_kernel<float, float><<<grid, 128, 0, st>>>(L, level, s, (const float*)c.src0,
                                                                     (const float*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                    (float*)xin, c.B, c.H, c.W, g, planar ? 1 : 0);
+                                                                    (float*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,
+                                                                    fbuf, fbuf_levels, fbuf_store ? 1 : 0);
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }
 
-int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, cudaStream_t st) {
+int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalOut& o, int io_dtype, const float* fbuf,
+                int fbuf_levels, cudaStream_t st) {
   const size_t n = (size_t)c.B * c.H * c.W;
   LevelsArg L = pack_levels(levels, nlev);
   WarpGeom g = make_geom(c.H, c.W);
@@ -497,7 +518,8 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
 #define RIFE_EVAL(T, TIO)                                                                                         \
   eval_kernel<T, T, TIO><<<egrid, 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
                                                        c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
-                                                       (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g)
+                                                       (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, \
+                                                       fbuf_levels)
   if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
   else if (!c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(float, __half);
   else if (c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(__half, float);
