@@ -10,6 +10,8 @@
 // left-to-right summation order as the reference's `flow = flow + fd`) for exactly the pixels it needs.
 // For s >= 4 the 1/s resize only touches the centre 2x2 of each s x s cell, so the full-resolution
 // tensors are never needed.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rife {
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 
 // ---------------------------------------------------------------------------------------------------
 // block input: one thread per low-resolution pixel of the (H/s, W/s) block input.
-template <typename T, typename Tt>
+template <typename T, typename Tt, int NS, bool LEVEL0>
 __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level, int s, const T* __restrict__ src0,
                                                           const T* __restrict__ src1, const float* __restrict__ gridx,
                                                           const float* __restrict__ gridy,
@@ -231,8 +233,8 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
   const T* s0 = src0 + (size_t)b * H * W * SRC_C;
   const T* s1 = src1 + (size_t)b * H * W * SRC_C;
   const float t = tstep[b];
-  const int ns = (s == 1) ? 1 : 2;            // samples per axis: F.interpolate(1/s) reads the centre 2x2 (lambda = 0.5)
-  const int off = (s == 1) ? 0 : (s / 2 - 1);
+  constexpr int ns = NS;                      // samples per axis: F.interpolate(1/s) reads the centre 2x2 (lambda = 0.5)
+  const int off = (NS == 1) ? 0 : (s / 2 - 1);
   float acc[28];
   float row[28];
 #pragma unroll 1
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
     for (int sx = 0; sx < ns; ++sx) {
       const int y = Y * s + off + sy, x = X * s + off + sx;
       float v[28];
-      if (level == 0) {
+      if constexpr (LEVEL0) {
         // IFNet_HDv3.py:141: cat(img0[:, :3], img1[:, :3], f0, f1, timestep)
         float a[8], c[8];
         ld8(s0 + (y * W + x) * SRC_C, a);
@@ -313,6 +315,167 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
 #pragma unroll
   for (int i = 4; i < 8; ++i) o[i] = 0.f;
   st8(dst + 3 * gstride, o);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// fp16-storage fast path of the block-input gather (level >= 1).  Same semantics as block_input_kernel, with
+//   * the four samples of the 1/s resize sharing their bilinear taps of every coarser tmp level (a 2x2 sample
+//     block never straddles a cell of a coarser level), and mask/feat averaged through the mean tap weights;
+//   * warp taps blended with packed half2 FMAs (values in [0,1], weights to 11 bits: below the fp16 storage
+//     rounding of the block input itself); coordinates and flow stay fp32.
+struct Lerp2 {  // two adjacent positions d, d+1 sharing their taps
+  int i0, i1;
+  float a0, a1;  // lambda1 of position d and d+1
+};
+__device__ __forceinline__ Lerp2 make_lerp2(int d, int in_size, float rs) {
+  const Lerp l0 = make_lerp(d, in_size, rs), l1 = make_lerp(d + 1, in_size, rs);
+  Lerp2 r;
+  r.i0 = l0.i0; r.i1 = l0.i1; r.a0 = l0.l1; r.a1 = l1.l1;
+  return r;
+}
+__device__ __forceinline__ void warp8_h2(const __half* __restrict__ src, int H, int W, const WarpGeom& g, float gx,
+                                         float gy, float fx, float fy, __half2 (&out)[4]) {
+  const float nx = gx + __fmul_rn(fx, g.inv_halfw);
+  const float ny = gy + __fmul_rn(fy, g.inv_halfh);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
+  ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float ax = ix - x0f, ay = iy - y0f;
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int dx = (x0 + 1 < W) ? SRC_C : 0, dy = (y0 + 1 < H) ? W * SRC_C : 0;  // beyond the edge: weight is 0 anyway
+  const __half* p = src + (y0 * W + x0) * SRC_C;
+  const uint4 u00 = *reinterpret_cast<const uint4*>(p), u01 = *reinterpret_cast<const uint4*>(p + dx);
+  const uint4 u10 = *reinterpret_cast<const uint4*>(p + dy), u11 = *reinterpret_cast<const uint4*>(p + dy + dx);
+  const __half2 w00 = __float2half2_rn((1.f - ax) * (1.f - ay)), w01 = __float2half2_rn(ax * (1.f - ay));
+  const __half2 w10 = __float2half2_rn((1.f - ax) * ay), w11 = __float2half2_rn(ax * ay);
+  const __half2 *h00 = reinterpret_cast<const __half2*>(&u00), *h01 = reinterpret_cast<const __half2*>(&u01);
+  const __half2 *h10 = reinterpret_cast<const __half2*>(&u10), *h11 = reinterpret_cast<const __half2*>(&u11);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    out[i] = __hfma2(w11, h11[i], __hfma2(w10, h10[i], __hfma2(w01, h01[i], __hmul2(w00, h00[i]))));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) block_input_h_kernel(LevelsArg L, int level, int s,
+                                                            const __half* __restrict__ src0,
+                                                            const __half* __restrict__ src1,
+                                                            const float* __restrict__ gridx,
+                                                            const float* __restrict__ gridy,
+                                                            const float* __restrict__ tstep, __half* __restrict__ xin,
+                                                            int B, int H, int W, WarpGeom geom, int planar,
+                                                            float* __restrict__ fbuf, int fbuf_levels, int fbuf_store) {
+  constexpr int NQ = NS * NS;
+  const int Hs = H / s, Ws = W / s;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Ws) return;
+  const __half* s0 = src0 + (size_t)b * H * W * SRC_C;
+  const __half* s1 = src1 + (size_t)b * H * W * SRC_C;
+  const int off = (NS == 1) ? 0 : (s / 2 - 1);
+  const int x0 = X * s + off, y0 = Y * s + off;
+  float flow[NQ][4];
+  if (fbuf_levels > 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) ld4(fbuf + (((size_t)b * H + y0 + q / NS) * W + x0 + q % NS) * 4, flow[q]);
+  }
+  float mf[12];  // channels 4..15 of the newest level (mask, feat x8, pad), averaged over the samples
+#pragma unroll 1
+  for (int j = fbuf_levels; j < level; ++j) {
+    const __half* base = reinterpret_cast<const __half*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
+    const int h = L.h[j], w = L.w[j], sj = L.s[j];
+    const float sc = L.sc[j];
+    const bool newest = j == level - 1;
+    if (sj == 1) {  // only possible as the newest level of a scale-1 eval; not reached from block inputs
+      continue;
+    }
+    const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
+    if (NS == 2 && sj == s) {
+      // the newest level may be as fine as the sample spacing allows only when s_j > s; s_j == s cannot occur
+    }
+    const __half* r0 = base + ly.i0 * w * TMP_C;
+    const __half* r1 = base + ly.i1 * w * TMP_C;
+    float v00[4], v01[4], v10[4], v11[4];
+    ld4(r0 + lx.i0 * TMP_C, v00); ld4(r0 + lx.i1 * TMP_C, v01);
+    ld4(r1 + lx.i0 * TMP_C, v10); ld4(r1 + lx.i1 * TMP_C, v11);
+    float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
+      const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
+      wsum[0] += w00; wsum[1] += w01; wsum[2] += w10; wsum[3] += w11;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float f = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
+        flow[q][c] = (j == 0) ? f * sc : fmaf(f, sc, flow[q][c]);
+      }
+    }
+    if (newest) {
+      const float inv = 1.f / (float)NQ;
+      const float a00 = wsum[0] * inv, a01 = wsum[1] * inv, a10 = wsum[2] * inv, a11 = wsum[3] * inv;
+      float t00[4], t01[4], t10[4], t11[4], u00[8], u01[8], u10[8], u11[8];
+      ld4(r0 + lx.i0 * TMP_C + 4, t00); ld4(r0 + lx.i1 * TMP_C + 4, t01);
+      ld4(r1 + lx.i0 * TMP_C + 4, t10); ld4(r1 + lx.i1 * TMP_C + 4, t11);
+      ld8(r0 + lx.i0 * TMP_C + 8, u00); ld8(r0 + lx.i1 * TMP_C + 8, u01);
+      ld8(r1 + lx.i0 * TMP_C + 8, u10); ld8(r1 + lx.i1 * TMP_C + 8, u11);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mf[c] = fmaf(a11, t11[c], fmaf(a10, t10[c], fmaf(a01, t01[c], a00 * t00[c])));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mf[4 + c] = fmaf(a11, u11[c], fmaf(a10, u10[c], fmaf(a01, u01[c], a00 * u00[c])));
+    }
+  }
+  // warps + accumulation over the samples
+  __half2 A[4], Cc[4];
+  const __half2 qw = __float2half2_rn(1.f / (float)NQ);
+  float fs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int y = y0 + q / NS, x = x0 + q % NS;
+    if (fbuf_store) st4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow[q]);
+    const float gx = gridx[x], gy = gridy[y];
+    __half2 a[4], c[4];
+    warp8_h2(s0, H, W, geom, gx, gy, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
+    warp8_h2(s1, H, W, geom, gx, gy, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (NQ == 1) { A[i] = a[i]; Cc[i] = c[i]; }
+      else if (q == 0) { A[i] = __hmul2(qw, a[i]); Cc[i] = __hmul2(qw, c[i]); }
+      else { A[i] = __hfma2(qw, a[i], A[i]); Cc[i] = __hfma2(qw, c[i], Cc[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fs[i] += flow[q][i];
+  }
+  // interpolate(flow, 1/s) * 1/s   (IFNet_HDv3.py:81)
+  const float fsc = 1.f / ((float)NQ * (float)s);
+  const float t = tstep[b];
+  __half2 o[16];
+  o[0] = A[2];                                   // warped img0 r, g
+  o[1] = __halves2half2(__low2half(A[3]), __low2half(Cc[2]));   // img0 b, img1 r
+  o[2] = __halves2half2(__high2half(Cc[2]), __low2half(Cc[3])); // img1 g, b
+  o[3] = A[0]; o[4] = A[1];                      // warped f0
+  o[5] = Cc[0]; o[6] = Cc[1];                    // warped f1
+  o[7] = __floats2half2_rn(t, mf[0]);            // timestep, mask
+  o[8] = __floats2half2_rn(mf[1], mf[2]);        // feat 0..7
+  o[9] = __floats2half2_rn(mf[3], mf[4]);
+  o[10] = __floats2half2_rn(mf[5], mf[6]);
+  o[11] = __floats2half2_rn(mf[7], mf[8]);
+  o[12] = __floats2half2_rn(fs[0] * fsc, fs[1] * fsc);
+  o[13] = __floats2half2_rn(fs[2] * fsc, fs[3] * fsc);
+  o[14] = __float2half2_rn(0.f);
+  o[15] = o[14];
+  const int par = (Y & 1) * 2 + (X & 1);
+  const size_t hw2 = (size_t)(Hs >> 1) * (Ws >> 1), pix2 = (size_t)(Y >> 1) * (Ws >> 1) + (X >> 1);
+  __half* dst = planar ? xin + (((size_t)b * 16 + par * 4) * hw2 + pix2) * 8 : xin + (((size_t)b * hw2 + pix2) * 4 + par) * XIN_C;
+  const size_t gstride = planar ? hw2 * 8 : 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 u;
+    __half2* hh = reinterpret_cast<__half2*>(&u);
+    hh[0] = o[4 * k]; hh[1] = o[4 * k + 1]; hh[2] = o[4 * k + 2]; hh[3] = o[4 * k + 3];
+    *reinterpret_cast<uint4*>(dst + k * gstride) = u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -495,16 +658,27 @@ int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int
   LevelsArg L = pack_levels(levels, level);
   WarpGeom g = make_geom(c.H, c.W);
   const dim3 grid(nblk((size_t)(c.W / s), 128), (unsigned)(c.H / s), (unsigned)c.B);
-  if (c.half_act)
-    block_input_kernel<__half, __half><<<grid, 128, 0, st>>>(L, level, s, (const __half*)c.src0,
-                                                                      (const __half*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                      (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,
-                                                                      fbuf, fbuf_levels, fbuf_store ? 1 : 0);
-  else
-    block_input_kernel<float, float><<<grid, 128, 0, st>>>(L, level, s, (const float*)c.src0,
-                                                                    (const float*)c.src1, c.gridx, c.gridy, c.tstep,
-                                                                    (float*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,
-                                                                    fbuf, fbuf_levels, fbuf_store ? 1 : 0);
+#define RIFE_BI(T, NS_, L0_)                                                                                       \
+  block_input_kernel<T, T, NS_, L0_><<<grid, 128, 0, st>>>(L, level, s, (const T*)c.src0, (const T*)c.src1, c.gridx,   \
+                                                           c.gridy, c.tstep, (T*)xin, c.B, c.H, c.W, g, planar ? 1 : 0, \
+                                                           fbuf, fbuf_levels, fbuf_store ? 1 : 0)
+  const bool l0 = level == 0, s1 = s == 1;
+  static const bool no_fast = getenv("RIFE_NO_FAST_INPUT") != nullptr;
+  if (c.half_act && !l0 && !no_fast) {
+#define RIFE_BIH(NS_)                                                                                                 \
+  block_input_h_kernel<NS_><<<grid, 128, 0, st>>>(L, level, s, (const __half*)c.src0, (const __half*)c.src1, c.gridx, \
+                                                  c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,   \
+                                                  fbuf, fbuf_levels, fbuf_store ? 1 : 0)
+    if (s1) RIFE_BIH(1); else RIFE_BIH(2);
+#undef RIFE_BIH
+  } else if (c.half_act) {
+    if (l0 && s1) RIFE_BI(__half, 1, true); else if (l0) RIFE_BI(__half, 2, true);
+    else if (s1) RIFE_BI(__half, 1, false); else RIFE_BI(__half, 2, false);
+  } else {
+    if (l0 && s1) RIFE_BI(float, 1, true); else if (l0) RIFE_BI(float, 2, true);
+    else if (s1) RIFE_BI(float, 1, false); else RIFE_BI(float, 2, false);
+  }
+#undef RIFE_BI
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }
