@@ -474,6 +474,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     io.in = p->at(L.head_b); io.out = p->at(L.head_a);
     RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, c.planar_head, st));
     io.in = p->at(L.head_a); io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
+    io.res = c.planar_head ? p->at(L.head_in) : nullptr;  // halo kernel: assembles the full SRC pixel (see conv_halo.cu)
     RIFE_STAGE("head.cnn3", run_conv(p, w->head[3], io, c.planar_head, st));
   }
 

@@ -256,11 +256,27 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
     const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * c.x + 2 * (par & 1) + (sub & 1);
     store16h(p.out + (((size_t)c.b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
   } else if constexpr (EPI == EPI_HEADT) {
+    // Head.cnn3 (ConvTranspose 16 -> 4): writes the complete 8-channel SRC pixel [f0..f3 | r g b a] of the four
+    // full-resolution pixels (2y+py, 2x+px); the image channels come from the s2d Head input (p.res, planar-8
+    // [2B][2][H][W][8]: ch par*3+c = RGB of pixel par, ch 12+par = alpha), so the input-packing kernel never
+    // touches SRC and every store is a full 16-byte pixel.
+    const size_t hp = ((size_t)c.b * 2 * p.H + y) * p.W + c.x;
+    float im[16];
+    {
+      float a[8];
+      ld8(p.res + hp * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) im[i] = a[i];
+      ld8(p.res + (hp + (size_t)p.H * p.W) * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) im[8 + i] = a[i];
+    }
 #pragma unroll
     for (int par = 0; par < 4; ++par) {
       const int oy = 2 * y + (par >> 1), ox = 2 * c.x + (par & 1);
-      float f[4] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3]};
-      st4(p.out + (((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c, f);
+      float f[8] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3],
+                    im[par * 3], im[par * 3 + 1], im[par * 3 + 2], im[12 + par]};
+      st8(p.out + (((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * SRC_C, f);
     }
   } else if constexpr (EPI == EPI_CONVT) {
     for (int i = 0; i < 16; ++i) {
@@ -624,6 +640,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
   if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES needs beta and res");
   if (io.epi == EPI_RES && L.cin != io.out_c) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES is the c -> c ResConv (residual = input)");
+  if (io.epi == EPI_HEADT && !io.res) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_HEADT needs the s2d Head input as io.res");
   if (io.epi == EPI_HEADT && L.ncols != 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_HEADT expects N = 16");
   HaloParams p{};
   p.B = io.B; p.H = io.H; p.W = io.W;

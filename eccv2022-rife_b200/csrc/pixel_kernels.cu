@@ -174,7 +174,7 @@ template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                    T* __restrict__ src0, T* __restrict__ src1,
                                                    T* __restrict__ head_in, int B, int C, int H, int W,
-                                                   int planar) {
+                                                   int planar, int write_src) {
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)B * H2 * W2;
@@ -199,9 +199,11 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
       const Tio* p = img + (size_t)b * C * plane + (size_t)y * W + x;
       for (int c = 0; c < C; ++c) v[4 + c] = to_f(p[c * plane]);
-      st8(src + (((size_t)b * H + y) * W + x) * SRC_C, v);
+      // fused mode: Head.cnn3's epilogue assembles the whole SRC pixel (feature + image) from the s2d Head input
+      if (write_src) st8(src + (((size_t)b * H + y) * W + x) * SRC_C, v);
 #pragma unroll
       for (int c = 0; c < 3; ++c) hv[(py * 2 + px) * 3 + c] = v[4 + c];
+      hv[12 + py * 2 + px] = v[7];  // alpha rides in the 4 spare channels (Head.cnn0 has zero weights there)
     }
   }
   // pixel-major [2B][H/2][W/2][16] or planar-8 [2B][2][H/2][W/2][8] (conv_halo.cu)
@@ -629,7 +631,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   dim3 grid(nblk(nq, 256), 2);
 #define RIFE_PREP(TIO, T)                                                                                        \
   prep_kernel<TIO, T><<<grid, 256, 0, st>>>((const TIO*)img0, (const TIO*)img1, (T*)src0, (T*)src1, (T*)head_in, \
-                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0)
+                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1)
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
