@@ -461,7 +461,56 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) mbar_wait(smem_u32(&a_full[stage]), phase);  // acquire the TMA-written tile
       mbar_wait_t(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u, t_tf);
       tc_fence_after();
-      if constexpr (KIND >= 0 && EPI >= 0) {
+      if constexpr (KIND == 2 && EPI == EPI_PS) {
+        // ConvTranspose + PixelShuffle: every input pixel yields a 4x4 patch of 16-channel tmp pixels (32 B each).
+        // Stage one output row (py, dy') of the warp's 4 x 8 input pixels in smem, then write 512 contiguous bytes
+        // per store instruction (a thread-per-pixel store would touch 32 different 128-byte lines per instruction).
+        __shared__ uint4 ps_stage[4][4][64];
+        uint4(*stg)[64] = ps_stage[q];
+        const int tyl = lane >> 3;
+        const int swz_w = (tx_ + 2 * tyl) & 7;
+#pragma unroll 1
+        for (int mi = 0; mi < MT; ++mi) {
+          const int yw = (ty * MT + mi) * TH + q * 4;  // first input row of this warp
+#pragma unroll 1
+          for (int r = 0; r < 4; ++r) {
+            const int py = r >> 1, dyp = r & 1;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int j = (py * 2 + (o >> 1)) * 4 + dyp * 2 + (o & 1);
+              float v[16];
+              tmem_ld16(trow + (uint32_t)((buf * MT + mi) * 256 + j * 16), v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(s_bias + j * 16 + 4 * i);
+                v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
+                stg[tyl][((tx_ * 4 + o) * 2 + h) ^ swz_w] = u;
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int idx = k * 32 + lane;
+              const int row = idx >> 6, col = idx & 63, txc = col >> 3;
+              const uint4 u = stg[row][col ^ ((txc + 2 * row) & 7)];
+              const int y = yw + row, x = tx * TW + txc;
+              if (y < p.H && x < p.W) {
+                const int oy = 4 * y + 2 * py + dyp;
+                __half* dst = p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * TMP_C + col * 8;
+                *reinterpret_cast<uint4*>(dst) = u;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else if constexpr (KIND >= 0 && EPI >= 0) {
         constexpr int NCOLS = KIND == 2 ? 256 : NE;
         c.y0 = ty * MT * TH + ty_;
 #pragma unroll
@@ -565,7 +614,7 @@ bool halo_fits(const HostLayer& h, bool ps_layout) {
   const int a_stage = (h.cin / 8) * (TH + R) * (TW + R) * 16;
   const int w_bytes = ps_layout ? 16 * (h.cin / 8) * 64 * 16 : h.taps * (h.cin / 8) * h.npad * 16;
   if (!ps_layout && h.npad > 128) return false;
-  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET;
+  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET - (ps_layout ? 16 * 1024 : 0);
 }
 
 int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
@@ -629,7 +678,10 @@ static int set_smem_attr(const void* fn) {
   cudaGetDevice(&dev);
   for (auto& s : seen)
     if (s.first == fn && s.second == dev) return RIFE_OK;
-  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+  cudaFuncAttributes fa;
+  RIFE_CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+  const int max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // 227 KB opt-in limit per CTA, static part included
+  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   seen.emplace_back(fn, dev);
   return RIFE_OK;
 }
@@ -669,7 +721,8 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.mt * L.ncols) p.tmem_cols <<= 1;
   const int w_al = (L.w_bytes + 1023) / 1024 * 1024;
-  int stages = (SMEM_BUDGET - w_al - 2048) / p.a_stage_bytes;
+  const int budget = SMEM_BUDGET - (io.epi == EPI_PS ? 16 * 1024 : 0);  // the PixelShuffle epilogue stages rows in 16 KB of static smem
+  int stages = (budget - w_al - 2048) / p.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
   int smem = w_al + stages * p.a_stage_bytes + 1024;

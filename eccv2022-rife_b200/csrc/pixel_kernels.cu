@@ -219,6 +219,56 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
   st8(hp + gstride, a);
 }
 
+
+// fp16 fused-mode input packing: NCHW frames -> planar-8 s2d Head input [2B][2][H/2][W/2][8] only (SRC is assembled
+// by Head.cnn3's epilogue).  One thread converts a 2 x 8 pixel strip: 16-byte loads per channel row, 16-byte stores.
+template <typename Tio>
+__global__ void __launch_bounds__(256) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
+                                                          __half* __restrict__ head_in, int B, int C, int H, int W) {
+  const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
+  const int xs = blockIdx.x * blockDim.x + threadIdx.x;  // strip index along x (8 pixels)
+  const int y2 = blockIdx.y, fb = blockIdx.z;            // fb = frame * B + b
+  if (xs >= W8) return;
+  const int frame = fb / B, b = fb - frame * B;
+  const Tio* img = (frame ? img1 : img0) + (size_t)b * C * H * W;
+  float px[2][4][8];  // [row][channel][x]
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < C) {
+        const Tio* p = img + ((size_t)c * H + 2 * y2 + r) * W + xs * 8;
+        if constexpr (sizeof(Tio) == 2) {
+          ld8(reinterpret_cast<const __half*>(p), px[r][c]);
+        } else {
+          ld8(reinterpret_cast<const float*>(p), px[r][c]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) px[r][c][i] = 0.f;
+      }
+    }
+  __half* o = head_in + (((size_t)fb * 2 * H2 + y2) * W2 + xs * 4) * 8;
+  const size_t gstride = (size_t)H2 * W2 * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // 4 s2d pixels of this strip
+    float hv[16];
+#pragma unroll
+    for (int par = 0; par < 4; ++par) {
+      const int r = par >> 1, xx = 2 * k + (par & 1);
+      hv[par * 3 + 0] = px[r][0][xx]; hv[par * 3 + 1] = px[r][1][xx]; hv[par * 3 + 2] = px[r][2][xx];
+      hv[12 + par] = px[r][3][xx];
+    }
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = hv[i];
+    st8(o + k * 8, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = hv[8 + i];
+    st8(o + gstride + k * 8, a);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // block input: one thread per low-resolution pixel of the (H/s, W/s) block input.
 template <typename T, typename Tt, int NS, bool LEVEL0>
@@ -627,6 +677,17 @@ inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
                 void* head_in, cudaStream_t st) {
+  if (c.planar_head && c.half_act && c.W % 8 == 0) {
+    const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)(2 * c.B));
+    if (io_dtype == RIFE_F16)
+      prep_planar_kernel<__half><<<g, 256, 0, st>>>((const __half*)img0, (const __half*)img1, (__half*)head_in, c.B, c.C, c.H, c.W);
+    else if (io_dtype == RIFE_F32)
+      prep_planar_kernel<float><<<g, 256, 0, st>>>((const float*)img0, (const float*)img1, (__half*)head_in, c.B, c.C, c.H, c.W);
+    else
+      RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
+    RIFE_LAUNCH_CHECK();
+    return RIFE_OK;
+  }
   const size_t nq = (size_t)c.B * (c.H / 2) * (c.W / 2);
   dim3 grid(nblk(nq, 256), 2);
 #define RIFE_PREP(TIO, T)                                                                                        \
