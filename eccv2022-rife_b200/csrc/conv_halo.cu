@@ -28,7 +28,7 @@ namespace {
 
 constexpr int TW = 8, TH = 16;  // M-tile: 16 rows x 8 pixels = 128 GEMM rows, row m = ty*8 + tx
 constexpr int MAX_MMA = 128;    // (schedule entries) x (K steps) per M-tile
-constexpr int NUM_THREADS = 192;
+constexpr int MAX_THREADS = 64 + 32 * 8;  // 2 control warps + 4 or 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ENTRIES = 16;
 constexpr int SMEM_BUDGET = 220 * 1024;
@@ -305,8 +305,12 @@ __device__ __forceinline__ void epi_chunk_rt(const HaloParams& p, const EpiCtx& 
 
 // KIND < 0: generic table-driven schedule (any layer that fits); otherwise the compile-time schedule <KIND,KSTEPS,NE,MT>
 // EPI >= 0 additionally fixes the epilogue at compile time (fully unrolled over M-tiles and 16-column chunks).
+// Epilogue warps: 4 (one per SM sub-partition); the column-heavy PixelShuffle epilogue (256 columns per M-tile) uses 8,
+// warps w and w+4 sharing a TMEM lane quarter and splitting the output rows.
+template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS) ? 8 : 4; };
+
 template <int KIND, int KSTEPS, int NE, int MT, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_STAGES];
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
   __shared__ uint32_t tab_a[MAX_MMA];               // A start-address field relative to the stage base (16-byte units)
   __shared__ uint32_t tab_d[MAX_MMA];               // accumulator column offset | (accumulate << 31)
 
+  constexpr int NUM_EPI_WARPS = EpiWarps<EPI>::value;
+  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = w_smem + (((uint32_t)p.w_bytes + 1023u) & ~1023u);
@@ -332,12 +338,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       mbar_init(smem_u32(&a_full[s]), 1);
       // ResConv epilogues read the residual (= centre tap of the input tile) from the smem stage itself, so the
       // stage is released by the MMA commit AND the four epilogue warps
-      mbar_init(smem_u32(&a_empty[s]), p.epi == EPI_RES ? 5 : 1);
+      mbar_init(smem_u32(&a_empty[s]), p.epi == EPI_RES ? 1 + NUM_EPI_WARPS : 1);
     }
     mbar_init(smem_u32(&w_full), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&t_full[i]), 1);
-      mbar_init(smem_u32(&t_empty[i]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&t_empty[i]), NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -439,8 +445,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       }
     }
   } else {
-    // ---------------- epilogue warps: TMEM lanes 32*(warp%4)..+31
+    // ---------------- epilogue warps: TMEM lanes 32*(warp%4)..+31; warps w and w+4 share a lane quarter and split
+    // the 16-column chunks (even / odd) between them
     const int q = warp & 3;
+    const int ehalf = (warp - 2) >> 2;
+    constexpr int ESPLIT = NUM_EPI_WARPS / 4;  // 1 or 2 warps per lane quarter
     const int m = q * 32 + lane;
     const int ty_ = m >> 3, tx_ = m & 7;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -465,15 +474,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         // ConvTranspose + PixelShuffle: every input pixel yields a 4x4 patch of 16-channel tmp pixels (32 B each).
         // Stage one output row (py, dy') of the warp's 4 x 8 input pixels in smem, then write 512 contiguous bytes
         // per store instruction (a thread-per-pixel store would touch 32 different 128-byte lines per instruction).
-        __shared__ uint4 ps_stage[4][4][64];
-        uint4(*stg)[64] = ps_stage[q];
+        __shared__ uint4 ps_stage[NUM_EPI_WARPS][4][64];
+        uint4(*stg)[64] = ps_stage[warp - 2];
         const int tyl = lane >> 3;
         const int swz_w = (tx_ + 2 * tyl) & 7;
 #pragma unroll 1
         for (int mi = 0; mi < MT; ++mi) {
           const int yw = (ty * MT + mi) * TH + q * 4;  // first input row of this warp
 #pragma unroll 1
-          for (int r = 0; r < 4; ++r) {
+          for (int r = (4 / ESPLIT) * ehalf; r < (4 / ESPLIT) * (ehalf + 1); ++r) {
             const int py = r >> 1, dyp = r & 1;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         for (int mi = 0; mi < MT; ++mi) {
 #pragma unroll
           for (int j = 0; j < NCOLS / 16; ++j) {
+            if (ESPLIT == 2 && ((mi * (NCOLS / 16) + j) & 1) != ehalf) continue;
             float v[16];
             tmem_ld16(trow + (uint32_t)((buf * MT + mi) * NCOLS + j * 16), v);
             epi_chunk<EPI>(p, c, s_bias, s_beta, pitch, mi, j, v);
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
         }
       } else {
         c.y0 = ty * p.mt * TH + ty_;
-        for (int jm = 0; jm < nchunk16 * p.mt; ++jm) {
+        for (int jm = ehalf; jm < nchunk16 * p.mt; jm += ESPLIT) {
           const int mi = jm / nchunk16, j = jm - mi * nchunk16;
           float v[16];
           __syncwarp();
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_halo_kernel(const __grid_con
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    if (p.dbg && warp == 2 && lane == 0) {
+    if (p.dbg && warp == 2 && lane == 0) {  // timers of the first epilogue warp
       p.dbg[blockIdx.x * 8 + 5] = t_tf;
       p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
       p.dbg[blockIdx.x * 8 + 7] = it;
@@ -614,7 +624,7 @@ bool halo_fits(const HostLayer& h, bool ps_layout) {
   const int a_stage = (h.cin / 8) * (TH + R) * (TW + R) * 16;
   const int w_bytes = ps_layout ? 16 * (h.cin / 8) * 64 * 16 : h.taps * (h.cin / 8) * h.npad * 16;
   if (!ps_layout && h.npad > 128) return false;
-  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET - (ps_layout ? 16 * 1024 : 0);
+  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET - (ps_layout ? 32 * 1024 : 0);
 }
 
 int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
@@ -721,7 +731,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.mt * L.ncols) p.tmem_cols <<= 1;
   const int w_al = (L.w_bytes + 1023) / 1024 * 1024;
-  const int budget = SMEM_BUDGET - (io.epi == EPI_PS ? 16 * 1024 : 0);  // the PixelShuffle epilogue stages rows in 16 KB of static smem
+  const int budget = SMEM_BUDGET - (io.epi == EPI_PS ? 32 * 1024 : 0);  // the PixelShuffle epilogue stages rows in 32 KB of static smem
   int stages = (budget - w_al - 2048) / p.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
@@ -771,7 +781,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #define RIFE_HK_CASE(K, KS, N_, MT_, E_)                                                                     \
   if (!done && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {                   \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_>));                              \
-    conv_halo_kernel<K, KS, N_, MT_, E_><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);                         \
+    conv_halo_kernel<K, KS, N_, MT_, E_><<<grid, 64 + 32 * EpiWarps<E_>::value, smem, st>>>(tm_a, p);                         \
     done = true;                                                                                             \
   }
   RIFE_HK_CASE(1, 1, 16, 2, EPI_LRELU)      // Head.cnn0            (s2d, cin 16 -> 16)
@@ -788,7 +798,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #undef RIFE_HK_CASE
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
-    conv_halo_kernel<-1, 0, 0, 0, -1><<<grid, NUM_THREADS, smem, st>>>(tm_a, p);
+    conv_halo_kernel<-1, 0, 0, 0, -1><<<grid, 64 + 32 * EpiWarps<-1>::value, smem, st>>>(tm_a, p);
   }
   RIFE_LAUNCH_CHECK();
   if (debug) {
