@@ -149,10 +149,10 @@ class IFNet(nn.Module):
         self._weights[key] = (h, stamp)
         return h
 
-    def _get_plan(self, device, prec, b, c, h, w, scale):
+    def _get_plan(self, device, prec, b, c, h, w, scale, slot=0):
         lib = _lib.load()
         wh = self._get_weights(device, prec)
-        key = ((device.index, prec), b, c, h, w, float(scale))
+        key = ((device.index, prec), b, c, h, w, float(scale), slot)
         pl = self._plans.get(key)
         if pl is not None:
             return pl

@@ -50,16 +50,18 @@ class Model:
         """RIFE_HDv3.py:56-60.  Positional order (img0, img1, timestep, scale) is the reference's."""
         return self.flownet.run(img0, img1, timestep, scale, want_all=False)
 
-    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None):
+    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0):
         """End-to-end call on HOST (ideally pinned) NCHW tensors: H2D copies, inference and the D2H copy of the
-        result are enqueued on `stream` (default: current) by rife_inference_host; returns without syncing."""
+        result are enqueued on `stream` (default: current) by rife_inference_host; returns without syncing.
+        `slot` selects an independent plan (workspace + staging buffers): calls with different slots on different
+        streams overlap their PCIe copies with each other's compute."""
         net = self.flownet
         if img0_host.is_cuda or out_host.is_cuda:
             raise ValueError("inference_host takes host tensors")
         lib = _lib.load()
         b, c, h, w = img0_host.shape
         prec = net._resolve_precision(img0_host.dtype)
-        pl = net._get_plan(device, prec, b, c, h, w, scale)
+        pl = net._get_plan(device, prec, b, c, h, w, scale, slot)
         io = _lib.RIFE_F32 if img0_host.dtype == torch.float32 else _lib.RIFE_F16
         ts = net._timesteps(timestep, b)
         with torch.cuda.device(device):
