@@ -321,8 +321,12 @@ def main():
     rk = "b4.input"
     k_ms = stage_ms.get(rk, 0.0) / max(stage_launches.get(rk, 1), 1)
     achieved = alg[rk] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp) and P == 4 and args.precision == "fp16":
+        traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[rk], "kernel_ms": k_ms,
                 "top_stage_by_time": top,
                 "pipeline_model": {"bytes_per_pair_stage_fused_model": BYTES_PER_PIXEL_MODEL * H * W * esz,
