@@ -10,5 +10,6 @@ from .ifnet import IFNet, IFBlock, Head, ResConv
 from .model import Model
 from .warplayer import warp
 from .sharding import shard_range, run_sharded
+from . import eccv
 
 __all__ = ["Model", "IFNet", "IFBlock", "Head", "ResConv", "warp", "RifeError", "shard_range", "run_sharded"]

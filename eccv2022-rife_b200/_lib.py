@@ -17,6 +17,8 @@ SYMBOLS = [
     "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_plan_set_profiling",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
+    "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
+    "rife_nhwc_resize", "rife_nhwc_warp", "rife_nhwc_s2d", "rife_eccv_merge",
 ]
 
 
@@ -62,6 +64,15 @@ def load():
     lib.rife_resize_bilinear.argtypes = [vp, vp, i, i, i, i, i, i, f, vp]
     lib.rife_conv3x3.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]
     lib.rife_conv_transpose4x4s2.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.rife_layer_create.argtypes = [C.POINTER(vp), i, vp, vp, vp, i, i, i, i]
+    lib.rife_layer_destroy.argtypes = [vp]
+    lib.rife_layer_run.argtypes = [vp, vp, i, vp, i, i, i, i, vp, i, i, vp]
+    lib.rife_nhwc_from_nchw.argtypes = [vp, i, vp, i, i, i, i, i, i, vp]
+    lib.rife_nhwc_to_nchw.argtypes = [vp, i, i, vp, i, i, i, i, i, i, vp]
+    lib.rife_nhwc_resize.argtypes = [vp, i, i, vp, i, i, i, i, i, i, i, i, f, i, vp]
+    lib.rife_nhwc_warp.argtypes = [vp, i, i, vp, i, i, vp, i, i, i, i, i, i, vp, vp, vp]
+    lib.rife_nhwc_s2d.argtypes = [vp, i, i, i, vp, i, i, i, i, vp]
+    lib.rife_eccv_merge.argtypes = [vp, i, i, vp, i, i, vp, i, i, vp, i, i, vp, i, i, i, i, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("rife_abi_version",):

@@ -76,23 +76,24 @@ static HostLayer pack_conv3x3_s2d(const float* W, const float* b, int co, int ci
 
 // ConvTranspose2d IOHW (ci, co, 4, 4), stride 2, pad 1 as a 3x3-tap GEMM with N = 4 parities x co:
 // out[(2y+py, 2x+px), o] = sum_{dy,dx} in[(y+dy, x+dx)] * W[., o, py+1-2dy, px+1-2dx]   
-static HostLayer pack_convT(const float* W, const float* b, int ci, int co, int cin_pad) {
+static HostLayer pack_convT(const float* W, const float* b, int ci, int co, int cin_pad, int co_pad = 0) {
   HostLayer L;
-  L.kind = CONV_3x3; L.taps = 9; L.cin = cin_pad; L.n = 4 * co; L.npad = round_up(4 * co, 16);
-  L.convt_co = co;
+  const int cp = co_pad ? co_pad : co;  // columns per output parity (>= co, zero-padded)
+  L.kind = CONV_3x3; L.taps = 9; L.cin = cin_pad; L.n = 4 * cp; L.npad = round_up(4 * cp, 16);
+  L.convt_co = cp;
   L.w.assign((size_t)9 * cin_pad * L.npad, 0.f);
   L.bias.assign(L.npad, 0.f);
   for (int par = 0; par < 4; ++par) {
     const int py = par >> 1, px = par & 1;
     for (int o = 0; o < co; ++o) {
-      if (b) L.bias[par * co + o] = b[o];
+      if (b) L.bias[par * cp + o] = b[o];
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
           const int ky = py + 1 - 2 * dy, kx = px + 1 - 2 * dx;
           if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
           const int t = (dy + 1) * 3 + (dx + 1);
           for (int i = 0; i < ci; ++i)
-            L.w[((size_t)t * cin_pad + i) * L.npad + par * co + o] = W[(((size_t)i * co + o) * 4 + ky) * 4 + kx];
+            L.w[((size_t)t * cin_pad + i) * L.npad + par * cp + o] = W[(((size_t)i * co + o) * 4 + ky) * 4 + kx];
         }
     }
   }
@@ -688,6 +689,110 @@ int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, 
   const int cpad = round_up(Cout, 4);
   return run_single_conv(L, precision, x, B, Cin, H, W, false, nullptr, y, EPI_CONVT, cpad, Cout, Cout, 2 * H, 2 * W, cpad,
                          (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------------
+// Generic NHWC layer / operator API (ECCV-paper network path; fp32).  See include/rife_b200.h.
+struct rife_layer {
+  rife_weights store;  // owns the device allocations
+  DevLayer d;
+  int kind = 0, cin_store = 0, cout = 0, co_pad = 0;
+};
+
+extern "C" {
+
+int rife_layer_create(rife_layer** out, int kind, const float* w_host, const float* bias_host, const float* slope_host,
+                      int cin, int cout, int cin_store, int precision) {
+  if (!out || !w_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_create: null argument");
+  if (kind < 0 || kind > 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_create: kind must be 0 (3x3 s1), 1 (3x3 s2) or 2 (ConvTranspose 4x4 s2)");
+  if (precision != RIFE_PRECISION_FP32) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_layer_create: the generic layer API is fp32 only in this build");
+  if (cin_store < cin || cin_store % 8) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_create: cin_store must be >= cin and a multiple of 8");
+  auto* l = new rife_layer();
+  l->store.precision = RIFE_PRECISION_FP32;
+  cudaGetDevice(&l->store.device);
+  l->kind = kind; l->cin_store = cin_store; l->cout = cout;
+  HostLayer h;
+  if (kind == 0) h = pack_conv3x3(w_host, bias_host, cout, cin, cin_store);
+  else if (kind == 1) h = pack_conv3x3_s2d(w_host, bias_host, cout, cin, cin_store, 4 * cin_store);
+  else { l->co_pad = round_up(cout, 4); h = pack_convT(w_host, bias_host, cin, cout, cin_store, l->co_pad); }
+  if (slope_host) {
+    h.beta.assign(h.npad, 0.f);
+    if (kind == 2) { for (int par = 0; par < 4; ++par) for (int o = 0; o < cout; ++o) h.beta[par * l->co_pad + o] = slope_host[o]; }
+    else { for (int o = 0; o < cout; ++o) h.beta[o] = slope_host[o]; }
+  }
+  int rc = upload_layer(&l->store, h, &l->d);
+  if (rc != RIFE_OK) { rife_layer_destroy(l); return rc; }
+  *out = l;
+  return RIFE_OK;
+}
+
+int rife_layer_destroy(rife_layer* l) {
+  if (!l) return RIFE_OK;
+  for (void* p : l->store.allocs) cudaFree(p);
+  delete l;
+  return RIFE_OK;
+}
+
+int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_pitch, int B, int H, int W,
+                   const void* res, int res_pitch, int act, void* stream) {
+  if (!l || !in || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: null argument");
+  ConvIO io;
+  io.B = B; io.H = H; io.W = W; io.in = in; io.out = out; io.res = res;
+  io.in_pitch = in_pitch; io.res_pitch = res_pitch; io.out_c = out_pitch;
+  if (l->kind == 2) {
+    if (act != 0 && act != 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: ConvTranspose supports act 0 (none) or 2 (PReLU)");
+    if (out_pitch < l->co_pad) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: out_pitch too small for the ConvTranspose output");
+    io.epi = act == 2 ? EPI_CONVT_PRELU : EPI_CONVT;
+    io.co_per_par = l->co_pad;
+  } else {
+    switch (act) {
+      case 0: io.epi = EPI_LINEAR; break;
+      case 1: io.epi = EPI_LRELU; break;
+      case 2: io.epi = EPI_PRELU; break;
+      case 3: io.epi = EPI_PRELU_ADD; break;
+      default: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: bad act");
+    }
+    if (out_pitch < l->d.f32.n) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: out_pitch smaller than the (4-padded) output channels");
+  }
+  if (l->kind == 1 && in_pitch != 0 && in_pitch != 4 * l->cin_store) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: stride-2 layers read a dense s2d tensor");
+  return launch_conv_f32(l->d.f32, io, (cudaStream_t)stream);
+}
+
+int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int B, int C, int H, int W, int pitch, int off, void* stream) {
+  if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_from_nchw: null argument");
+  return launch_nchw_to_nhwc_slice(src, io_dtype, (float*)dst, B, C, H, W, pitch, off, (cudaStream_t)stream);
+}
+int rife_nhwc_to_nchw(const void* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W, int sigmoid,
+                      void* stream) {
+  if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_to_nchw: null argument");
+  return launch_nhwc_slice_to_nchw((const float*)src, pitch, off, dst, io_dtype, B, C, H, W, sigmoid, (cudaStream_t)stream);
+}
+int rife_nhwc_resize(const void* src, int spitch, int soff, void* dst, int dpitch, int doff, int B, int C, int Hs, int Ws,
+                     int Hd, int Wd, float mul, int accumulate, void* stream) {
+  if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_resize: null argument");
+  auto pow2 = [](int a, int b) { int r = a > b ? a / b : b / a; return (a > b ? a % b : b % a) == 0 && (r & (r - 1)) == 0; };
+  if (!pow2(Hs, Hd) || !pow2(Ws, Wd) || (long long)Hs * Wd != (long long)Hd * Ws) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_resize: power-of-two isotropic factors only");
+  return launch_resize_nhwc((const float*)src, spitch, soff, (float*)dst, dpitch, doff, B, C, Hs, Ws, Hd, Wd, mul, accumulate,
+                            (cudaStream_t)stream);
+}
+int rife_nhwc_warp(const void* src, int spitch, int soff, const void* flow, int fpitch, int foff, void* dst, int dpitch,
+                   int doff, int B, int C, int H, int W, const float* gridx_dev, const float* gridy_dev, void* stream) {
+  if (!src || !flow || !dst || !gridx_dev || !gridy_dev) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_warp: null argument");
+  return launch_warp_nhwc((const float*)src, spitch, soff, (const float*)flow, fpitch, foff, (float*)dst, dpitch, doff, B, C, H,
+                          W, gridx_dev, gridy_dev, (cudaStream_t)stream);
+}
+int rife_nhwc_s2d(const void* src, int spitch, int soff, int C, void* dst, int cpad, int B, int H, int W, void* stream) {
+  if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_s2d: null argument");
+  if (H % 2 || W % 2 || cpad < C) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_s2d: even H, W and cpad >= C required");
+  return launch_s2d_nhwc((const float*)src, spitch, soff, C, (float*)dst, cpad, B, H, W, (cudaStream_t)stream);
+}
+int rife_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm, int om,
+                    const void* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W, void* stream) {
+  if (!w0 || !w1 || !mask || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_eccv_merge: null argument");
+  return launch_eccv_merge((const float*)w0, p0, o0, (const float*)w1, p1, o1, (const float*)mask, pm, om, (const float*)refine,
+                           pr, orf, out, io_dtype, B, H, W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -120,6 +120,10 @@ enum ConvEpi : int {
   EPI_HEADT = 4,      // Head.cnn3 ConvTranspose scatter into channels 0..3 of the SRC tensor
   EPI_LINEAR = 5,     // y = acc + bias (no activation)                 -> NHWC [.., N]
   EPI_CONVT = 6,      // generic ConvTranspose(4,2,1) parity scatter to NHWC [B][2H][2W][N/4] (op-level entry)
+  // ECCV-paper network (model/IFNet.py, model/refine.py): per-channel PReLU tails (slopes in `beta`)
+  EPI_PRELU = 7,        // y = prelu(acc + bias)
+  EPI_PRELU_ADD = 8,    // y = prelu(acc + bias) + res        (convblock(x) + x, model/IFNet.py:46)
+  EPI_CONVT_PRELU = 9,  // ConvTranspose parity scatter + prelu   (deconv(), model/refine.py:19-23)
 };
 
 // Device-side view of one packed conv layer (fp32 FMA path).
@@ -141,6 +145,8 @@ struct ConvIO {
   int epi = EPI_LRELU;
   int out_c = 0;              // channel count of the destination pixel (NHWC pitch)
   int co_per_par = 0;         // EPI_PS / EPI_CONVT / EPI_HEADT: output channels per parity
+  int in_pitch = 0;           // channels per pixel of the tensor `in` points into (0 = cin: dense); fp32 path only
+  int res_pitch = 0;          // same for `res` (0 = out_c)
 };
 
 int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);
@@ -190,5 +196,21 @@ int launch_fill_grid(float* g, int n, cudaStream_t st);
 // layout converters for the op-level entry points
 int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, bool s2d, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st);
+
+// ------------------------------------------------------------------ generic NHWC ops (generic_ops.cu)
+// All tensors are fp32 NHWC [B][H][W][pitch]; an op touches the channel slice [off, off + C).
+int launch_nchw_to_nhwc_slice(const void* src, int io_dtype, float* dst, int B, int C, int H, int W, int pitch, int off,
+                              cudaStream_t st);
+int launch_nhwc_slice_to_nchw(const float* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W,
+                              int sigmoid, cudaStream_t st);
+int launch_resize_nhwc(const float* src, int spitch, int soff, float* dst, int dpitch, int doff, int B, int C, int Hs,
+                       int Ws, int Hd, int Wd, float mul, int accumulate, cudaStream_t st);
+int launch_warp_nhwc(const float* src, int spitch, int soff, const float* flow, int fpitch, int foff, float* dst,
+                     int dpitch, int doff, int B, int C, int H, int W, const float* gridx, const float* gridy,
+                     cudaStream_t st);
+int launch_s2d_nhwc(const float* src, int spitch, int soff, int C, float* dst, int cpad, int B, int H, int W,
+                    cudaStream_t st);
+int launch_eccv_merge(const float* w0, int p0, int o0, const float* w1, int p1, int o1, const float* mask, int pm, int om,
+                      const float* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W, cudaStream_t st);
 
 }  // namespace rife

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ res, float* __restrict__ out,
                                                             int B, int H, int W, int cin, int n_valid, int npad,
-                                                            int epi, int out_c, int cpp) {
+                                                            int epi, int out_c, int cpp, int in_pitch, int res_pitch) {
   constexpr int RH = (KIND == CONV_3x3) ? 2 : 1;  // halo extent: taps cover rows/cols [-1, RH-1]
   constexpr int NTAP = (RH + 1) * (RH + 1);
   constexpr int IH = TH + RH, IW = TW + RH;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
 
-  const float* in_b = in + (size_t)b * H * W * cin;
+  const float* in_b = in + (size_t)b * H * W * in_pitch;
   for (int ci0 = 0; ci0 < cin; ci0 += KC) {
     // ---- stage the input halo tile (transposed to [row][kc][col]) and this chunk's weights
     for (int i = tid; i < IH * IW * 2; i += NTHREADS) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
       const int gy = y0 + r - 1, gx = x0 + c - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = *reinterpret_cast<const float4*>(in_b + ((size_t)gy * W + gx) * cin + ci0 + half * 4);
+        v = *reinterpret_cast<const float4*>(in_b + ((size_t)gy * W + gx) * in_pitch + ci0 + half * 4);
       in_s[r][half * 4 + 0][c] = v.x;
       in_s[r][half * 4 + 1][c] = v.y;
       in_s[r][half * 4 + 2][c] = v.z;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
   if (n >= n_valid) return;
   const float4 bv = *reinterpret_cast<const float4*>(bias + n);
   float4 be = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (epi == EPI_RES) be = *reinterpret_cast<const float4*>(beta + n);
+  if (epi == EPI_RES || epi >= EPI_PRELU) be = *reinterpret_cast<const float4*>(beta + n);
   const int y = y0 + row;
   if (y >= H) return;
 #pragma unroll
@@ -124,12 +124,27 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
       case EPI_RES: {
         const size_t o = (((size_t)b * H + y) * W + x) * out_c + n;
         float r[4];
-        ld4(res + o, r);
+        ld4(res + (((size_t)b * H + y) * W + x) * res_pitch + n, r);
         v[0] = lrelu02(v[0] * be.x + r[0]);
         v[1] = lrelu02(v[1] * be.y + r[1]);
         v[2] = lrelu02(v[2] * be.z + r[2]);
         v[3] = lrelu02(v[3] * be.w + r[3]);
         st4(out + o, v);
+      } break;
+      case EPI_PRELU:
+      case EPI_PRELU_ADD: {
+        v[0] = v[0] >= 0.f ? v[0] : v[0] * be.x;
+        v[1] = v[1] >= 0.f ? v[1] : v[1] * be.y;
+        v[2] = v[2] >= 0.f ? v[2] : v[2] * be.z;
+        v[3] = v[3] >= 0.f ? v[3] : v[3] * be.w;
+        const size_t pix = ((size_t)b * H + y) * W + x;
+        if (epi == EPI_PRELU_ADD) {
+          float r[4];
+          ld4(res + pix * res_pitch + n, r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] += r[q];
+        }
+        st4(out + pix * out_c + n, v);
       } break;
       case EPI_PS: {
         // ConvT output (2y+py, 2x+px), channel co = 4k + 2dy + dx  ->  PixelShuffle -> (4y+2py+dy, 4x+2px+dx), channel k
@@ -143,7 +158,14 @@ __global__ void __launch_bounds__(NTHREADS) conv_f32_kernel(const float* __restr
         }
       } break;
       case EPI_HEADT:
-      case EPI_CONVT: {
+      case EPI_CONVT:
+      case EPI_CONVT_PRELU: {
+        if (epi == EPI_CONVT_PRELU) {
+          v[0] = v[0] >= 0.f ? v[0] : v[0] * be.x;
+          v[1] = v[1] >= 0.f ? v[1] : v[1] * be.y;
+          v[2] = v[2] >= 0.f ? v[2] : v[2] * be.z;
+          v[3] = v[3] >= 0.f ? v[3] : v[3] * be.w;
+        }
         const int par = n / cpp, co = n % cpp;
         const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
         st4(out + (((size_t)b * 2 * H + oy) * 2 * W + ox) * out_c + co, v);
@@ -159,7 +181,9 @@ int launch_t(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st) {
   dim3 grid((io.W + TW - 1) / TW, (io.H + TH - 1) / TH, io.B * ntn);
   conv_f32_kernel<KIND, NT><<<grid, NTHREADS, 0, st>>>((const float*)io.in, L.w, L.bias, L.beta,
                                                        (const float*)io.res, (float*)io.out, io.B, io.H, io.W, L.cin,
-                                                       L.n, L.npad, io.epi, io.out_c, io.co_per_par);
+                                                       L.n, L.npad, io.epi, io.out_c, io.co_per_par,
+                                                       io.in_pitch ? io.in_pitch : L.cin,
+                                                       io.res_pitch ? io.res_pitch : io.out_c);
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }
@@ -169,6 +193,8 @@ int launch_t(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st) {
 int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st) {
   if (L.cin % KC != 0 || L.npad % 4 != 0 || L.n % 4 != 0) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_f32: channel padding");
   if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_f32: EPI_RES needs beta and res");
+  if (io.epi >= EPI_PRELU && !L.beta) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_f32: PReLU epilogues need the slope vector");
+  if (io.epi == EPI_PRELU_ADD && !io.res) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_f32: EPI_PRELU_ADD needs res");
   const bool wide = L.npad > 32, mid = L.npad > 16;
   if (L.kind == CONV_3x3) {
     if (wide) return launch_t<CONV_3x3, 64>(L, io, st);

@@ -1,0 +1,362 @@
+"""ECCV-paper RIFE network (reference `model/IFNet.py`, `model/refine.py`, `model/RIFE.py`; BASELINE config 5).
+
+Parameter containers with the reference's state-dict keys / construction order, and a forward that issues the whole
+network through the generic NHWC layer API of librife_b200.so (`rife_layer_*`, `rife_nhwc_*`, `rife_eccv_merge`):
+fp32 activations `[B][H][W][pitch]`, every `torch.cat` of the reference replaced by producers writing into channel
+slices of the consumer's tensor.  PyTorch only allocates the buffers.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .warplayer import base_grids
+
+
+def _conv_prelu(cin, cout, stride=1):
+    # model/IFNet.py:13-18 / model/refine.py:11-16: Sequential(Conv2d, PReLU(out))
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride, 1, bias=True), nn.PReLU(cout))
+
+
+def _deconv_prelu(cin, cout):
+    # model/refine.py:18-22
+    return nn.Sequential(nn.ConvTranspose2d(cin, cout, 4, 2, 1, bias=True), nn.PReLU(cout))
+
+
+class IFBlock(nn.Module):
+    """Parameters of model/IFNet.py:20-37."""
+
+    def __init__(self, in_planes, c=64):
+        super().__init__()
+        self.conv0 = nn.Sequential(_conv_prelu(in_planes, c // 2, 2), _conv_prelu(c // 2, c, 2))
+        self.convblock = nn.Sequential(*[_conv_prelu(c, c) for _ in range(8)])
+        self.lastconv = nn.ConvTranspose2d(c, 5, 4, 2, 1)
+
+
+class Conv2(nn.Module):
+    """model/refine.py:24-33."""
+
+    def __init__(self, cin, cout, stride=2):
+        super().__init__()
+        self.conv1 = _conv_prelu(cin, cout, stride)
+        self.conv2 = _conv_prelu(cout, cout, 1)
+
+
+_C = 16
+
+
+class Contextnet(nn.Module):
+    """Parameters of model/refine.py:36-42."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = Conv2(3, _C)
+        self.conv2 = Conv2(_C, 2 * _C)
+        self.conv3 = Conv2(2 * _C, 4 * _C)
+        self.conv4 = Conv2(4 * _C, 8 * _C)
+
+
+class Unet(nn.Module):
+    """Parameters of model/refine.py:59-70."""
+
+    def __init__(self):
+        super().__init__()
+        self.down0 = Conv2(17, 2 * _C)
+        self.down1 = Conv2(4 * _C, 4 * _C)
+        self.down2 = Conv2(8 * _C, 8 * _C)
+        self.down3 = Conv2(16 * _C, 16 * _C)
+        self.up0 = _deconv_prelu(32 * _C, 8 * _C)
+        self.up1 = _deconv_prelu(16 * _C, 4 * _C)
+        self.up2 = _deconv_prelu(8 * _C, 2 * _C)
+        self.up3 = _deconv_prelu(4 * _C, _C)
+        self.conv = nn.Conv2d(_C, 3, 3, 1, 1)
+
+
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class _Layer:
+    """One packed conv layer (rife_layer) plus its geometry."""
+
+    def __init__(self, lib, kind, conv, prelu, cin_store):
+        w = conv.weight.detach().to("cpu", torch.float32).contiguous()
+        b = conv.bias.detach().to("cpu", torch.float32).contiguous() if conv.bias is not None else None
+        s = prelu.weight.detach().to("cpu", torch.float32).contiguous() if prelu is not None else None
+        self.kind = kind
+        self.cin = w.shape[1] if kind != 2 else w.shape[0]
+        self.cout = w.shape[0] if kind != 2 else w.shape[1]
+        self.cin_store = cin_store
+        self.h = C.c_void_p()
+        self.lib = lib
+        _lib.check(lib.rife_layer_create(C.byref(self.h), kind, w.data_ptr(), b.data_ptr() if b is not None else None,
+                                         s.data_ptr() if s is not None else None, self.cin, self.cout, cin_store, 0))
+
+    def run(self, src, out, hh, ww, act, res=None, out_off=0, stream=0):
+        """src / out / res: NHWC fp32 tensors; the conv reads channels [0, cin_store) of src and writes channels
+        [out_off, ...) of out."""
+        b = src.shape[0]
+        _lib.check(self.lib.rife_layer_run(self.h, src.data_ptr(), src.shape[-1], out.data_ptr() + 4 * out_off, out.shape[-1],
+                                           b, hh, ww, res.data_ptr() if res is not None else None,
+                                           res.shape[-1] if res is not None else 0, act, stream))
+
+    def free(self):
+        if self.h:
+            self.lib.rife_layer_destroy(self.h)
+            self.h = None
+
+
+class IFNet(nn.Module):
+    """Drop-in for `model.IFNet.IFNet` (inference branch: `x` holds img0, img1 and no ground truth)."""
+
+    def __init__(self):
+        super().__init__()
+        self.block0 = IFBlock(6, c=240)          # model/IFNet.py:56-61: same construction order => same default init
+        self.block1 = IFBlock(13 + 4, c=150)
+        self.block2 = IFBlock(13 + 4, c=90)
+        self.block_tea = IFBlock(16 + 4, c=90)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
+        self.contextnet = Contextnet()
+        self.unet = Unet()
+        self._layers = None
+        self._stamp = None
+        self._generation = 0
+
+    # ---------------------------------------------------------------- packed-layer cache
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._generation += 1
+        return r
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._generation += 1
+        return r
+
+    def invalidate(self):
+        self._generation += 1
+
+    def release(self):
+        if self._layers:
+            for l in self._layers.values():
+                l.free()
+        self._layers = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _pack(self, device):
+        stamp = (self._generation, sum(p._version for p in self.parameters()), str(device))
+        if self._layers is not None and self._stamp == stamp:
+            return self._layers
+        self.release()
+        lib = _lib.load()
+        L = {}
+        with torch.cuda.device(device):
+            for i, blk in enumerate((self.block0, self.block1, self.block2)):
+                c = blk.lastconv.weight.shape[0]
+                cin = blk.conv0[0][0].weight.shape[1]
+                L[f"b{i}.c00"] = _Layer(lib, 1, blk.conv0[0][0], blk.conv0[0][1], _pad8(cin))
+                L[f"b{i}.c01"] = _Layer(lib, 1, blk.conv0[1][0], blk.conv0[1][1], _pad8(c // 2))
+                for j in range(8):
+                    L[f"b{i}.cb{j}"] = _Layer(lib, 0, blk.convblock[j][0], blk.convblock[j][1], _pad8(c))
+                L[f"b{i}.last"] = _Layer(lib, 2, blk.lastconv, None, _pad8(c))
+            cn = self.contextnet
+            for k, (m, cin) in enumerate(((cn.conv1, 3), (cn.conv2, _C), (cn.conv3, 2 * _C), (cn.conv4, 4 * _C))):
+                L[f"ctx{k}.1"] = _Layer(lib, 1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"ctx{k}.2"] = _Layer(lib, 0, m.conv2[0], m.conv2[1], _pad8(m.conv2[0].weight.shape[1]))
+            un = self.unet
+            for k, (m, cin) in enumerate(((un.down0, 17), (un.down1, 4 * _C), (un.down2, 8 * _C), (un.down3, 16 * _C))):
+                L[f"dn{k}.1"] = _Layer(lib, 1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"dn{k}.2"] = _Layer(lib, 0, m.conv2[0], m.conv2[1], _pad8(m.conv2[0].weight.shape[1]))
+            for k, m in enumerate((un.up0, un.up1, un.up2, un.up3)):
+                L[f"up{k}"] = _Layer(lib, 2, m[0], m[1], m[0].weight.shape[0])
+            L["out"] = _Layer(lib, 0, un.conv, None, _C)
+        self._layers, self._stamp = L, stamp
+        return L
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x, scale=[4, 2, 1], timestep=0.5):
+        """model/IFNet.py:63-108, inference branch.  Returns the reference's 6-tuple
+        (flow_list[3], sigmoid(mask), merged[3], None, None, 0).  `timestep` is ignored by this network."""
+        if not x.is_cuda:
+            raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
+        if x.dtype not in (torch.float32, torch.float16):
+            raise TypeError("float32 or float16 frames required")
+        if x.shape[1] != 6:
+            raise NotImplementedError("training branch (ground truth appended to x, model/IFNet.py:66,88-97) is out of scope")
+        s3 = [float(v) for v in scale[:3]]
+        if any(v not in (1.0, 2.0, 4.0, 8.0, 16.0) for v in s3):
+            raise NotImplementedError(f"scale entries must be powers of two >= 1, got {list(scale)}")
+        B, _, H, W = x.shape
+        need = int(max(16, 4 * max(s3)))
+        if H % need or W % need:
+            raise RuntimeError(f"ECCV IFNet: H and W must be multiples of {need} for scale list {list(scale)} (got {H}x{W})")
+        lib = _lib.load()
+        dev = x.device
+        L = self._pack(dev)
+        x = x.contiguous()
+        io = _lib.RIFE_F32 if x.dtype == torch.float32 else _lib.RIFE_F16
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            z = lambda h, w, p: torch.zeros((B, h, w, p), dtype=torch.float32, device=dev)
+            e = lambda h, w, p: torch.empty((B, h, w, p), dtype=torch.float32, device=dev)
+            chk = _lib.check
+
+            def resize(src, soff, c, dst, doff, mul=1.0, acc=0):
+                chk(lib.rife_nhwc_resize(src.data_ptr(), src.shape[-1], soff, dst.data_ptr(), dst.shape[-1], doff, B, c,
+                                         src.shape[1], src.shape[2], dst.shape[1], dst.shape[2], mul, acc, st))
+
+            def warp(src, soff, c, fl, foff, dst, doff):
+                h, w = src.shape[1], src.shape[2]
+                _, _, gx, gy = base_grids(h, w, dev)
+                chk(lib.rife_nhwc_warp(src.data_ptr(), src.shape[-1], soff, fl.data_ptr(), fl.shape[-1], foff, dst.data_ptr(),
+                                       dst.shape[-1], doff, B, c, h, w, gx.data_ptr(), gy.data_ptr(), st))
+
+            def s2d(src, c, cpad, soff=0):
+                h, w = src.shape[1], src.shape[2]
+                dst = e(h // 2, w // 2, 4 * cpad)
+                chk(lib.rife_nhwc_s2d(src.data_ptr(), src.shape[-1], soff, c, dst.data_ptr(), cpad, B, h, w, st))
+                return dst
+
+            def conv2(prefix, src, c_in, dst, doff, soff=0):
+                """Conv2 (model/refine.py:24-33): stride-2 conv + PReLU, conv + PReLU; result into dst[..., doff:]."""
+                l1, l2 = L[prefix + ".1"], L[prefix + ".2"]
+                h, w = src.shape[1] // 2, src.shape[2] // 2
+                a = z(h, w, _pad8(l1.cout))
+                l1.run(s2d(src, c_in, l1.cin_store, soff), a, h, w, 2, stream=st)
+                l2.run(a, dst, h, w, 2, out_off=doff, stream=st)
+
+            # full-resolution working tensor in Unet.down0's cat order (model/refine.py:73):
+            # [img0 0:3 | img1 3:6 | warped0 6:9 | warped1 9:12 | mask 12 | flow 13:17 | pad]
+            full = z(H, W, 24)
+            chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), B, 6, H, W, 24, 0, st))
+            flow_list, merged, mask_sig = [], [], None
+            out_dt = x.dtype
+            for i in range(3):                                                        # model/IFNet.py:74-86
+                s = int(s3[i])
+                hs, ws = H // s, W // s
+                cin = 6 if i == 0 else 17
+                xin = z(hs, ws, _pad8(cin))
+                if i == 0:
+                    resize(full, 0, 6, xin, 0)                                        # :40 (identity when scale == 1)
+                else:
+                    resize(full, 0, 13, xin, 0)                                       # cat(img0,img1,warped0,warped1,mask)
+                    resize(full, 13, 4, xin, 13, mul=1.0 / s)                         # :42 interp(flow) * 1/scale
+                c = (240, 150, 90)[i]
+                a = z(hs // 2, ws // 2, _pad8(c // 2))
+                L[f"b{i}.c00"].run(s2d(xin, cin, _pad8(cin)), a, hs // 2, ws // 2, 2, stream=st)
+                bq = z(hs // 4, ws // 4, _pad8(c))
+                L[f"b{i}.c01"].run(s2d(a, c // 2, _pad8(c // 2)), bq, hs // 4, ws // 4, 2, stream=st)
+                pp = (z(hs // 4, ws // 4, _pad8(c)), z(hs // 4, ws // 4, _pad8(c)))
+                y = bq
+                for j in range(8):                                                    # :45-46 convblock(x) + x
+                    dst = pp[j & 1]
+                    L[f"b{i}.cb{j}"].run(y, dst, hs // 4, ws // 4, 3 if j == 7 else 2, res=bq if j == 7 else None, stream=st)
+                    y = dst
+                tmp = e(hs // 2, ws // 2, 8)
+                L[f"b{i}.last"].run(y, tmp, hs // 4, ws // 4, 0, stream=st)           # :47 lastconv -> 5 ch at 1/(2s)
+                resize(tmp, 0, 4, full, 13, mul=float(2 * s), acc=int(i > 0))         # :48-49,76: flow (+)= up(tmp)*scale*2
+                resize(tmp, 4, 1, full, 12, mul=1.0, acc=int(i > 0))                  # :50,77: mask (+)= up(tmp)
+                warp(full, 0, 3, full, 13, full, 6)                                   # :82
+                warp(full, 3, 3, full, 15, full, 9)                                   # :83
+                fl = torch.empty((B, 4, H, W), dtype=out_dt, device=dev)
+                chk(lib.rife_nhwc_to_nchw(full.data_ptr(), 24, 13, fl.data_ptr(), io, B, 4, H, W, 0, st))
+                flow_list.append(fl)
+                if i < 2:                                                             # :98-99
+                    mg = torch.empty((B, 3, H, W), dtype=out_dt, device=dev)
+                    chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, None, 0, 0,
+                                            mg.data_ptr(), io, B, H, W, st))
+                    merged.append(mg)
+            mask_sig = torch.empty((B, 1, H, W), dtype=out_dt, device=dev)
+            chk(lib.rife_nhwc_to_nchw(full.data_ptr(), 24, 12, mask_sig.data_ptr(), io, B, 1, H, W, 1, st))
+
+            # Contextnet on both frames (model/refine.py:44-57), features warped straight into the Unet's cat slices
+            d1, d2, d3, u0 = z(H // 2, W // 2, 64), z(H // 4, W // 4, 128), z(H // 8, W // 8, 256), z(H // 16, W // 16, 512)
+            for f, (img_off, flow_off) in enumerate(((0, 13), (3, 15))):
+                fl = z(H // 2, W // 2, 8)
+                resize(full, flow_off, 2, fl, 0, mul=0.5)
+                feat = e(H // 2, W // 2, 16)
+                conv2("ctx0", full, 3, feat, 0, soff=img_off)
+                warp(feat, 0, 16, fl, 0, d1, 32 + 16 * f)
+                prev, prev_c = feat, 16
+                for k, (dst, base) in enumerate(((d2, 64), (d3, 128), (u0, 256))):
+                    cc = 32 << k
+                    h, w = prev.shape[1] // 2, prev.shape[2] // 2
+                    nxt = e(h, w, cc)
+                    conv2(f"ctx{k + 1}", prev, prev_c, nxt, 0)
+                    fl2 = z(h, w, 8)
+                    resize(fl, 0, 2, fl2, 0, mul=0.5)
+                    warp(nxt, 0, cc, fl2, 0, dst, base + cc * f)
+                    prev, prev_c, fl = nxt, cc, fl2
+
+            # Unet (model/refine.py:72-82)
+            conv2("dn0", full, 17, d1, 0)
+            conv2("dn1", d1, 64, d2, 0)
+            conv2("dn2", d2, 128, d3, 0)
+            conv2("dn3", d3, 256, u0, 0)
+            u1, u2, u3 = e(H // 8, W // 8, 256), e(H // 4, W // 4, 128), e(H // 2, W // 2, 64)
+            L["up0"].run(u0, u1, H // 16, W // 16, 2, stream=st)
+            resize(d3, 0, 128, u1, 128)                                               # cat((x, s2))
+            L["up1"].run(u1, u2, H // 8, W // 8, 2, stream=st)
+            resize(d2, 0, 64, u2, 64)
+            L["up2"].run(u2, u3, H // 4, W // 4, 2, stream=st)
+            resize(d1, 0, 32, u3, 32)
+            xo = e(H, W, 16)
+            L["up3"].run(u3, xo, H // 2, W // 2, 2, stream=st)
+            ref = e(H, W, 8)
+            L["out"].run(xo, ref, H, W, 0, stream=st)
+            mg = torch.empty((B, 3, H, W), dtype=out_dt, device=dev)
+            chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, ref.data_ptr(), 8, 0,
+                                    mg.data_ptr(), io, B, H, W, st))
+            merged.append(mg)                                                          # :105-107
+        return flow_list, mask_sig, merged, None, None, 0
+
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+class Model:
+    """Drop-in for `model.RIFE.Model` (inference side, model/RIFE.py:18-65)."""
+
+    def __init__(self, local_rank=-1, arbitrary=False):
+        if arbitrary:
+            raise NotImplementedError("IFNet_m (arbitrary-timestep ECCV variant) is out of scope (SURVEY 2.1 row 6)")
+        if local_rank != -1:
+            raise NotImplementedError("DDP training wrapper is out of scope: inference only")
+        self.flownet = IFNet()
+        self.device()
+
+    def train(self):
+        self.flownet.train()
+
+    def eval(self):
+        self.flownet.eval()
+
+    def device(self):
+        self.flownet.to(device)
+
+    def load_model(self, path, rank=0):
+        """model/RIFE.py:41-50: keeps only 'module.'-prefixed keys, strips the prefix, strict load."""
+        if rank <= 0:
+            sd = torch.load("{}/flownet.pkl".format(path), map_location="cpu" if not torch.cuda.is_available() else None)
+            self.flownet.load_state_dict({k.replace("module.", ""): v for k, v in sd.items() if "module." in k})
+
+    def save_model(self, path, rank=0):
+        if rank == 0:
+            torch.save(self.flownet.state_dict(), "{}/flownet.pkl".format(path))
+
+    def inference(self, img0, img1, scale=1, scale_list=[4, 2, 1], TTA=False, timestep=0.5):
+        """model/RIFE.py:56-65.  (The reference rescales its default `scale_list` argument in place; here a copy is used.)"""
+        sl = [scale_list[i] * 1.0 / scale for i in range(3)]
+        imgs = torch.cat((img0, img1), 1)
+        merged = self.flownet(imgs, sl, timestep=timestep)[2]
+        if not TTA:
+            return merged[2]
+        merged2 = self.flownet(imgs.flip(2).flip(3), sl, timestep=timestep)[2]
+        return (merged[2] + merged2[2].flip(2).flip(3)) / 2

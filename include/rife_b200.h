@@ -137,6 +137,40 @@ int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, 
                              int Cin, int H, int W, int Cout, int pixel_shuffle, int precision,
                              void* stream);
 
+/* ---- generic NHWC layer / operator API: the ECCV-paper network (model/IFNet.py, model/refine.py, -------------
+ *      model/RIFE.py:56-65; BASELINE config 5).  fp32 NHWC tensors [B][H][W][pitch]; an operator touches the
+ *      channel slice [off, off + C) so that torch.cat (model/IFNet.py:75-79, model/refine.py:73-80) is free. */
+typedef struct rife_layer rife_layer;
+/* kind 0: nn.Conv2d(cin,cout,3,1,1); kind 1: nn.Conv2d(cin,cout,3,2,1) reading the space-to-depth tensor produced by
+ * rife_nhwc_s2d (cpad = cin_store); kind 2: nn.ConvTranspose2d(cin,cout,4,2,1).  w_host in the reference's layout
+ * (OIHW / IOHW), bias_host [cout] or NULL, slope_host [cout] = nn.PReLU(cout).weight or NULL.  cin_store = channels
+ * of the input slice incl. zero padding (multiple of 8). */
+int rife_layer_create(rife_layer** out, int kind, const float* w_host, const float* bias_host,
+                      const float* slope_host, int cin, int cout, int cin_store, int precision);
+int rife_layer_destroy(rife_layer* l);
+/* act: 0 none, 1 LeakyReLU(0.2), 2 PReLU, 3 PReLU then "+ res" (convblock(x) + x, model/IFNet.py:46).
+ * H, W: spatial size of the input grid (for kind 1: of the s2d tensor, i.e. of the output). */
+int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_pitch, int B, int H,
+                   int W, const void* res, int res_pitch, int act, void* stream);
+int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int B, int C, int H, int W, int pitch, int off,
+                        void* stream);
+int rife_nhwc_to_nchw(const void* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W,
+                      int sigmoid, void* stream);
+/* F.interpolate(bilinear, align_corners=False) by a power-of-two factor; dst = (accumulate ? dst : 0) + value * mul */
+int rife_nhwc_resize(const void* src, int spitch, int soff, void* dst, int dpitch, int doff, int B, int C, int Hs,
+                     int Ws, int Hd, int Wd, float mul, int accumulate, void* stream);
+/* warp() of model/warplayer.py:8-22; flow = channels [foff, foff+2) of an NHWC tensor at the same resolution */
+int rife_nhwc_warp(const void* src, int spitch, int soff, const void* flow, int fpitch, int foff, void* dst,
+                   int dpitch, int doff, int B, int C, int H, int W, const float* gridx_dev, const float* gridy_dev,
+                   void* stream);
+int rife_nhwc_s2d(const void* src, int spitch, int soff, int C, void* dst, int cpad, int B, int H, int W,
+                  void* stream);
+/* merged = w0*sigmoid(mask) + w1*(1-sigmoid(mask)) (model/IFNet.py:98-99); with refine (pre-sigmoid Unet output):
+ * clamp(merged + sigmoid(refine)*2 - 1, 0, 1) (model/IFNet.py:105-107).  out: NCHW (B,3,H,W) of io_dtype. */
+int rife_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm,
+                    int om, const void* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

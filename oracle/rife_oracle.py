@@ -268,3 +268,96 @@ def state_dict_to_numpy(sd):
         k = k.replace("module.", "")
         out[k] = v.detach().cpu().numpy().astype(F32) if hasattr(v, "detach") else np.asarray(v, F32)
     return out
+
+
+# ----------------------------------------------------------------------------- ECCV-paper network (config 5)
+def prelu(x, slope):
+    """nn.PReLU(C): per-channel slope (model/IFNet.py:17, model/refine.py:15,21)."""
+    s = np.asarray(slope, F32).reshape(1, -1, 1, 1)
+    return np.where(x >= 0, x, x * s).astype(F32)
+
+
+def _conv_prelu(sd, p, x, stride=1):
+    return prelu(conv2d(x, _p(sd, p + "0.weight"), _p(sd, p + "0.bias"), stride, 1), _p(sd, p + "1.weight"))
+
+
+def eccv_ifblock(sd, p, x, flow, scale):
+    """IFBlock.forward of model/IFNet.py:39-51."""
+    if scale != 1:
+        x = interpolate_bilinear(x, 1.0 / scale)                                         # :41
+    if flow is not None:
+        flow = (interpolate_bilinear(flow, 1.0 / scale) * F32(1.0) / F32(scale)).astype(F32)  # :43
+        x = np.concatenate([x, flow], 1)
+    x = _conv_prelu(sd, p + "conv0.0.", x, 2)                                             # :45
+    x = _conv_prelu(sd, p + "conv0.1.", x, 2)
+    y = x
+    for j in range(8):
+        y = _conv_prelu(sd, f"{p}convblock.{j}.", y)
+    x = (y + x).astype(F32)                                                               # :46
+    tmp = conv_transpose2d_k4s2p1(x, _p(sd, p + "lastconv.weight"), _p(sd, p + "lastconv.bias"))  # :47
+    tmp = interpolate_bilinear(tmp, scale * 2)                                            # :48
+    return (tmp[:, :4] * F32(scale) * F32(2)).astype(F32), tmp[:, 4:5]                   # :49-50
+
+
+def _conv2(sd, p, x):
+    """Conv2 of model/refine.py:24-33."""
+    return _conv_prelu(sd, p + "conv2.", _conv_prelu(sd, p + "conv1.", x, 2))
+
+
+def eccv_contextnet(sd, x, flow, p="contextnet."):
+    """model/refine.py:44-57."""
+    out = []
+    for k in range(1, 5):
+        x = _conv2(sd, f"{p}conv{k}.", x)
+        flow = (interpolate_bilinear(flow, 0.5) * F32(0.5)).astype(F32)
+        out.append(warp(x, flow))
+    return out
+
+
+def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet."):
+    """model/refine.py:72-82."""
+    def deconv(q, x):
+        return prelu(conv_transpose2d_k4s2p1(x, _p(sd, q + "0.weight"), _p(sd, q + "0.bias")), _p(sd, q + "1.weight"))
+    s0 = _conv2(sd, p + "down0.", np.concatenate([img0, img1, w0, w1, mask, flow], 1))
+    s1 = _conv2(sd, p + "down1.", np.concatenate([s0, c0[0], c1[0]], 1))
+    s2 = _conv2(sd, p + "down2.", np.concatenate([s1, c0[1], c1[1]], 1))
+    s3 = _conv2(sd, p + "down3.", np.concatenate([s2, c0[2], c1[2]], 1))
+    x = deconv(p + "up0.", np.concatenate([s3, c0[3], c1[3]], 1))
+    x = deconv(p + "up1.", np.concatenate([x, s2], 1))
+    x = deconv(p + "up2.", np.concatenate([x, s1], 1))
+    x = deconv(p + "up3.", np.concatenate([x, s0], 1))
+    return sigmoid(conv2d(x, _p(sd, p + "conv.weight"), _p(sd, p + "conv.bias"), 1, 1))
+
+
+def eccv_ifnet_forward(sd, x, scale=(4, 2, 1)):
+    """IFNet.forward of model/IFNet.py:63-108, inference branch (x = cat(img0, img1), no ground truth)."""
+    x = np.asarray(x, F32)
+    img0, img1 = x[:, :3], x[:, 3:6]
+    flow_list, merged, mask_list = [], [], []
+    w0, w1, flow, mask = img0, img1, None, None
+    for i in range(3):
+        p = f"block{i}."
+        if flow is not None:
+            fd, md = eccv_ifblock(sd, p, np.concatenate([img0, img1, w0, w1, mask], 1), flow, scale[i])  # :76
+            flow = (flow + fd).astype(F32)
+            mask = (mask + md).astype(F32)
+        else:
+            flow, mask = eccv_ifblock(sd, p, np.concatenate([img0, img1], 1), None, scale[i])           # :80
+        mask_list.append(sigmoid(mask))
+        flow_list.append(flow)
+        w0, w1 = warp(img0, flow[:, :2]), warp(img1, flow[:, 2:4])                                       # :83-84
+        merged.append((w0, w1))
+    for i in range(3):
+        merged[i] = (merged[i][0] * mask_list[i] + merged[i][1] * (F32(1) - mask_list[i])).astype(F32)   # :99
+    c0 = eccv_contextnet(sd, img0, flow[:, :2])                                                          # :103
+    c1 = eccv_contextnet(sd, img1, flow[:, 2:4])
+    tmp = eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1)                                          # :105
+    res = (tmp[:, :3] * F32(2) - F32(1)).astype(F32)
+    merged[2] = np.clip(merged[2] + res, 0, 1).astype(F32)                                               # :107
+    return flow_list, mask_list[2], merged
+
+
+def eccv_model_inference(sd, img0, img1, scale=1.0, scale_list=(4, 2, 1)):
+    """Model.inference of model/RIFE.py:56-65 (TTA=False)."""
+    sl = [s * 1.0 / scale for s in scale_list]
+    return eccv_ifnet_forward(sd, np.concatenate([np.asarray(img0, F32), np.asarray(img1, F32)], 1), sl)[2][2]

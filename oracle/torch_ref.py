@@ -81,3 +81,83 @@ def model_inference(sd, img0, img1, timestep=0.5, scale=1.0):
     imgs = torch.cat((img0, img1), 1)
     scale_list = [16 / scale, 8 / scale, 4 / scale, 2 / scale, 1 / scale]
     return ifnet_forward(sd, imgs, timestep, scale_list)[2][-1]
+
+
+# ----------------------------------------------------------------------------- ECCV-paper network (config 5)
+def _cp(sd, p, x, stride=1):
+    return F.prelu(F.conv2d(x, sd[p + "0.weight"], sd[p + "0.bias"], stride, 1), sd[p + "1.weight"])
+
+
+def eccv_ifblock(sd, p, x, flow, scale):
+    """model/IFNet.py:39-51."""
+    if scale != 1:
+        x = F.interpolate(x, scale_factor=1. / scale, mode="bilinear", align_corners=False)
+    if flow is not None:
+        flow = F.interpolate(flow, scale_factor=1. / scale, mode="bilinear", align_corners=False) * 1. / scale
+        x = torch.cat((x, flow), 1)
+    x = _cp(sd, p + "conv0.1.", _cp(sd, p + "conv0.0.", x, 2), 2)
+    y = x
+    for j in range(8):
+        y = _cp(sd, f"{p}convblock.{j}.", y)
+    x = y + x
+    tmp = F.conv_transpose2d(x, sd[p + "lastconv.weight"], sd[p + "lastconv.bias"], 2, 1)
+    tmp = F.interpolate(tmp, scale_factor=scale * 2, mode="bilinear", align_corners=False)
+    return tmp[:, :4] * scale * 2, tmp[:, 4:5]
+
+
+def _conv2(sd, p, x):
+    return _cp(sd, p + "conv2.", _cp(sd, p + "conv1.", x, 2))
+
+
+def eccv_contextnet(sd, x, flow, p="contextnet."):
+    out = []
+    for k in range(1, 5):
+        x = _conv2(sd, f"{p}conv{k}.", x)
+        flow = F.interpolate(flow, scale_factor=0.5, mode="bilinear", align_corners=False, recompute_scale_factor=False) * 0.5
+        out.append(warp(x, flow))
+    return out
+
+
+def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet."):
+    def deconv(q, x):
+        return F.prelu(F.conv_transpose2d(x, sd[q + "0.weight"], sd[q + "0.bias"], 2, 1), sd[q + "1.weight"])
+    s0 = _conv2(sd, p + "down0.", torch.cat((img0, img1, w0, w1, mask, flow), 1))
+    s1 = _conv2(sd, p + "down1.", torch.cat((s0, c0[0], c1[0]), 1))
+    s2 = _conv2(sd, p + "down2.", torch.cat((s1, c0[1], c1[1]), 1))
+    s3 = _conv2(sd, p + "down3.", torch.cat((s2, c0[2], c1[2]), 1))
+    x = deconv(p + "up0.", torch.cat((s3, c0[3], c1[3]), 1))
+    x = deconv(p + "up1.", torch.cat((x, s2), 1))
+    x = deconv(p + "up2.", torch.cat((x, s1), 1))
+    x = deconv(p + "up3.", torch.cat((x, s0), 1))
+    return torch.sigmoid(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], 1, 1))
+
+
+@torch.no_grad()
+def eccv_ifnet_forward(sd, x, scale=(4, 2, 1)):
+    """model/IFNet.py:63-108, inference branch."""
+    img0, img1 = x[:, :3], x[:, 3:6]
+    flow_list, merged, mask_list = [], [], []
+    w0, w1, flow, mask = img0, img1, None, None
+    for i in range(3):
+        p = f"block{i}."
+        if flow is not None:
+            fd, md = eccv_ifblock(sd, p, torch.cat((img0, img1, w0, w1, mask), 1), flow, scale[i])
+            flow, mask = flow + fd, mask + md
+        else:
+            flow, mask = eccv_ifblock(sd, p, torch.cat((img0, img1), 1), None, scale[i])
+        mask_list.append(torch.sigmoid(mask))
+        flow_list.append(flow)
+        w0, w1 = warp(img0, flow[:, :2]), warp(img1, flow[:, 2:4])
+        merged.append((w0, w1))
+    for i in range(3):
+        merged[i] = merged[i][0] * mask_list[i] + merged[i][1] * (1 - mask_list[i])
+    c0, c1 = eccv_contextnet(sd, img0, flow[:, :2]), eccv_contextnet(sd, img1, flow[:, 2:4])
+    tmp = eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1)
+    merged[2] = torch.clamp(merged[2] + (tmp[:, :3] * 2 - 1), 0, 1)
+    return flow_list, mask_list[2], merged
+
+
+@torch.no_grad()
+def eccv_model_inference(sd, img0, img1, scale=1.0, scale_list=(4, 2, 1)):
+    sl = [s * 1.0 / scale for s in scale_list]
+    return eccv_ifnet_forward(sd, torch.cat((img0, img1), 1), sl)[2][2]

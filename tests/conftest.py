@@ -67,3 +67,24 @@ def torch_state_dict(model):
 def psnr(a, b):
     mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
     return 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+_eccv = {}
+
+
+def seeded_eccv(pkg, amp=AMP):
+    """ECCV-paper model mirror under torch.manual_seed(1234) (sha256 in tests/golden/weights_eccv_seed1234.json);
+    `amp` scales block{0,1,2}.lastconv.weight as tests/golden/make_golden.py:case_eccv does."""
+    import torch
+    if amp not in _eccv:
+        torch.manual_seed(1234)
+        m = pkg.eccv.Model()
+        m.eval()
+        m._sha_state = {k: v.detach().cpu().clone() for k, v in m.flownet.state_dict().items()}
+        if amp != 1.0:
+            with torch.no_grad():
+                for b in (m.flownet.block0, m.flownet.block1, m.flownet.block2):
+                    b.lastconv.weight.mul_(amp)
+            m.flownet.invalidate()
+        _eccv[amp] = m
+    return _eccv[amp]

@@ -183,10 +183,48 @@ def case_ops():
     save("ops_cases", **arrs)
 
 
+def case_eccv():
+    """BASELINE config 5: the ECCV-paper net (model/RIFE.py Model.inference, model/IFNet.py IFNet.forward)."""
+    from model.RIFE import Model as EccvModel
+    torch.manual_seed(1234)
+    m = EccvModel()
+    m.eval()
+    sd = m.flownet.state_dict()
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().numpy().astype(np.float32).tobytes())
+    with open(os.path.join(OUT, "weights_eccv_seed1234.json"), "w") as f:
+        json.dump({"seed": 1234, "sha256": h.hexdigest(), "n_tensors": len(sd),
+                   "n_params": int(sum(v.numel() for v in sd.values()))}, f, indent=1)
+    # amplify lastconv so that |flow| is a few pixels with random weights
+    for b in (m.flownet.block0, m.flownet.block1, m.flownet.block2):
+        b.lastconv.weight.mul_(AMP)
+    arrs = {}
+    img0, img1 = rand_frames(41, 2, 3, 64, 96, smooth=True)
+    flow_list, mask, merged, _, _, _ = m.flownet(torch.cat((img0, img1), 1), [4, 2, 1])
+    arrs["a_img0"], arrs["a_img1"] = f32(img0), f32(img1)
+    for i in range(3):
+        arrs[f"a_flow{i}"], arrs[f"a_merged{i}"] = f32(flow_list[i]), f32(merged[i])
+    arrs["a_mask"] = f32(mask)
+    img0, img1 = rand_frames(42, 1, 3, 128, 128)
+    arrs["b_img0"], arrs["b_img1"] = f32(img0), f32(img1)
+    arrs["b_out"] = f32(m.inference(img0, img1, scale=0.5, scale_list=[4, 2, 1]))
+    img0, img1 = rand_frames(43, 1, 3, 256, 448, smooth=True)          # Vimeo90K frame shape (benchmark/Vimeo90K.py)
+    arrs["c_img0"], arrs["c_img1"] = f32(img0).astype(np.float16), f32(img1).astype(np.float16)
+    arrs["c_out"] = f32(m.inference(img0.half().float(), img1.half().float(), scale_list=[4, 2, 1])).astype(np.float16)
+    print("eccv |flow|max", float(flow_list[-1].abs().max()))
+    save("eccv_cases", **arrs)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "eccv":
+        case_eccv()
+        sys.exit(0)
     weights_manifest()
     case_demo()
     case_full_structure()
     case_inference_variants()
     case_warp()
     case_ops()
+    case_eccv()

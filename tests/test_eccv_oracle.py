@@ -1,0 +1,39 @@
+"""ECCV-paper network (BASELINE config 5): oracles pinned to goldens recorded from the unmodified reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from conftest import AMP, GOLDEN, load_golden, seeded_eccv
+from oracle import rife_oracle as O
+from oracle import torch_ref as T
+
+
+def test_eccv_mirror_regenerates_reference_weights(pkg):
+    man = json.load(open(os.path.join(GOLDEN, "weights_eccv_seed1234.json")))
+    m = seeded_eccv(pkg)
+    sd = m._sha_state
+    assert len(sd) == man["n_tensors"] == 190 and sum(v.numel() for v in sd.values()) == man["n_params"] == 10708215
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.numpy().astype(np.float32).tobytes())
+    assert h.hexdigest() == man["sha256"]
+
+
+def test_eccv_oracles_against_golden(pkg):
+    g = load_golden("eccv_cases")
+    m = seeded_eccv(pkg)
+    sdt = {k: v.detach().cpu().float() for k, v in m.flownet.state_dict().items()}
+    sdn = {k: v.numpy() for k, v in sdt.items()}
+    x = np.concatenate([g["a_img0"], g["a_img1"]], 1)
+    for name, (flows, mask, merged) in {"numpy": O.eccv_ifnet_forward(sdn, x, [4, 2, 1]),
+                                        "torch": T.eccv_ifnet_forward(sdt, torch.from_numpy(x), [4, 2, 1])}.items():
+        for i in range(3):
+            assert np.abs(np.asarray(flows[i]) - g[f"a_flow{i}"]).max() < 5e-4, (name, i)
+            assert np.abs(np.asarray(merged[i]) - g[f"a_merged{i}"]).max() < 1e-4, (name, i)
+        assert np.abs(np.asarray(mask) - g["a_mask"]).max() < 1e-4, name
+    out = T.eccv_model_inference(sdt, torch.from_numpy(g["b_img0"]), torch.from_numpy(g["b_img1"]), 0.5).numpy()
+    assert np.abs(out - g["b_out"]).max() < 1e-4
