@@ -8,13 +8,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librife_b200.so")
 
-RIFE_F32, RIFE_F16 = 0, 1
+RIFE_F32, RIFE_F16, RIFE_U8 = 0, 1, 2
 PRECISION_FP32, PRECISION_FP16 = 0, 1
 
 # every symbol declared in include/rife_b200.h
 SYMBOLS = [
     "rife_abi_version", "rife_last_error", "rife_launch_count", "rife_weights_create", "rife_weights_destroy",
-    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_plan_set_profiling",
+    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_plan_set_frame_size",
+    "rife_plan_set_profiling",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
     "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
@@ -55,6 +56,7 @@ def load():
     lib.rife_plan_workspace_bytes.restype = sz
     lib.rife_plan_create.argtypes = [C.POINTER(vp), vp, i, i, i, i, f, vp, sz, vp, vp]
     lib.rife_plan_destroy.argtypes = [vp]
+    lib.rife_plan_set_frame_size.argtypes = [vp, i, i]
     lib.rife_plan_set_profiling.argtypes = [vp, i]
     lib.rife_plan_get_profile.argtypes = [vp, C.POINTER(C.c_char_p), fp, i]
     lib.rife_inference.argtypes = [vp, vp, vp, fp, vp, i, vp]

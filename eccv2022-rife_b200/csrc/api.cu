@@ -312,6 +312,7 @@ static int plan_layout(int B, int C, int H, int W, float scale, int precision, P
 struct rife_plan {
   const rife_weights* w = nullptr;
   int B = 0, C = 0, H = 0, W = 0, precision = 0, device = 0;
+  int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
   PlanLayout L{};
   char* ws = nullptr;
   void* at(size_t off) const { return ws + off; }
@@ -407,6 +408,14 @@ int rife_plan_destroy(rife_plan* p) {
   return RIFE_OK;
 }
 
+int rife_plan_set_frame_size(rife_plan* p, int h, int w) {
+  if (!p) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_frame_size: null plan");
+  if (h < 1 || w < 1 || h > p->H || w > p->W)
+    RIFE_FAIL(RIFE_ERR_SHAPE, "rife_plan_set_frame_size: (h, w) must lie within the plan's padded size");
+  p->fh = h; p->fw = w;
+  return RIFE_OK;
+}
+
 int rife_plan_set_profiling(rife_plan* p, int enable) {
   if (!p) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_profiling: null plan");
   p->profile = enable != 0;
@@ -439,7 +448,8 @@ static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, boo
 static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
                         const rife_ifnet_outputs* outs, int io_dtype, cudaStream_t st) {
   if (!p || !img0 || !img1 || !timestep_host || !outs) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: null argument");
-  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16) RIFE_FAIL(RIFE_ERR_DTYPE, "rife: io_dtype must be RIFE_F32 or RIFE_F16");
+  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8)
+    RIFE_FAIL(RIFE_ERR_DTYPE, "rife: io_dtype must be RIFE_F32, RIFE_F16 or RIFE_U8");
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev != p->device) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: plan belongs to another device");
@@ -454,6 +464,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
 
   PixelCtx c;
   c.B = B; c.C = p->C; c.H = H; c.W = W;
+  c.h = p->fh; c.w = p->fw;
   c.gridx = (const float*)p->at(L.gridx);
   c.gridy = (const float*)p->at(L.gridy);
   c.tstep = (const float*)p->at(L.tstep);
@@ -543,9 +554,10 @@ int rife_inference(rife_plan* p, const void* img0, const void* img1, const float
 int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,
                         void* out_host, int io_dtype, void* stream) {
   if (!p || !img0_host || !img1_host || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host: null argument");
-  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host: bad io_dtype");
+  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host: bad io_dtype");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t bytes = (size_t)p->B * p->C * p->H * p->W * (io_dtype == RIFE_F16 ? 2 : 4);
+  const size_t esz = io_dtype == RIFE_F32 ? 4 : (io_dtype == RIFE_F16 ? 2 : 1);
+  const size_t bytes = (size_t)p->B * p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
   RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, bytes, cudaMemcpyHostToDevice, st));
   RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, bytes, cudaMemcpyHostToDevice, st));
   RIFE_TRY(rife_inference(p, p->at(p->L.stage_in0), p->at(p->L.stage_in1), timestep_host, p->at(p->L.stage_out), io_dtype,

@@ -101,9 +101,15 @@ __device__ __forceinline__ void st4(__half* p, const float (&v)[4]) {
 }
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+// uint8 frames: the callers' `frame / 255.` (inference_img.py:59-60, inference_video.py:191-193)
+__device__ __forceinline__ float to_f(uint8_t x) { return __fdiv_rn((float)x, 255.f); }
 template <typename T> __device__ __forceinline__ T from_f(float x);
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+// `(x * 255).byte()` of the callers (inference_img.py:111, inference_video.py:267): truncation; clamped to [0, 255]
+template <> __device__ __forceinline__ uint8_t from_f<uint8_t>(float x) {
+  return (uint8_t)fminf(fmaxf(__fmul_rn(x, 255.f), 0.f), 255.f);
+}
 
 __device__ __forceinline__ float lrelu02(float x) { return x >= 0.f ? x : x * 0.2f; }
 
@@ -158,8 +164,24 @@ struct TmpLevel {
   int s;            // up-sampling factor to full resolution (power of two >= 1)
 };
 
+// Frame tensors at the API boundary.  RIFE_F32 / RIFE_F16: NCHW (B,C,h,w); RIFE_U8: HWC (B,h,w,C) as video decoders
+// deliver them.  (h, w) <= (H, W): the pipeline zero-pads on the right / bottom to (H, W) and crops its outputs, which is
+// what the reference's callers do around Model.inference (inference_img.py:62-67,111).
+struct ImgLayout {
+  long long sb, sc, sy, sx;  // element strides of batch, channel, row, column
+  int h, w;
+};
+inline ImgLayout make_layout(int io_dtype, int C, int h, int w) {
+  ImgLayout L;
+  L.h = h; L.w = w;
+  if (io_dtype == RIFE_U8) { L.sx = C; L.sc = 1; L.sy = (long long)w * C; L.sb = (long long)h * w * C; }
+  else { L.sx = 1; L.sy = w; L.sc = (long long)h * w; L.sb = (long long)C * h * w; }
+  return L;
+}
+
 struct PixelCtx {
   int B, C, H, W;
+  int h = 0, w = 0;    // frame size seen by the caller (0 = H, W)
   const float* gridx;  // device, W entries (model/warplayer.py:11)
   const float* gridy;  // device, H entries (model/warplayer.py:13)
   const float* tstep;  // device, B entries

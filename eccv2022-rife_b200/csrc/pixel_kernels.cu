@@ -174,7 +174,7 @@ template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                    T* __restrict__ src0, T* __restrict__ src1,
                                                    T* __restrict__ head_in, int B, int C, int H, int W,
-                                                   int planar, int write_src) {
+                                                   int planar, int write_src, ImgLayout lay) {
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)B * H2 * W2;
@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
   const int b = (int)(q / ((size_t)W2 * H2));
   const Tio* img = frame ? img1 : img0;
   T* src = frame ? src1 : src0;
-  const size_t plane = (size_t)H * W;
   float hv[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) hv[i] = 0.f;
@@ -197,8 +196,10 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      const Tio* p = img + (size_t)b * C * plane + (size_t)y * W + x;
-      for (int c = 0; c < C; ++c) v[4 + c] = to_f(p[c * plane]);
+      if (y < lay.h && x < lay.w) {  // beyond the caller's frame: zero padding (F.pad of the reference's callers)
+        const Tio* p = img + b * lay.sb + y * lay.sy + x * lay.sx;
+        for (int c = 0; c < C; ++c) v[4 + c] = to_f(p[c * lay.sc]);
+      }
       // fused mode: Head.cnn3's epilogue assembles the whole SRC pixel (feature + image) from the s2d Head input
       if (write_src) st8(src + (((size_t)b * H + y) * W + x) * SRC_C, v);
 #pragma unroll
@@ -539,15 +540,15 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
                                                    Tio* __restrict__ omask, Tio* __restrict__ ow0,
                                                    Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
                                                    int H, int W, WarpGeom geom, const float* __restrict__ fbuf,
-                                                   int fbuf_levels) {
-  const size_t plane = (size_t)H * W;
+                                                   int fbuf_levels, ImgLayout lay) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
-  if (x >= W) return;
+  if (x >= lay.w || y >= lay.h) return;   // outputs are cropped to the caller's frame
+  const size_t plane = (size_t)lay.h * lay.w;
   float flow[4] = {0.f, 0.f, 0.f, 0.f}, last[16];
   if (fbuf_levels > 0) ld4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow);
   eval_state<Tt>(L, nlev, fbuf_levels, b, y, x, flow, last);
-  const size_t pix = (size_t)y * W + x;
+  const size_t pix = (size_t)y * lay.w + x;  // flow / mask outputs are always NCHW (B,4|1,h,w)
   if (oflow) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) oflow[((size_t)b * 4 + c) * plane + pix] = from_f<Tio>(flow[c]);
@@ -556,12 +557,12 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
   if (ow0 || ow1 || omerged) {
     const float gx = gridx[x], gy = gridy[y];
     float a[8], c[8];
-    warp8<T>(src0 + (size_t)b * plane * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);  // IFNet_HDv3.py:155
-    warp8<T>(src1 + (size_t)b * plane * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);  // IFNet_HDv3.py:156
+    warp8<T>(src0 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);  // IFNet_HDv3.py:155
+    warp8<T>(src1 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);  // IFNet_HDv3.py:156
     const float m = 1.f / (1.f + expf(-last[4]));                                         // IFNet_HDv3.py:158
     for (int ch = 0; ch < C; ++ch) {
       const float w0 = a[4 + ch], w1 = c[4 + ch];
-      const size_t o = ((size_t)b * C + ch) * plane + pix;
+      const size_t o = (size_t)(b * lay.sb + ch * lay.sc + y * lay.sy + x * lay.sx);
       if (ow0) ow0[o] = from_f<Tio>(w0);
       if (ow1) ow1[o] = from_f<Tio>(w1);
       if (omerged) omerged[o] = from_f<Tio>(w0 * m + w1 * (1.f - m));                     // IFNet_HDv3.py:159
@@ -677,7 +678,9 @@ inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
                 void* head_in, cudaStream_t st) {
-  if (c.planar_head && c.half_act && c.W % 8 == 0) {
+  const int fh = c.h ? c.h : c.H, fw = c.w ? c.w : c.W;
+  const ImgLayout lay = make_layout(io_dtype, c.C, fh, fw);
+  if (c.planar_head && c.half_act && c.W % 8 == 0 && fh == c.H && fw == c.W && io_dtype != RIFE_U8) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)(2 * c.B));
     if (io_dtype == RIFE_F16)
       prep_planar_kernel<__half><<<g, 256, 0, st>>>((const __half*)img0, (const __half*)img1, (__half*)head_in, c.B, c.C, c.H, c.W);
@@ -692,11 +695,13 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   dim3 grid(nblk(nq, 256), 2);
 #define RIFE_PREP(TIO, T)                                                                                        \
   prep_kernel<TIO, T><<<grid, 256, 0, st>>>((const TIO*)img0, (const TIO*)img1, (T*)src0, (T*)src1, (T*)head_in, \
-                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1)
+                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1, lay)
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
   else if (io_dtype == RIFE_F16 && c.half_act) RIFE_PREP(__half, __half);
+  else if (io_dtype == RIFE_U8 && !c.half_act) RIFE_PREP(uint8_t, float);
+  else if (io_dtype == RIFE_U8 && c.half_act) RIFE_PREP(uint8_t, __half);
   else RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
 #undef RIFE_PREP
   RIFE_LAUNCH_CHECK();
@@ -751,16 +756,21 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   const size_t n = (size_t)c.B * c.H * c.W;
   LevelsArg L = pack_levels(levels, nlev);
   WarpGeom g = make_geom(c.H, c.W);
-  const dim3 egrid(nblk((size_t)c.W, 256), (unsigned)c.H, (unsigned)c.B);
+  const int fh = c.h ? c.h : c.H, fw = c.w ? c.w : c.W;
+  const ImgLayout lay = make_layout(io_dtype, c.C, fh, fw);
+  if (io_dtype == RIFE_U8 && (o.flow || o.mask)) RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: flow / mask outputs need a float io dtype");
+  const dim3 egrid(nblk((size_t)fw, 256), (unsigned)fh, (unsigned)c.B);
 #define RIFE_EVAL(T, TIO)                                                                                         \
   eval_kernel<T, T, TIO><<<egrid, 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
                                                        c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
                                                        (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, \
-                                                       fbuf_levels)
+                                                       fbuf_levels, lay)
   if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
   else if (!c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(float, __half);
   else if (c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(__half, float);
   else if (c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(__half, __half);
+  else if (!c.half_act && io_dtype == RIFE_U8) RIFE_EVAL(float, uint8_t);
+  else if (c.half_act && io_dtype == RIFE_U8) RIFE_EVAL(__half, uint8_t);
   else RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: bad io dtype");
 #undef RIFE_EVAL
   RIFE_LAUNCH_CHECK();

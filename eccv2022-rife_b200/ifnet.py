@@ -64,7 +64,7 @@ def _precision_from_env(default):
 
 
 class _Plan:
-    __slots__ = ("handle", "workspace", "key")
+    __slots__ = ("handle", "workspace", "key", "frame")
 
 
 class IFNet(nn.Module):
@@ -198,20 +198,45 @@ class IFNet(nn.Module):
     def _check_input(self, x):
         if not x.is_cuda:
             raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
-        if x.dtype not in (torch.float32, torch.float16):
-            raise TypeError("eccv2022-rife_b200: float32 or float16 frames required")
+        if x.dtype not in (torch.float32, torch.float16, torch.uint8):
+            raise TypeError("eccv2022-rife_b200: float32 / float16 NCHW frames or uint8 HWC frames required")
 
-    def run(self, img0, img1, timestep, scale, want_all):
-        """Shared engine call.  Returns merged[-1] (want_all=False) or the full forward structure."""
+    @staticmethod
+    def _io(dtype):
+        return {torch.float32: _lib.RIFE_F32, torch.float16: _lib.RIFE_F16, torch.uint8: _lib.RIFE_U8}[dtype]
+
+    @staticmethod
+    def padded_size(h, w, scale):
+        """The network needs H, W multiples of 64/scale; the reference's callers zero-pad right/bottom and
+        crop the result (inference_img.py:62-67,111).  Here the first kernel pads and the last one crops."""
+        m = int(round(64 / float(scale)))
+        return (h + m - 1) // m * m, (w + m - 1) // m * m
+
+    def plan_for(self, device, prec, b, c, h, w, scale, slot=0, pad=True):
+        hp, wp = self.padded_size(h, w, scale) if pad else (h, w)
+        pl = self._get_plan(device, prec, b, c, hp, wp, scale, slot)
+        if (hp, wp) != (h, w) or getattr(pl, "frame", (hp, wp)) != (h, w):
+            _lib.check(_lib.load().rife_plan_set_frame_size(pl.handle, h, w))
+        pl.frame = (h, w)
+        return pl
+
+    def run(self, img0, img1, timestep, scale, want_all, pad=False):
+        """Shared engine call.  Returns merged[-1] (want_all=False) or the full forward structure.
+        float tensors are NCHW (B,C,H,W); uint8 tensors are HWC (B,H,W,C) frames (divided by 255 on the way in,
+        `(x*255).byte()` on the way out).  pad=True accepts any H, W (zero-pad + crop inside the kernels)."""
         self._check_input(img0)
         lib = _lib.load()
-        b, c, h, w = img0.shape
+        u8 = img0.dtype == torch.uint8
+        if u8:
+            b, h, w, c = img0.shape
+        else:
+            b, c, h, w = img0.shape
         img0 = img0.contiguous()
         img1 = img1.contiguous()
         dev = img0.device
-        prec = self._resolve_precision(img0.dtype)
-        pl = self._get_plan(dev, prec, b, c, h, w, scale)
-        io = _lib.RIFE_F32 if img0.dtype == torch.float32 else _lib.RIFE_F16
+        prec = self._resolve_precision(torch.float16 if u8 else img0.dtype)
+        pl = self.plan_for(dev, prec, b, c, h, w, scale, 0, pad or u8)
+        io = self._io(img0.dtype)
         ts = self._timesteps(timestep, b)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
@@ -219,6 +244,8 @@ class IFNet(nn.Module):
                 out = torch.empty_like(img0)
                 _lib.check(lib.rife_inference(pl.handle, img0.data_ptr(), img1.data_ptr(), ts, out.data_ptr(), io, stream))
                 return out
+            if u8:
+                raise TypeError("IFNet.forward returns float flows / masks: pass float frames")
             o = _lib.IFNetOutputs()
             flows = [torch.empty((b, 4, h, w), dtype=img0.dtype, device=dev) for _ in range(5)]
             w0 = [torch.empty_like(img0) for _ in range(5)]

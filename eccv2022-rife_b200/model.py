@@ -46,23 +46,30 @@ class Model:
         if rank == 0:
             torch.save(self.flownet.state_dict(), "{}/flownet.pkl".format(path))
 
-    def inference(self, img0, img1, timestep=0.5, scale=1.0):
-        """RIFE_HDv3.py:56-60.  Positional order (img0, img1, timestep, scale) is the reference's."""
-        return self.flownet.run(img0, img1, timestep, scale, want_all=False)
+    def inference(self, img0, img1, timestep=0.5, scale=1.0, pad=False):
+        """RIFE_HDv3.py:56-60.  Positional order (img0, img1, timestep, scale) is the reference's.
+        Extensions: pad=True accepts any H, W (the zero-pad to 64/scale and the crop the reference's callers do around
+        this call happen inside the first / last kernel); uint8 tensors are taken as HWC (B,H,W,C) frames."""
+        return self.flownet.run(img0, img1, timestep, scale, want_all=False, pad=pad)
 
     def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0):
-        """End-to-end call on HOST (ideally pinned) NCHW tensors: H2D copies, inference and the D2H copy of the
-        result are enqueued on `stream` (default: current) by rife_inference_host; returns without syncing.
+        """End-to-end call on HOST (ideally pinned) tensors -- NCHW float16/float32, or HWC uint8 frames exactly as a
+        video decoder delivers them (any H, W): H2D copies, inference and the D2H copy of the result are enqueued on
+        `stream` (default: current) by rife_inference_host; returns without syncing.
         `slot` selects an independent plan (workspace + staging buffers): calls with different slots on different
         streams overlap their PCIe copies with each other's compute."""
         net = self.flownet
         if img0_host.is_cuda or out_host.is_cuda:
             raise ValueError("inference_host takes host tensors")
         lib = _lib.load()
-        b, c, h, w = img0_host.shape
-        prec = net._resolve_precision(img0_host.dtype)
-        pl = net._get_plan(device, prec, b, c, h, w, scale, slot)
-        io = _lib.RIFE_F32 if img0_host.dtype == torch.float32 else _lib.RIFE_F16
+        u8 = img0_host.dtype == torch.uint8
+        if u8:
+            b, h, w, c = img0_host.shape
+        else:
+            b, c, h, w = img0_host.shape
+        prec = net._resolve_precision(torch.float16 if u8 else img0_host.dtype)
+        pl = net.plan_for(device, prec, b, c, h, w, scale, slot, True)
+        io = net._io(img0_host.dtype)
         ts = net._timesteps(timestep, b)
         with torch.cuda.device(device):
             st = (stream or torch.cuda.current_stream()).cuda_stream

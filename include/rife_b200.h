@@ -38,7 +38,9 @@ typedef enum rife_status {
   RIFE_ERR_NOT_DEVICE_PTR = -7 /* a pointer that must be device memory is not            */
 } rife_status;
 
-typedef enum rife_dtype { RIFE_F32 = 0, RIFE_F16 = 1 } rife_dtype;
+/* RIFE_F32 / RIFE_F16: NCHW float frames in [0,1].  RIFE_U8: HWC uint8 frames (B,h,w,C) as cv2 / video decoders deliver
+ * them; the library applies the callers' `/255.` on input and `(x*255).byte()` on output (inference_video.py:191,267). */
+typedef enum rife_dtype { RIFE_F32 = 0, RIFE_F16 = 1, RIFE_U8 = 2 } rife_dtype;
 
 /* Arithmetic mode of the whole pipeline.
  *  RIFE_PRECISION_FP32: fp32 storage, fp32 FMA convs        (<= 1e-4 max-abs vs reference fp32)
@@ -79,6 +81,11 @@ int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H
                      float scale, void* workspace, size_t workspace_bytes,
                      const float* gridx_host, const float* gridy_host);
 int rife_plan_destroy(rife_plan* p);
+/* Frame size seen by the caller, (h, w) <= the plan's padded (H, W) (default: H, W).  Inputs are then (B,C,h,w) /
+ * (B,h,w,C) tensors, zero-padded on the right / bottom inside the first kernel and every output is cropped back to
+ * (h, w) -- the F.pad / [:h, :w] the reference's callers wrap around Model.inference (inference_img.py:62-67,111,
+ * inference_video.py:199-202,267). */
+int rife_plan_set_frame_size(rife_plan* p, int h, int w);
 /* Per-kernel timing: when enabled, every launch of the pipeline is bracketed by CUDA events on the launch
  * stream.  After the stream has been synchronised, rife_plan_get_profile returns (up to `cap`) the stage names
  * (pointers valid until the next run) and durations in ms of the LAST run; return value = number of stages. */

@@ -200,3 +200,46 @@ def test_batch_consistency_fp16(pkg):
     assert torch.equal(full, m.inference(a, b))
     for i in range(3):
         assert torch.equal(full[i:i + 1], m.inference(a[i:i + 1], b[i:i + 1]))
+
+
+# ---------------------------------------------------------------------------------------------- pad/crop + uint8 frames
+def test_unpadded_frames_pad_and_crop(pkg):
+    """Callers of the reference pad to a multiple of 32/64 and crop (inference_img.py:62-67,111); pad=True does both
+    inside the kernels and must equal the explicit pad -> inference -> crop."""
+    rng = np.random.default_rng(21)
+    a = cu(rng.random((2, 3, 100, 150), dtype=np.float32))
+    b = cu(rng.random((2, 3, 100, 150), dtype=np.float32))
+    m = seeded_model(pkg, AMP, "fp32")
+    out = m.inference(a, b, 0.5, 1.0, pad=True)
+    assert out.shape == a.shape
+    ap, bp = torch.nn.functional.pad(a, (0, 42, 0, 28)), torch.nn.functional.pad(b, (0, 42, 0, 28))   # -> 128 x 192
+    ref = m.inference(ap, bp)[:, :, :100, :150]
+    assert torch.equal(out, ref)
+    cpu = T.model_inference(torch_state_dict(m), ap.cpu(), bp.cpu())[:, :, :100, :150].numpy()
+    assert np.abs(out.cpu().numpy() - cpu).max() < TOL32
+
+
+def test_uint8_hwc_frames(pkg):
+    """uint8 HWC frames in / out = `frame / 255.` ... `(mid * 255).byte()` of inference_video.py:191,267."""
+    rng = np.random.default_rng(22)
+    lo = torch.from_numpy(rng.random((2, 3, 12, 20), dtype=np.float32))
+    big = torch.nn.functional.interpolate(lo, size=(90, 150), mode="bicubic", align_corners=False).clamp(0, 1)
+    f0 = (big * 255).byte().permute(0, 2, 3, 1).contiguous()                 # (B, h, w, C) uint8
+    f1 = (big.roll(3, 3) * 255).byte().permute(0, 2, 3, 1).contiguous()
+    for prec, tol in (("fp32", 1), ("fp16", 2)):
+        m = seeded_model(pkg, AMP, prec)
+        m.flownet.precision = prec
+        out = m.flownet.run(f0.to(DEV), f1.to(DEV), 0.5, 1.0, want_all=False)
+        assert out.dtype == torch.uint8 and out.shape == f0.shape
+        a = torch.nn.functional.pad(f0.permute(0, 3, 1, 2).float() / 255., (0, 42, 0, 38))
+        b = torch.nn.functional.pad(f1.permute(0, 3, 1, 2).float() / 255., (0, 42, 0, 38))
+        ref = (T.model_inference(torch_state_dict(m), a, b)[:, :, :90, :150] * 255).byte().permute(0, 2, 3, 1)
+        diff = (out.cpu().int() - ref.int()).abs()
+        assert int(diff.max()) <= tol and float((diff > 0).float().mean()) < (0.02 if prec == "fp32" else 0.5)
+    # pinned host path
+    m = seeded_model(pkg, AMP, "fp16")
+    h0, h1 = f0.pin_memory(), f1.pin_memory()
+    ho = torch.empty_like(f0).pin_memory()
+    m.inference_host(h0, h1, ho)
+    torch.cuda.synchronize()
+    assert int((ho.int() - out.cpu().int()).abs().max()) == 0
