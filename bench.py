@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RIFE_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
-    ap.add_argument("--pairs", type=int, default=4, help="frame pairs per step per GPU (batch of one Model.inference)")
+    ap.add_argument("--pairs", type=int, default=8, help="frame pairs per step per GPU (batch of one Model.inference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -259,17 +259,25 @@ def main():
     ms_per_step = ms / args.steps
     value = world * P * args.steps / (ms / 1e3)
 
-    # ---- (2) end to end through the host-buffer API: pinned host frames -> H2D -> inference -> D2H, every step.
-    #      Three plan slots on three streams: the PCIe copies of one step overlap the compute of its neighbours.
+    # ---- (2) end to end through the host-buffer C-ABI call (rife_inference_host): pinned host frames exactly as a video
+    #      decoder delivers them -- uint8 HWC, true 1080 x 1920 (the library pads to 1088 and crops back) -> H2D ->
+    #      inference -> D2H of the uint8 result, every step.  Three plan slots on three streams: the PCIe copies of
+    #      one step overlap the compute of its neighbours.
     NSLOT = 3
-    host_out = [torch.empty((P, CH, H, W), dtype=dt).pin_memory() for _ in range(NSLOT)]
+    FH, FW = 1080, 1920
+    u8_sets = []
+    for a, b in host_sets:
+        fa = (a[:, :, :FH, :FW].float() * 255).byte().permute(0, 2, 3, 1).contiguous().pin_memory()
+        fb = (b[:, :, :FH, :FW].float() * 255).byte().permute(0, 2, 3, 1).contiguous().pin_memory()
+        u8_sets.append((fa, fb))
+    host_out = [torch.empty((P, FH, FW, CH), dtype=torch.uint8).pin_memory() for _ in range(NSLOT)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSLOT)]
     cur = torch.cuda.current_stream()
 
     def e2e_steps(n):
         for i in range(n):
             k = i % NSLOT
-            a, b = host_sets[i % NSETS]
+            a, b = u8_sets[i % NSETS]
             model.inference_host(a, b, host_out[k], stream=streams[k], slot=k)
 
     e2e_steps(2 * NSLOT)
@@ -284,10 +292,12 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = world * P * args.steps / (ms_e2e / 1e3)
-    frame_bytes = P * CH * H * W * esz
+    frame_bytes = P * CH * FH * FW
 
     # ---- (3) per-kernel CUDA-event timing (separate pass over the same steps so that `value` is undisturbed)
     plan = net._plans[next(k for k in net._plans if k[-1] == 0)]
+    lib.rife_plan_set_frame_size(plan.handle, H, W)   # slot 0 was last used by the 1080-row e2e path
+    plan.frame = (H, W)
     lib.rife_plan_set_profiling(plan.handle, 1)
     acc, cnt = {}, {}
     names = (C.c_char_p * 128)()
@@ -323,8 +333,8 @@ def main():
     achieved = alg[rk] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
     tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tp) and P == 4 and args.precision == "fp16":
-        traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
+    if os.path.exists(tp) and args.precision == "fp16":
+        traffic = json.load(open(tp)).get("traffic_bytes_per_launch") * P / 4.0   # captured at P = 4; bytes scale with P
     roofline = {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[rk], "kernel_ms": k_ms,
@@ -343,7 +353,8 @@ def main():
                    "parallelism": f"frame-pair sharding x{world}, no collective",
                    "l2_policy": f"inputs rotate over {NSETS} distinct batches; each step streams >1 GB of intermediates (> 126 MB L2)"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": frame_bytes,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "rife_inference_host: pinned uint8 HWC 1080x1920 frames in, uint8 HWC frame out, 3 plan slots / streams"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
