@@ -570,6 +570,54 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
   }
 }
 
+
+// fp16-storage fast path of the final merge (Model.inference only wants merged[-1]): the full-resolution flow of
+// the first nlev-1 blocks is in `fbuf`, the last block's tmp is at full resolution (s = 1), and only the image
+// channels (upper 8 bytes of each 16-byte SRC pixel) are blended.  fp32 arithmetic, fp32 coordinates.
+__device__ __forceinline__ void warp_img4(const __half* __restrict__ src, int H, int W, const WarpGeom& g, float gx,
+                                          float gy, float fx, float fy, float (&out)[4]) {
+  const float nx = gx + __fmul_rn(fx, g.inv_halfw);
+  const float ny = gy + __fmul_rn(fy, g.inv_halfh);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
+  ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float ax = ix - x0f, ay = iy - y0f;
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int dx = (x0 + 1 < W) ? SRC_C : 0, dy = (y0 + 1 < H) ? W * SRC_C : 0;  // beyond the edge the weight is 0
+  const __half* p = src + (y0 * W + x0) * SRC_C + 4;
+  float v00[4], v01[4], v10[4], v11[4];
+  ld4(p, v00); ld4(p + dx, v01); ld4(p + dy, v10); ld4(p + dy + dx, v11);
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
+}
+
+template <typename Tio>
+__global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__ tmp, const __half* __restrict__ src0,
+                                                      const __half* __restrict__ src1, const float* __restrict__ gridx,
+                                                      const float* __restrict__ gridy, const float* __restrict__ fbuf,
+                                                      Tio* __restrict__ omerged, int C, int H, int W, WarpGeom geom,
+                                                      ImgLayout lay) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= lay.w || y >= lay.h) return;
+  const size_t pix = ((size_t)b * H + y) * W + x;
+  float flow[4], t8[8];
+  ld4(fbuf + pix * 4, flow);
+  ld8(tmp + pix * TMP_C, t8);   // channels 0..3 flow of the last block (scale 1), 4 mask logit
+#pragma unroll
+  for (int c = 0; c < 4; ++c) flow[c] += t8[c];                                    // IFNet_HDv3.py:152
+  const float gx = gridx[x], gy = gridy[y];
+  float a[4], c[4];
+  warp_img4(src0 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);   // IFNet_HDv3.py:155
+  warp_img4(src1 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);   // IFNet_HDv3.py:156
+  const float m = 1.f / (1.f + __expf(-t8[4]));                                    // IFNet_HDv3.py:158
+  for (int ch = 0; ch < C; ++ch)
+    omerged[(size_t)(b * lay.sb + ch * lay.sc + y * lay.sy + x * lay.sx)] = from_f<Tio>(a[ch] * m + c[ch] * (1.f - m));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // stand-alone operators (NCHW, op-level API)
 template <typename Tio>
@@ -760,6 +808,20 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   const ImgLayout lay = make_layout(io_dtype, c.C, fh, fw);
   if (io_dtype == RIFE_U8 && (o.flow || o.mask)) RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: flow / mask outputs need a float io dtype");
   const dim3 egrid(nblk((size_t)fw, 256), (unsigned)fh, (unsigned)c.B);
+  static const bool no_fast_merge = getenv("RIFE_NO_FAST_MERGE") != nullptr;
+  if (c.half_act && !no_fast_merge && o.merged && !o.flow && !o.mask && !o.warped0 && !o.warped1 && nlev >= 2 &&
+      fbuf_levels == nlev - 1 && levels[nlev - 1].s == 1) {
+    const __half* tmp = (const __half*)levels[nlev - 1].ptr;
+#define RIFE_MERGE(TIO)                                                                                              \
+  merge_h_kernel<TIO><<<egrid, 256, 0, st>>>(tmp, (const __half*)c.src0, (const __half*)c.src1, c.gridx, c.gridy, fbuf, \
+                                             (TIO*)o.merged, c.C, c.H, c.W, g, lay)
+    if (io_dtype == RIFE_F32) RIFE_MERGE(float);
+    else if (io_dtype == RIFE_F16) RIFE_MERGE(__half);
+    else RIFE_MERGE(uint8_t);
+#undef RIFE_MERGE
+    RIFE_LAUNCH_CHECK();
+    return RIFE_OK;
+  }
 #define RIFE_EVAL(T, TIO)                                                                                         \
   eval_kernel<T, T, TIO><<<egrid, 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
                                                        c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
