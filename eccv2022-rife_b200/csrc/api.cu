@@ -115,8 +115,10 @@ struct rife_weights {
   int device = 0;
   int precision = RIFE_PRECISION_FP32;
   bool force_nhwc = false;  // test hook: never pick the halo kernel
-  bool head_hk = false;     // Head / block i run on the halo kernel with planar-8 activations
-  bool blk_hk[5] = {false, false, false, false, false};
+  bool head_hk = false;     // Head runs on the halo kernel with planar-8 activations
+  // per block: 0 = NHWC tcgen05 kernel everywhere; 1 = halo kernel everywhere (planar-8 activations);
+  // 2 = conv0.* on the NHWC kernel (conv0.1 stores planar-8), ResConv x8 + lastconv on the halo kernel (streamed weights)
+  int blk_hk[5] = {0, 0, 0, 0, 0};
   std::vector<void*> allocs;
   DevLayer head[4];
   struct Block {
@@ -234,9 +236,9 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
       if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
     }
     if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last, /*ps_layout=*/true))) return fail(st);
-    bool all = B.conv00.use_hk && B.conv01.use_hk && B.last.use_hk;
-    for (int j = 0; j < 8; ++j) all = all && B.res[j].use_hk;
-    w->blk_hk[i] = all;
+    bool tail = B.last.use_hk;
+    for (int j = 0; j < 8; ++j) tail = tail && B.res[j].use_hk;
+    w->blk_hk[i] = (tail && B.conv00.use_hk && B.conv01.use_hk) ? 1 : (tail ? 2 : 0);
   }
   w->head_hk = w->head[0].use_hk && w->head[1].use_hk && w->head[2].use_hk && w->head[3].use_hk;
   *out = w;
@@ -498,7 +500,9 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     const int s = L.s[i], c_ = kBlockC[i];
     const int hs = H / s, wsz = W / s;
     const std::string bn = "b" + std::to_string(i);
-    const bool hk = half_act && w->blk_hk[i];
+    const int hkm = half_act ? w->blk_hk[i] : 0;
+    const bool hk = hkm == 1;            // conv0.* on the halo kernel (planar-8 block input)
+    const bool hk_tail = hkm != 0;       // ResConv x8 + lastconv on the halo kernel
     RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
     if (i > 0 && s <= 2) fbuf_levels = i;  // every full-resolution pixel was sampled: fbuf = flow after blocks [0, i)
     ConvIO io;
@@ -508,17 +512,19 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, hk, st));
     // conv0.1: stride 2 on (hs/2, wsz/2) == 2x2 taps on (hs/4, wsz/4)
     io.H = hs / 4; io.W = wsz / 4; io.in = p->at(L.c0); io.out = p->at(L.act_a); io.epi = EPI_LRELU; io.out_c = c_;
+    io.planar_out = (hk_tail && !hk) ? 1 : 0;
     RIFE_STAGE(bn + ".conv0.1", run_conv(p, w->blk[i].conv01, io, hk, st));
+    io.planar_out = 0;
     void* cur = p->at(L.act_a);
     void* nxt = p->at(L.act_b);
     for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
       io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
-      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk, st));
+      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk_tail, st));
       void* t = cur; cur = nxt; nxt = t;
     }
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
     io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
-    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk, st));
+    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk_tail, st));
     lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = s;
 
     EvalOut eo;
@@ -639,7 +645,8 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
   io.B = B; io.H = gh; io.W = gw; io.in = xin; io.res = res; io.out = yout; io.epi = epi; io.out_c = out_c_store;
   io.co_per_par = cpp;
   if (precision == RIFE_PRECISION_FP16) {
-    if (d.use_hk) RIFE_SC(launch_conv_halo_f32io(d.hk, io, st));
+    // streamed-weight halo instantiations exist for the ResConv / lastconv epilogues only
+    if (d.use_hk && !(d.hk.stream && epi != EPI_RES && epi != EPI_PS)) RIFE_SC(launch_conv_halo_f32io(d.hk, io, st));
     else RIFE_SC(launch_conv_umma_f32io(d.h16, io, st));
   } else {
     RIFE_SC(launch_conv_f32(d.f32, io, st));

@@ -153,6 +153,7 @@ struct ConvIO {
   int co_per_par = 0;         // EPI_PS / EPI_CONVT / EPI_HEADT: output channels per parity
   int in_pitch = 0;           // channels per pixel of the tensor `in` points into (0 = cin: dense); fp32 path only
   int res_pitch = 0;          // same for `res` (0 = out_c)
+  int planar_out = 0;         // NHWC tcgen05 kernel, EPI_LRELU only: store planar-8 [B][C/8][H][W][8] (feeds conv_halo.cu)
 };
 
 int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);

@@ -38,6 +38,7 @@ struct HaloParams {
   int kgroups, ksteps, R, mt;  // mt = vertically stacked M-tiles per pipeline step (they share one halo load)
   int plane_bytes, a_stage_bytes, a_tx_bytes, stages;
   int nentries, ne, ncols, tmem_cols, n_valid, w_bytes, wtile_bytes;
+  int nb, wtile_al;  // weight streaming: ring of nb tiles of wtile_al bytes (0 = weights resident)
   int epi, out_c, cpp;
   const __half* w;
   const float* bias;
@@ -136,6 +137,15 @@ __device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
   st8(dst + 8, a);
 }
 
+template <int I> struct IntC { static constexpr int value = I; };
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F& f) {
+  if constexpr (I < N) {
+    f(IntC<I>{});
+    static_for<N, I + 1>(f);
+  }
+}
+
 // Compile-time MMA schedules (must match halo_pack_weights): KIND 0 = 3x3 taps, 1 = 2x2 taps on the s2d grid,
 // 2 = ConvTranspose(4,2,1)+PixelShuffle as (output parity, tap) pairs.
 template <int KIND> struct Sched;
@@ -184,6 +194,23 @@ __device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64
   }
 }
 
+
+// weight-streaming variant: the MMAs of ONE schedule entry (one weight tile) for all MT stacked M-tiles
+template <int KIND, int KSTEPS, int NE, int MT, int E, int M = 0, int KK = 0>
+__device__ __forceinline__ void issue_entry(uint32_t acc0, uint32_t ncols, uint64_t a_base0, uint32_t mt_step,
+                                            uint64_t b_base, uint32_t idesc) {
+  using S = Sched<KIND>;
+  if constexpr (M < MT) {
+    constexpr int pitch = TW + S::R;
+    constexpr int plane16 = (TH * MT + S::R) * pitch;
+    constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
+    umma_f16_c<!(S::first(E) && KK == 0)>(acc0 + (uint32_t)M * ncols + S::col16(E) * 16,
+                                          a_base0 + (uint64_t)((uint32_t)M * mt_step + a_off), b_base + (uint64_t)(2 * KK * NE),
+                                          idesc);
+    if constexpr (KK + 1 < KSTEPS) issue_entry<KIND, KSTEPS, NE, MT, E, M, KK + 1>(acc0, ncols, a_base0, mt_step, b_base, idesc);
+    else issue_entry<KIND, KSTEPS, NE, MT, E, M + 1, 0>(acc0, ncols, a_base0, mt_step, b_base, idesc);
+  }
+}
 
 // Per-tile epilogue context of one thread (= one pixel column position tx_ of the tile; rows come from (mi, ty_)).
 struct EpiCtx {
@@ -309,13 +336,17 @@ __device__ __forceinline__ void epi_chunk_rt(const HaloParams& p, const EpiCtx& 
 // warps w and w+4 sharing a TMEM lane quarter and splitting the output rows.
 template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS) ? 8 : 4; };
 
-template <int KIND, int KSTEPS, int NE, int MT, int EPI>
-__global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a,
-                                                                const HaloParams p) {
+// STREAM: the layer's weights do not fit in smem next to the activation ring (c >= 96): an extra producer warp streams
+// one weight tile per schedule entry through a ring of p.nb slots, re-using every tile for the MT stacked M-tiles.
+template <int KIND, int KSTEPS, int NE, int MT, int EPI, bool STREAM = false>
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value + (STREAM ? 32 : 0))
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t a_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t w_full;
+  __shared__ __align__(8) uint64_t b_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t t_full[2];
   __shared__ __align__(8) uint64_t t_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -327,10 +358,10 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
   __shared__ uint32_t tab_d[MAX_MMA];               // accumulator column offset | (accumulate << 31)
 
   constexpr int NUM_EPI_WARPS = EpiWarps<EPI>::value;
-  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // without the optional weight-streaming warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_smem = w_smem + (((uint32_t)p.w_bytes + 1023u) & ~1023u);
+  const uint32_t a_smem = w_smem + (STREAM ? (uint32_t)(p.nb * p.wtile_al) : (((uint32_t)p.w_bytes + 1023u) & ~1023u));
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -341,6 +372,12 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
       mbar_init(smem_u32(&a_empty[s]), p.epi == EPI_RES ? 1 + NUM_EPI_WARPS : 1);
     }
     mbar_init(smem_u32(&w_full), 1);
+    if (STREAM) {
+      for (int i = 0; i < p.nb; ++i) {
+        mbar_init(smem_u32(&b_full[i]), 1);
+        mbar_init(smem_u32(&b_empty[i]), 1);
+      }
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&t_full[i]), 1);
       mbar_init(smem_u32(&t_empty[i]), NUM_EPI_WARPS);  // one arrive per epilogue warp
@@ -353,7 +390,7 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 2 + NUM_EPI_WARPS) {
     for (int i = threadIdx.x - 64; i < p.ncols; i += NUM_THREADS - 64) {
       s_bias[i] = p.bias[i];
       if (p.beta && i < 128) s_beta[i] = p.beta[i];
@@ -378,11 +415,13 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer: resident weights once, then one halo box per tile
-      const uint32_t wb = smem_u32(&w_full);
-      mbar_expect_tx(wb, (uint32_t)p.w_bytes);
-      for (int off = 0; off < p.w_bytes; off += 32768) {
-        const int n = min(32768, p.w_bytes - off);
-        bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wb);
+      if (!STREAM) {
+        const uint32_t wb = smem_u32(&w_full);
+        mbar_expect_tx(wb, (uint32_t)p.w_bytes);
+        for (int off = 0; off < p.w_bytes; off += 32768) {
+          const int n = min(32768, p.w_bytes - off);
+          bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wb);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -399,6 +438,23 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = t_wait;
     }
+  } else if (STREAM && warp == 2 + NUM_EPI_WARPS) {
+    if (lane == 0) {
+      // ---------------- weight-tile producer: entry e of every tile -> ring slot
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int e = 0; e < p.nentries; ++e) {
+          mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
+          const uint32_t fb = smem_u32(&b_full[bs]);
+          mbar_expect_tx(fb, (uint32_t)p.wtile_bytes);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)e * p.wtile_bytes;
+          for (int off = 0; off < p.wtile_bytes; off += 32768)
+            bulk_load(w_smem + bs * p.wtile_al + off, src + off, (uint32_t)min(32768, p.wtile_bytes - off), fb);
+          if (++bs == p.nb) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer
@@ -407,16 +463,29 @@ __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value) conv_halo_kern
       const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
       long long t_w = 0, t_te = 0, t_af = 0;
       const long long t_begin = clock64();
-      mbar_wait_t(smem_u32(&w_full), 0, t_w);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
+      if (!STREAM) mbar_wait_t(smem_u32(&w_full), 0, t_w);
+      int stage = 0, it = 0, bs = 0;
+      uint32_t phase = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait_t(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u, t_te);
         mbar_wait_t(smem_u32(&a_full[stage]), phase, t_af);
         tc_fence_after();
         const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
-        if constexpr (KIND >= 0) {
+        if constexpr (KIND >= 0 && STREAM) {
+          const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)NE * 16u, 128u);
+          const uint32_t acc0 = tmem_base + (uint32_t)(buf * MT * p.ncols);
+          auto one = [&](auto ec) {
+            constexpr int E = decltype(ec)::value;
+            mbar_wait_t(smem_u32(&b_full[bs]), bph, t_w);
+            tc_fence_after();
+            issue_entry<KIND, KSTEPS, NE, MT, E>(acc0, (uint32_t)p.ncols, a_desc0 + (uint64_t)sa16, mt_step,
+                                                 b_desc0 + (uint64_t)((w_smem + (uint32_t)(bs * p.wtile_al)) >> 4), idesc);
+            umma_commit(smem_u32(&b_empty[bs]));
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          };
+          static_for<Sched<KIND>::NENT>(one);
+        } else if constexpr (KIND >= 0) {
           const uint64_t b_base = make_desc_noswz(w_smem, (uint32_t)NE * 16u, 128u);
 #pragma unroll
           for (int m = 0; m < MT; ++m)
@@ -618,14 +687,23 @@ int num_sms() {
 
 }  // namespace
 
-bool halo_fits(const HostLayer& h, bool ps_layout) {
-  if (h.cin % 16 || h.cin > 128) return false;
+// 0 = does not fit, 1 = weights resident in smem, 2 = weights streamed per schedule entry (templated shapes only:
+// the c = 96 / 128 ResConv and lastconv layers of IFBlock 2 / 1)
+int halo_mode(const HostLayer& h, bool ps_layout) {
+  if (h.cin % 16) return 0;
   const int R = h.kind == CONV_3x3 ? 2 : 1;
-  const int a_stage = (h.cin / 8) * (TH + R) * (TW + R) * 16;
-  const int w_bytes = ps_layout ? 16 * (h.cin / 8) * 64 * 16 : h.taps * (h.cin / 8) * h.npad * 16;
-  if (!ps_layout && h.npad > 128) return false;
-  return w_bytes + 2 * ((a_stage + 1023) / 1024 * 1024) + 2048 <= SMEM_BUDGET - (ps_layout ? 32 * 1024 : 0);
+  const int a_stage = ((h.cin / 8) * (TH + R) * (TW + R) * 16 + 1023) / 1024 * 1024;
+  const int ne = ps_layout ? 64 : h.npad;
+  const int w_bytes = (ps_layout ? 16 : h.taps) * (h.cin / 8) * ne * 16;
+  const int budget = SMEM_BUDGET - (ps_layout ? 32 * 1024 : 0);
+  if (h.cin <= 128 && (ps_layout || h.npad <= 128) && w_bytes + 2 * a_stage + 2048 <= budget) return 1;
+  const bool templated = h.kind == CONV_3x3 && (h.cin == 96 || h.cin == 128) &&
+                         (ps_layout ? h.convt_co == 52 : (h.npad == h.cin && h.convt_co == 0));
+  const int wtile = ((h.cin / 8) * ne * 16 + 1023) / 1024 * 1024;
+  if (templated && 2 * a_stage + 2 * wtile + 2048 <= budget) return 2;
+  return 0;
 }
+bool halo_fits(const HostLayer& h, bool ps_layout) { return halo_mode(h, ps_layout) != 0; }
 
 int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
                       std::vector<float>* beta, HaloLayer* L) {
@@ -678,6 +756,7 @@ int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
     }
   }
   L->w_bytes = (int)(packed->size() * sizeof(__half));
+  L->stream = halo_mode(h, ps_layout) == 2 ? 1 : 0;
   return RIFE_OK;
 }
 
@@ -710,12 +789,15 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   p.R = L.kind == CONV_3x3 ? 2 : 1;
   if (L.nentries * p.ksteps > MAX_MMA) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: MMA schedule too long");
   // stack up to 4 M-tiles per pipeline step for thin layers: amortises the per-step barrier chain and the halo
+  const int wtile_al = (p.kgroups * L.ne * 16 + 1023) / 1024 * 1024;
   {
-    const int w_al0 = (L.w_bytes + 1023) / 1024 * 1024;
+    // resident: all weights + >= 3 activation stages; streamed: 2 activation stages + >= 3 weight tiles
+    const int w_al0 = L.stream ? 3 * wtile_al : (L.w_bytes + 1023) / 1024 * 1024;
+    const int nst = L.stream ? 2 : 3;
     static const int mt_max = []() { const char* e = getenv("RIFE_HK_MT"); return e ? atoi(e) : 2; }();
     int mt = mt_max < 1 ? 1 : (mt_max > 4 ? 4 : mt_max);
     while (mt > 1 && (2 * mt * L.ncols > 512 || io.H < TH * mt ||
-                      w_al0 + 3 * (p.kgroups * (TH * mt + p.R) * (TW + p.R) * 16 + 1024) + 2048 > SMEM_BUDGET))
+                      w_al0 + nst * (p.kgroups * (TH * mt + p.R) * (TW + p.R) * 16 + 1024) + 2048 > SMEM_BUDGET))
       mt >>= 1;
     p.mt = mt;
   }
@@ -730,16 +812,30 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   p.wtile_bytes = p.kgroups * L.ne * 16;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.mt * L.ncols) p.tmem_cols <<= 1;
-  const int w_al = (L.w_bytes + 1023) / 1024 * 1024;
   const int budget = SMEM_BUDGET - (io.epi == EPI_PS ? 32 * 1024 : 0);  // the PixelShuffle epilogue stages rows in 32 KB of static smem
-  int stages = (budget - w_al - 2048) / p.a_stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
+  int w_al = (L.w_bytes + 1023) / 1024 * 1024;
+  int stages;
+  p.nb = 0; p.wtile_al = wtile_al;
+  if (L.stream) {
+    stages = 2;
+    int nb = (budget - 2048 - stages * p.a_stage_bytes) / wtile_al;
+    if (nb > MAX_STAGES) nb = MAX_STAGES;
+    if (nb > L.nentries) nb = L.nentries;
+    if (nb < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: streamed layer does not fit in shared memory");
+    // spare smem goes to a third activation stage
+    if (budget - 2048 - nb * wtile_al >= 3 * p.a_stage_bytes) stages = 3;
+    p.nb = nb;
+    w_al = nb * wtile_al;
+  } else {
+    stages = (budget - w_al - 2048) / p.a_stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: layer does not fit in shared memory");
+  }
   int smem = w_al + stages * p.a_stage_bytes + 1024;
   // co-resident CTAs per SM hide the per-step latency chain of thin layers when smem and TMEM allow
   int per_sm = 1;
   static const int persm_max = []() { const char* e = getenv("RIFE_HK_PERSM"); return e ? atoi(e) : 4; }();
-  for (int k = persm_max; k >= 2; --k) {
+  for (int k = L.stream ? 1 : persm_max; k >= 2; --k) {
     if (k * p.tmem_cols > 512) continue;
     int s2 = stages;
     while (s2 > 3 && k * (w_al + s2 * p.a_stage_bytes + 2048) > 224 * 1024) --s2;
@@ -796,6 +892,19 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   RIFE_HK_CASE(0, 4, 64, 2, EPI_RES)        // block3 ResConv       (3x3, 64 -> 64)
   RIFE_HK_CASE(2, 4, 64, 1, EPI_PS)         // block3.lastconv      (ConvT+PS, 64 -> 4x64)
 #undef RIFE_HK_CASE
+#define RIFE_HK_STREAM(K, KS, N_, MT_, E_)                                                                   \
+  if (!done && L.stream && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {       \
+    RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_, true>));                        \
+    conv_halo_kernel<K, KS, N_, MT_, E_, true><<<grid, 96 + 32 * EpiWarps<E_>::value, smem, st>>>(tm_a, p);  \
+    done = true;                                                                                             \
+  }
+  RIFE_HK_STREAM(0, 6, 96, 2, EPI_RES)      // block2 ResConv       (3x3, 96 -> 96), two stacked M-tiles
+  RIFE_HK_STREAM(0, 6, 96, 1, EPI_RES)
+  RIFE_HK_STREAM(0, 8, 128, 1, EPI_RES)     // block1 ResConv       (3x3, 128 -> 128)
+  RIFE_HK_STREAM(2, 6, 64, 1, EPI_PS)       // block2.lastconv      (ConvT+PS, 96 -> 4x64)
+  RIFE_HK_STREAM(2, 8, 64, 1, EPI_PS)       // block1.lastconv      (ConvT+PS, 128 -> 4x64)
+#undef RIFE_HK_STREAM
+  if (!done && L.stream) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no streamed instantiation for this layer / epilogue");
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
     conv_halo_kernel<-1, 0, 0, 0, -1><<<grid, 64 + 32 * EpiWarps<-1>::value, smem, st>>>(tm_a, p);

@@ -32,7 +32,7 @@ struct UmmaParams {
   int ntaps, nchunks, kc, stages;
   int npad, n_valid, tmem_cols, nw;  // nw = accumulator columns per CTA (N split over blockIdx.y)
   int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
-  int epi, out_c, cpp;
+  int epi, out_c, cpp, planar_out;
   const float* bias;
   const float* beta;
   const __half* res;
@@ -277,7 +277,22 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
           }
-          if (n0 < p.n_valid) store16h(p.out + pix * p.out_c + n0, v);
+          if (n0 < p.n_valid) {
+            if (p.planar_out) {
+              // planar-8 destination [B][out_c/8][H][W][8]: the consumer is the halo kernel (conv_halo.cu)
+              const size_t hw = (size_t)p.H * p.W;
+              __half* d = p.out + (((size_t)b * (p.out_c >> 3) + (n0 >> 3)) * hw + (size_t)y * p.W + x) * 8;
+              float a8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a8[i] = v[i];
+              st8(d, a8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a8[i] = v[8 + i];
+              st8(d + hw * 8, a8);
+            } else {
+              store16h(p.out + pix * p.out_c + n0, v);
+            }
+          }
         } else if constexpr (EPI == EPI_LRELU_S2D) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
@@ -442,7 +457,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   const int ksteps = p.ntaps * p.nchunks;
   if (stages > ksteps) stages = ksteps;
   p.stages = stages;
-  p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par;
+  p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par; p.planar_out = io.planar_out;
   p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
   if (L.kind == CONV_3x3) {

@@ -132,10 +132,11 @@ def test_conv3x3_fp16_tcgen05(pkg, ci, co, h, w, stride, prec):
     assert np.abs(y - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))   # fp16 output rounding (2^-11 relative)
 
 
-@pytest.mark.parametrize("prec,c", [(1, 64), (3, 64), (1, 32), (1, 96)])
-def test_resconv_fp16_tcgen05(pkg, prec, c):
+@pytest.mark.parametrize("prec,c,hh", [(1, 64, 20), (3, 64, 20), (1, 32, 20), (1, 96, 20), (1, 96, 40), (3, 96, 20),
+                                       (1, 128, 20), (1, 128, 36), (1, 192, 20)])
+def test_resconv_fp16_tcgen05(pkg, prec, c, hh):
     rng = np.random.default_rng(5)
-    x = _h(rng.standard_normal((1, c, 20, 28)).astype(np.float32))
+    x = _h(rng.standard_normal((2, c, hh, 28)).astype(np.float32))
     wt = _h((rng.standard_normal((c, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
     b = rng.standard_normal(c).astype(np.float32)
     beta = rng.standard_normal(c).astype(np.float32)
@@ -145,7 +146,7 @@ def test_resconv_fp16_tcgen05(pkg, prec, c):
 
 
 @pytest.mark.parametrize("prec", [1, 3])
-@pytest.mark.parametrize("ci,co,ps", [(32, 52, 1), (16, 4, 0), (192, 52, 1), (64, 52, 1)])
+@pytest.mark.parametrize("ci,co,ps", [(32, 52, 1), (16, 4, 0), (192, 52, 1), (64, 52, 1), (96, 52, 1), (128, 52, 1)])
 def test_conv_transpose_fp16_tcgen05(pkg, ci, co, ps, prec):
     lib = pkg._lib.load()
     rng = np.random.default_rng(ci + co)
