@@ -68,13 +68,13 @@ def load():
     lib.rife_conv_transpose4x4s2.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.rife_layer_create.argtypes = [C.POINTER(vp), i, vp, vp, vp, i, i, i, i]
     lib.rife_layer_destroy.argtypes = [vp]
-    lib.rife_layer_run.argtypes = [vp, vp, i, vp, i, i, i, i, vp, i, i, vp]
-    lib.rife_nhwc_from_nchw.argtypes = [vp, i, vp, i, i, i, i, i, i, vp]
-    lib.rife_nhwc_to_nchw.argtypes = [vp, i, i, vp, i, i, i, i, i, i, vp]
-    lib.rife_nhwc_resize.argtypes = [vp, i, i, vp, i, i, i, i, i, i, i, i, f, i, vp]
-    lib.rife_nhwc_warp.argtypes = [vp, i, i, vp, i, i, vp, i, i, i, i, i, i, vp, vp, vp]
-    lib.rife_nhwc_s2d.argtypes = [vp, i, i, i, vp, i, i, i, i, vp]
-    lib.rife_eccv_merge.argtypes = [vp, i, i, vp, i, i, vp, i, i, vp, i, i, vp, i, i, i, i, vp]
+    lib.rife_layer_run.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp, i, i, vp]
+    lib.rife_nhwc_from_nchw.argtypes = [vp, i, vp, i, i, i, i, i, i, i, vp]
+    lib.rife_nhwc_to_nchw.argtypes = [vp, i, i, i, vp, i, i, i, i, i, i, vp]
+    lib.rife_nhwc_resize.argtypes = [vp, i, i, i, vp, i, i, i, i, i, i, i, i, i, f, i, vp]
+    lib.rife_nhwc_warp.argtypes = [vp, i, i, i, vp, i, i, i, vp, i, i, i, i, i, i, i, vp, vp, vp]
+    lib.rife_nhwc_s2d.argtypes = [vp, i, i, i, i, vp, i, i, i, i, i, vp]
+    lib.rife_eccv_merge.argtypes = [vp, i, i, vp, i, i, vp, i, i, i, vp, i, i, i, vp, i, i, i, i, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("rife_abi_version",):

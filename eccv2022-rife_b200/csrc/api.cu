@@ -726,16 +726,20 @@ int rife_layer_create(rife_layer** out, int kind, const float* w_host, const flo
                       int cin, int cout, int cin_store, int precision) {
   if (!out || !w_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_create: null argument");
   if (kind < 0 || kind > 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_create: kind must be 0 (3x3 s1), 1 (3x3 s2) or 2 (ConvTranspose 4x4 s2)");
-  if (precision != RIFE_PRECISION_FP32) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_layer_create: the generic layer API is fp32 only in this build");
-  if (cin_store < cin || cin_store % 8) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_create: cin_store must be >= cin and a multiple of 8");
+  if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_layer_create: bad precision");
+  const bool h16 = precision == RIFE_PRECISION_FP16;
+  const int mult = (h16 && kind != 1) ? 16 : 8;  // the tcgen05 kernel consumes K in chunks of 16 channels (kind 1: 4 * cin_store)
+  if (cin < 1 || cout < 1 || cin_store < cin || cin_store % mult)
+    RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_create: cin_store must be >= cin and a multiple of " + std::to_string(mult));
   auto* l = new rife_layer();
-  l->store.precision = RIFE_PRECISION_FP32;
+  l->store.precision = precision;
+  l->store.force_nhwc = true;  // generic layers run on the NHWC kernels (no planar-8 halo variant)
   cudaGetDevice(&l->store.device);
   l->kind = kind; l->cin_store = cin_store; l->cout = cout;
   HostLayer h;
   if (kind == 0) h = pack_conv3x3(w_host, bias_host, cout, cin, cin_store);
   else if (kind == 1) h = pack_conv3x3_s2d(w_host, bias_host, cout, cin, cin_store, 4 * cin_store);
-  else { l->co_pad = round_up(cout, 4); h = pack_convT(w_host, bias_host, cin, cout, cin_store, l->co_pad); }
+  else { l->co_pad = round_up(cout, h16 ? 8 : 4); h = pack_convT(w_host, bias_host, cin, cout, cin_store, l->co_pad); }
   if (slope_host) {
     h.beta.assign(h.npad, 0.f);
     if (kind == 2) { for (int par = 0; par < 4; ++par) for (int o = 0; o < cout; ++o) h.beta[par * l->co_pad + o] = slope_host[o]; }
@@ -754,9 +758,12 @@ int rife_layer_destroy(rife_layer* l) {
   return RIFE_OK;
 }
 
-int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_pitch, int B, int H, int W,
-                   const void* res, int res_pitch, int act, void* stream) {
+int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_dtype, int out_pitch, int B, int H,
+                   int W, const void* res, int res_pitch, int act, void* stream) {
   if (!l || !in || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: null argument");
+  const bool h16 = l->store.precision == RIFE_PRECISION_FP16;
+  if (out_dtype != (h16 ? RIFE_F16 : RIFE_F32) && !(h16 && out_dtype == RIFE_F32 && act == 0))
+    RIFE_FAIL(RIFE_ERR_DTYPE, "rife_layer_run: out_dtype must match the layer precision (fp16 layers may write fp32 when act == 0)");
   ConvIO io;
   io.B = B; io.H = H; io.W = W; io.in = in; io.out = out; io.res = res;
   io.in_pitch = in_pitch; io.res_pitch = res_pitch; io.out_c = out_pitch;
@@ -773,45 +780,61 @@ int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out,
       case 3: io.epi = EPI_PRELU_ADD; break;
       default: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: bad act");
     }
-    if (out_pitch < l->d.f32.n) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: out_pitch smaller than the (4-padded) output channels");
+    const int nout = h16 ? l->d.h16.npad : l->d.f32.n;
+    if (out_pitch < nout) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: out_pitch smaller than the padded output channels (" + std::to_string(nout) + ")");
   }
+  if (act == 3 && !res) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_layer_run: act 3 needs res");
   if (l->kind == 1 && in_pitch != 0 && in_pitch != 4 * l->cin_store) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: stride-2 layers read a dense s2d tensor");
+  if (h16) {
+    // TMA / 16-byte vector access: pitches in multiples of 8 halfs, 16-byte aligned slice bases
+    io.out_f32 = out_dtype == RIFE_F32;
+    if ((in_pitch % 8) || (out_pitch % 8) || (res && res_pitch % 8) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || ((uintptr_t)res & 15))
+      RIFE_FAIL(RIFE_ERR_SHAPE, "rife_layer_run: fp16 layers need pitches in multiples of 8 and 16-byte aligned slices");
+    return launch_conv_umma(l->d.h16, io, (cudaStream_t)stream);
+  }
   return launch_conv_f32(l->d.f32, io, (cudaStream_t)stream);
 }
 
-int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int B, int C, int H, int W, int pitch, int off, void* stream) {
+static bool bad_dt(int dt) { return dt != RIFE_F32 && dt != RIFE_F16; }
+
+int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int dst_dtype, int B, int C, int H, int W, int pitch,
+                        int off, void* stream) {
   if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_from_nchw: null argument");
-  return launch_nchw_to_nhwc_slice(src, io_dtype, (float*)dst, B, C, H, W, pitch, off, (cudaStream_t)stream);
+  return launch_nchw_to_nhwc_slice(src, io_dtype, dst, dst_dtype, B, C, H, W, pitch, off, (cudaStream_t)stream);
 }
-int rife_nhwc_to_nchw(const void* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W, int sigmoid,
-                      void* stream) {
+int rife_nhwc_to_nchw(const void* src, int src_dtype, int pitch, int off, void* dst, int io_dtype, int B, int C, int H,
+                      int W, int sigmoid, void* stream) {
   if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_to_nchw: null argument");
-  return launch_nhwc_slice_to_nchw((const float*)src, pitch, off, dst, io_dtype, B, C, H, W, sigmoid, (cudaStream_t)stream);
+  return launch_nhwc_slice_to_nchw(src, src_dtype, pitch, off, dst, io_dtype, B, C, H, W, sigmoid, (cudaStream_t)stream);
 }
-int rife_nhwc_resize(const void* src, int spitch, int soff, void* dst, int dpitch, int doff, int B, int C, int Hs, int Ws,
-                     int Hd, int Wd, float mul, int accumulate, void* stream) {
+int rife_nhwc_resize(const void* src, int src_dtype, int spitch, int soff, void* dst, int dst_dtype, int dpitch, int doff,
+                     int B, int C, int Hs, int Ws, int Hd, int Wd, float mul, int accumulate, void* stream) {
   if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_resize: null argument");
   auto pow2 = [](int a, int b) { int r = a > b ? a / b : b / a; return (a > b ? a % b : b % a) == 0 && (r & (r - 1)) == 0; };
   if (!pow2(Hs, Hd) || !pow2(Ws, Wd) || (long long)Hs * Wd != (long long)Hd * Ws) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_resize: power-of-two isotropic factors only");
-  return launch_resize_nhwc((const float*)src, spitch, soff, (float*)dst, dpitch, doff, B, C, Hs, Ws, Hd, Wd, mul, accumulate,
+  return launch_resize_nhwc(src, src_dtype, spitch, soff, dst, dst_dtype, dpitch, doff, B, C, Hs, Ws, Hd, Wd, mul, accumulate,
                             (cudaStream_t)stream);
 }
-int rife_nhwc_warp(const void* src, int spitch, int soff, const void* flow, int fpitch, int foff, void* dst, int dpitch,
-                   int doff, int B, int C, int H, int W, const float* gridx_dev, const float* gridy_dev, void* stream) {
+int rife_nhwc_warp(const void* src, int src_dtype, int spitch, int soff, const void* flow, int flow_dtype, int fpitch,
+                   int foff, void* dst, int dst_dtype, int dpitch, int doff, int B, int C, int H, int W,
+                   const float* gridx_dev, const float* gridy_dev, void* stream) {
   if (!src || !flow || !dst || !gridx_dev || !gridy_dev) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_warp: null argument");
-  return launch_warp_nhwc((const float*)src, spitch, soff, (const float*)flow, fpitch, foff, (float*)dst, dpitch, doff, B, C, H,
+  return launch_warp_nhwc(src, src_dtype, spitch, soff, flow, flow_dtype, fpitch, foff, dst, dst_dtype, dpitch, doff, B, C, H,
                           W, gridx_dev, gridy_dev, (cudaStream_t)stream);
 }
-int rife_nhwc_s2d(const void* src, int spitch, int soff, int C, void* dst, int cpad, int B, int H, int W, void* stream) {
+int rife_nhwc_s2d(const void* src, int src_dtype, int spitch, int soff, int C, void* dst, int dst_dtype, int cpad, int B,
+                  int H, int W, void* stream) {
   if (!src || !dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_s2d: null argument");
   if (H % 2 || W % 2 || cpad < C) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_s2d: even H, W and cpad >= C required");
-  return launch_s2d_nhwc((const float*)src, spitch, soff, C, (float*)dst, cpad, B, H, W, (cudaStream_t)stream);
+  return launch_s2d_nhwc(src, src_dtype, spitch, soff, C, dst, dst_dtype, cpad, B, H, W, (cudaStream_t)stream);
 }
 int rife_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm, int om,
-                    const void* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W, void* stream) {
+                    int w_dtype, const void* refine, int refine_dtype, int pr, int orf, void* out, int io_dtype, int B,
+                    int H, int W, void* stream) {
   if (!w0 || !w1 || !mask || !out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_eccv_merge: null argument");
-  return launch_eccv_merge((const float*)w0, p0, o0, (const float*)w1, p1, o1, (const float*)mask, pm, om, (const float*)refine,
-                           pr, orf, out, io_dtype, B, H, W, (cudaStream_t)stream);
+  if (bad_dt(w_dtype) || (refine && bad_dt(refine_dtype))) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_eccv_merge: bad tensor dtype");
+  return launch_eccv_merge(w0, p0, o0, w1, p1, o1, mask, pm, om, w_dtype, refine, refine_dtype, pr, orf, out, io_dtype, B, H,
+                           W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -153,6 +153,7 @@ struct ConvIO {
   int co_per_par = 0;         // EPI_PS / EPI_CONVT / EPI_HEADT: output channels per parity
   int in_pitch = 0;           // channels per pixel of the tensor `in` points into (0 = cin: dense); fp32 path only
   int res_pitch = 0;          // same for `res` (0 = out_c)
+  int out_f32 = 0;            // NHWC tcgen05 kernel, EPI_LINEAR / EPI_CONVT only: the destination tensor is fp32
   int planar_out = 0;         // NHWC tcgen05 kernel, EPI_LRELU only: store planar-8 [B][C/8][H][W][8] (feeds conv_halo.cu)
 };
 
@@ -221,19 +222,21 @@ int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W
 int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st);
 
 // ------------------------------------------------------------------ generic NHWC ops (generic_ops.cu)
-// All tensors are fp32 NHWC [B][H][W][pitch]; an op touches the channel slice [off, off + C).
-int launch_nchw_to_nhwc_slice(const void* src, int io_dtype, float* dst, int B, int C, int H, int W, int pitch, int off,
-                              cudaStream_t st);
-int launch_nhwc_slice_to_nchw(const float* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W,
-                              int sigmoid, cudaStream_t st);
-int launch_resize_nhwc(const float* src, int spitch, int soff, float* dst, int dpitch, int doff, int B, int C, int Hs,
-                       int Ws, int Hd, int Wd, float mul, int accumulate, cudaStream_t st);
-int launch_warp_nhwc(const float* src, int spitch, int soff, const float* flow, int fpitch, int foff, float* dst,
-                     int dpitch, int doff, int B, int C, int H, int W, const float* gridx, const float* gridy,
-                     cudaStream_t st);
-int launch_s2d_nhwc(const float* src, int spitch, int soff, int C, float* dst, int cpad, int B, int H, int W,
-                    cudaStream_t st);
-int launch_eccv_merge(const float* w0, int p0, int o0, const float* w1, int p1, int o1, const float* mask, int pm, int om,
-                      const float* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W, cudaStream_t st);
+// Tensors are NHWC [B][H][W][pitch], each RIFE_F32 or RIFE_F16 (its own *dt argument); an op touches the channel
+// slice [off, off + C) (offsets and pitches in elements).
+int launch_nchw_to_nhwc_slice(const void* src, int io_dtype, void* dst, int ddt, int B, int C, int H, int W, int pitch,
+                              int off, cudaStream_t st);
+int launch_nhwc_slice_to_nchw(const void* src, int sdt, int pitch, int off, void* dst, int io_dtype, int B, int C, int H,
+                              int W, int sigmoid, cudaStream_t st);
+int launch_resize_nhwc(const void* src, int sdt, int spitch, int soff, void* dst, int ddt, int dpitch, int doff, int B,
+                       int C, int Hs, int Ws, int Hd, int Wd, float mul, int accumulate, cudaStream_t st);
+int launch_warp_nhwc(const void* src, int sdt, int spitch, int soff, const void* flow, int fdt, int fpitch, int foff,
+                     void* dst, int ddt, int dpitch, int doff, int B, int C, int H, int W, const float* gridx,
+                     const float* gridy, cudaStream_t st);
+int launch_s2d_nhwc(const void* src, int sdt, int spitch, int soff, int C, void* dst, int ddt, int cpad, int B, int H,
+                    int W, cudaStream_t st);
+int launch_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm, int om,
+                      int wdt, const void* refine, int rdt, int pr, int orf, void* out, int io_dtype, int B, int H, int W,
+                      cudaStream_t st);
 
 }  // namespace rife

@@ -32,7 +32,7 @@ struct UmmaParams {
   int ntaps, nchunks, kc, stages;
   int npad, n_valid, tmem_cols, nw;  // nw = accumulator columns per CTA (N split over blockIdx.y)
   int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
-  int epi, out_c, cpp, planar_out;
+  int epi, out_c, cpp, planar_out, res_pitch, out_f32;
   const float* bias;
   const float* beta;
   const __half* res;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.nw; i += NUM_THREADS - 64) {
       s_bias[i] = p.bias[n_off + i];
-      if (EPI == EPI_RES) s_beta[i] = p.beta[n_off + i];
+      if (EPI == EPI_RES || EPI >= EPI_PRELU) s_beta[i] = p.beta[n_off + i];
     }
   }
   tc_fence_before();
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
     // ResConv: fetch the residual while the MMAs run (it does not depend on them)
     constexpr int MAXRES = 6;
     uint4 resv[2 * MAXRES];
-    if constexpr (EPI == EPI_RES) {
+    if constexpr (EPI == EPI_RES || EPI == EPI_PRELU_ADD) {
       if (valid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.out_c + n_off);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n_off);
 #pragma unroll
         for (int j = 0; j < MAXRES; ++j)
           if (j < nchunk16) { resv[2 * j] = __ldg(rp + 2 * j); resv[2 * j + 1] = __ldg(rp + 2 * j + 1); }
@@ -278,7 +278,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
           }
           if (n0 < p.n_valid) {
-            if (p.planar_out) {
+            if (EPI == EPI_LINEAR && p.out_f32) {
+              // flow / mask / refine heads keep fp32 (no rounding of a value that is later scaled and accumulated)
+              float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_c + n0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else if (p.planar_out) {
               // planar-8 destination [B][out_c/8][H][W][8]: the consumer is the halo kernel (conv_halo.cu)
               const size_t hw = (size_t)p.H * p.W;
               __half* d = p.out + (((size_t)b * (p.out_c >> 3) + (n0 >> 3)) * hw + (size_t)y * p.W + x) * 8;
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
           uint4 r2[2];
           if (jb == 0) { r2[0] = resv[2 * jj]; r2[1] = resv[2 * jj + 1]; }
           else {  // slices wider than 16*MAXRES columns: fetch late (not used by the network's shapes)
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.out_c + n0);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n0);
             r2[0] = __ldg(rp); r2[1] = __ldg(rp + 1);
           }
 #pragma unroll
@@ -319,6 +324,48 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
             }
           }
           store16h(p.out + pix * p.out_c + n0, v);
+        } else if constexpr (EPI == EPI_PRELU || EPI == EPI_PRELU_ADD) {
+          // ECCV-paper net: per-channel PReLU (slopes in s_beta), optionally "+ res" afterwards (model/IFNet.py:46)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * s_beta[nl + i];
+          if constexpr (EPI == EPI_PRELU_ADD) {
+            uint4 r2[2];
+            if (jb == 0) { r2[0] = resv[2 * jj]; r2[1] = resv[2 * jj + 1]; }
+            else {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + n0);
+              r2[0] = __ldg(rp); r2[1] = __ldg(rp + 1);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const __half2* hh = reinterpret_cast<const __half2*>(&r2[h]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                v[8 * h + 2 * i] += f.x;
+                v[8 * h + 2 * i + 1] += f.y;
+              }
+            }
+          }
+          if (n0 < p.n_valid) store16h(p.out + pix * p.out_c + n0, v);
+        } else if constexpr (EPI == EPI_CONVT_PRELU) {
+          if ((p.cpp & 15) == 0) {
+            // a 16-column chunk lies inside one output parity: one 32-byte store per output pixel
+            if (n0 < p.n_valid) {
+              const int par = n0 / p.cpp, co = n0 - par * p.cpp;
+              const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * s_beta[nl + i];
+              store16h(p.out + (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co, v);
+            }
+          } else
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + i;
+            if (n >= p.n_valid) break;
+            const int par = n / p.cpp, co = n - par * p.cpp;
+            const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
+            const float r = v[i] >= 0.f ? v[i] : v[i] * s_beta[nl + i];
+            p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(r);
+          }
         } else if constexpr (EPI == EPI_PS) {
           // permuted columns: global chunk jg = par*4 + (dy*2+dx) holds the 13 (+3 zero) channels of one output pixel
           const int jg = n0 >> 4;
@@ -338,7 +385,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
             if (n >= p.n_valid) break;
             const int par = n / p.cpp, co = n - par * p.cpp;
             const int oy = 2 * y + (par >> 1), ox = 2 * x + (par & 1);
-            p.out[(((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
+            const size_t o = (((size_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co;
+            if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v[i];
+            else p.out[o] = __float2half_rn(v[i]);
           }
         }
       }
@@ -403,7 +452,7 @@ int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
     for (int i = 0; i < h.npad; ++i) colmap[i] = i;
   }
   const int np = (int)colmap.size();
-  if (np % 16 || np > 256) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: N must be a multiple of 16 and <= 256");
+  if (np % 16 || (np > 256 && np % 128)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: N must be a multiple of 16 (of 128 above 256)");
   packed->assign((size_t)h.taps * nchunks * np * kc, __float2half_rn(0.f));
   for (int t = 0; t < h.taps; ++t)
     for (int ch = 0; ch < nchunks; ++ch)
@@ -434,6 +483,9 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_PS needs the PixelShuffle column layout");
   if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_RES needs beta and res");
+  if (io.epi >= EPI_PRELU && !L.beta) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: PReLU epilogues need the slope vector");
+  if (io.epi == EPI_PRELU_ADD && !io.res) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_PRELU_ADD needs res");
+  if (io.out_f32 && io.epi != EPI_LINEAR && io.epi != EPI_CONVT) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: fp32 output is for the activation-free epilogues only");
   if (io.epi == EPI_HEADT && L.npad != 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: EPI_HEADT expects N = 16");
 
   UmmaParams p{};
@@ -446,6 +498,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   // N split: 64-column slices when the layer is wide and has too few pixel tiles to fill the machine
   p.nw = L.npad;
   if (L.npad >= 128 && L.npad % 64 == 0 && p.tiles_x * p.tiles_y * io.B <= 148 / 2 + 16 && io.epi != EPI_HEADT) p.nw = 64;
+  if (p.nw > 256) p.nw = (L.npad % 256 == 0) ? 256 : 128;  // one MMA / TMEM accumulator holds at most 256 columns
   p.tmem_cols = 32;
   while (p.tmem_cols < p.nw) p.tmem_cols <<= 1;
   p.a_bytes = TILE_M * L.kc * 2;
@@ -458,6 +511,8 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   if (stages > ksteps) stages = ksteps;
   p.stages = stages;
   p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par; p.planar_out = io.planar_out;
+  p.out_f32 = io.out_f32;
+  p.res_pitch = io.res_pitch ? io.res_pitch : io.out_c;
   p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
   if (L.kind == CONV_3x3) {
@@ -469,7 +524,8 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   CUtensorMap tm_a, tm_b;
   {
     cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)io.W, (cuuint64_t)io.H, (cuuint64_t)io.B};
-    cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)io.W * L.cin * 2, (cuuint64_t)io.H * io.W * L.cin * 2};
+    const cuuint64_t pitch = io.in_pitch ? io.in_pitch : L.cin;  // the conv may read a channel slice of a wider tensor
+    cuuint64_t strides[3] = {pitch * 2, (cuuint64_t)io.W * pitch * 2, (cuuint64_t)io.H * io.W * pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)L.kc, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(io.in), dims, strides, box, es,
@@ -508,6 +564,9 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
     RIFE_UMMA_LAUNCH(EPI_HEADT)
     RIFE_UMMA_LAUNCH(EPI_LINEAR)
     RIFE_UMMA_LAUNCH(EPI_CONVT)
+    RIFE_UMMA_LAUNCH(EPI_PRELU)
+    RIFE_UMMA_LAUNCH(EPI_PRELU_ADD)
+    RIFE_UMMA_LAUNCH(EPI_CONVT_PRELU)
     default: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_umma: bad epilogue");
   }
 #undef RIFE_UMMA_LAUNCH

@@ -2,8 +2,12 @@
 
 Parameter containers with the reference's state-dict keys / construction order, and a forward that issues the whole
 network through the generic NHWC layer API of librife_b200.so (`rife_layer_*`, `rife_nhwc_*`, `rife_eccv_merge`):
-fp32 activations `[B][H][W][pitch]`, every `torch.cat` of the reference replaced by producers writing into channel
+activations `[B][H][W][pitch]`, every `torch.cat` of the reference replaced by producers writing into channel
 slices of the consumer's tensor.  PyTorch only allocates the buffers.  No CPU fallback.
+
+Two precisions, like the HDv3 path: "fp32" (fp32 tensors, FMA convs, <= 1e-4 vs the reference) and "fp16" (fp16 conv
+activations / weights on the tcgen05 kernel with fp32 accumulation; the full-resolution flow / mask / warped-frame
+tensor and every flow used by a warp stay fp32).  "auto" picks fp16 for fp16 frames.
 """
 from __future__ import annotations
 
@@ -13,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .ifnet import _precision_from_env
 from .warplayer import base_grids
 
 
@@ -79,10 +84,22 @@ def _pad8(c):
     return (c + 7) // 8 * 8
 
 
+def _padc(c, h16):
+    """Stored channel count of an activation tensor: fp32 -> multiple of 8; fp16 -> 16, or a multiple of 32 so that the
+    tcgen05 kernel consumes K in 32- / 64-channel TMA boxes (conv_umma.cu)."""
+    if not h16:
+        return _pad8(c)
+    return 16 if c <= 16 else (c + 31) // 32 * 32
+
+
+def _dt(t):
+    return _lib.RIFE_F16 if t.dtype == torch.float16 else _lib.RIFE_F32
+
+
 class _Layer:
     """One packed conv layer (rife_layer) plus its geometry."""
 
-    def __init__(self, lib, kind, conv, prelu, cin_store):
+    def __init__(self, lib, kind, conv, prelu, cin_store, prec=0):
         w = conv.weight.detach().to("cpu", torch.float32).contiguous()
         b = conv.bias.detach().to("cpu", torch.float32).contiguous() if conv.bias is not None else None
         s = prelu.weight.detach().to("cpu", torch.float32).contiguous() if prelu is not None else None
@@ -93,13 +110,15 @@ class _Layer:
         self.h = C.c_void_p()
         self.lib = lib
         _lib.check(lib.rife_layer_create(C.byref(self.h), kind, w.data_ptr(), b.data_ptr() if b is not None else None,
-                                         s.data_ptr() if s is not None else None, self.cin, self.cout, cin_store, 0))
+                                         s.data_ptr() if s is not None else None, self.cin, self.cout, cin_store, prec))
+        self.esz = 2 if prec == _lib.PRECISION_FP16 else 4
 
     def run(self, src, out, hh, ww, act, res=None, out_off=0, stream=0):
-        """src / out / res: NHWC fp32 tensors; the conv reads channels [0, cin_store) of src and writes channels
-        [out_off, ...) of out."""
+        """src / out / res: NHWC tensors of the layer's precision; the conv reads channels [0, cin_store) of src and
+        writes channels [out_off, ...) of out."""
         b = src.shape[0]
-        _lib.check(self.lib.rife_layer_run(self.h, src.data_ptr(), src.shape[-1], out.data_ptr() + 4 * out_off, out.shape[-1],
+        _lib.check(self.lib.rife_layer_run(self.h, src.data_ptr(), src.shape[-1], out.data_ptr() + out.element_size() * out_off,
+                                           _dt(out), out.shape[-1],
                                            b, hh, ww, res.data_ptr() if res is not None else None,
                                            res.shape[-1] if res is not None else 0, act, stream))
 
@@ -112,15 +131,16 @@ class _Layer:
 class IFNet(nn.Module):
     """Drop-in for `model.IFNet.IFNet` (inference branch: `x` holds img0, img1 and no ground truth)."""
 
-    def __init__(self):
+    def __init__(self, precision="auto"):
         super().__init__()
+        self.precision = _precision_from_env(precision)
         self.block0 = IFBlock(6, c=240)          # model/IFNet.py:56-61: same construction order => same default init
         self.block1 = IFBlock(13 + 4, c=150)
         self.block2 = IFBlock(13 + 4, c=90)
         self.block_tea = IFBlock(16 + 4, c=90)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
         self.contextnet = Contextnet()
         self.unet = Unet()
-        self._layers = None
+        self._layers = {}      # precision -> {name: _Layer}
         self._stamp = None
         self._generation = 0
 
@@ -139,10 +159,10 @@ class IFNet(nn.Module):
         self._generation += 1
 
     def release(self):
-        if self._layers:
-            for l in self._layers.values():
+        for layers in (self._layers or {}).values():
+            for l in layers.values():
                 l.free()
-        self._layers = None
+        self._layers = {}
 
     def __del__(self):
         try:
@@ -150,34 +170,39 @@ class IFNet(nn.Module):
         except Exception:
             pass
 
-    def _pack(self, device):
+    def _pack(self, device, prec):
         stamp = (self._generation, sum(p._version for p in self.parameters()), str(device))
-        if self._layers is not None and self._stamp == stamp:
-            return self._layers
-        self.release()
+        if self._stamp != stamp:
+            self.release()
+            self._stamp = stamp
+        if prec in self._layers:
+            return self._layers[prec]
         lib = _lib.load()
+        h16 = prec == _lib.PRECISION_FP16
+        pc = lambda c: _padc(c, h16)
+        mk = lambda kind, conv, prelu, cs: _Layer(lib, kind, conv, prelu, cs, prec)
         L = {}
         with torch.cuda.device(device):
             for i, blk in enumerate((self.block0, self.block1, self.block2)):
                 c = blk.lastconv.weight.shape[0]
                 cin = blk.conv0[0][0].weight.shape[1]
-                L[f"b{i}.c00"] = _Layer(lib, 1, blk.conv0[0][0], blk.conv0[0][1], _pad8(cin))
-                L[f"b{i}.c01"] = _Layer(lib, 1, blk.conv0[1][0], blk.conv0[1][1], _pad8(c // 2))
+                L[f"b{i}.c00"] = mk(1, blk.conv0[0][0], blk.conv0[0][1], _pad8(cin))
+                L[f"b{i}.c01"] = mk(1, blk.conv0[1][0], blk.conv0[1][1], pc(c // 2))
                 for j in range(8):
-                    L[f"b{i}.cb{j}"] = _Layer(lib, 0, blk.convblock[j][0], blk.convblock[j][1], _pad8(c))
-                L[f"b{i}.last"] = _Layer(lib, 2, blk.lastconv, None, _pad8(c))
+                    L[f"b{i}.cb{j}"] = mk(0, blk.convblock[j][0], blk.convblock[j][1], pc(c))
+                L[f"b{i}.last"] = mk(2, blk.lastconv, None, pc(c))
             cn = self.contextnet
             for k, (m, cin) in enumerate(((cn.conv1, 3), (cn.conv2, _C), (cn.conv3, 2 * _C), (cn.conv4, 4 * _C))):
-                L[f"ctx{k}.1"] = _Layer(lib, 1, m.conv1[0], m.conv1[1], _pad8(cin))
-                L[f"ctx{k}.2"] = _Layer(lib, 0, m.conv2[0], m.conv2[1], _pad8(m.conv2[0].weight.shape[1]))
+                L[f"ctx{k}.1"] = mk(1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"ctx{k}.2"] = mk(0, m.conv2[0], m.conv2[1], pc(m.conv2[0].weight.shape[1]))
             un = self.unet
             for k, (m, cin) in enumerate(((un.down0, 17), (un.down1, 4 * _C), (un.down2, 8 * _C), (un.down3, 16 * _C))):
-                L[f"dn{k}.1"] = _Layer(lib, 1, m.conv1[0], m.conv1[1], _pad8(cin))
-                L[f"dn{k}.2"] = _Layer(lib, 0, m.conv2[0], m.conv2[1], _pad8(m.conv2[0].weight.shape[1]))
+                L[f"dn{k}.1"] = mk(1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"dn{k}.2"] = mk(0, m.conv2[0], m.conv2[1], pc(m.conv2[0].weight.shape[1]))
             for k, m in enumerate((un.up0, un.up1, un.up2, un.up3)):
-                L[f"up{k}"] = _Layer(lib, 2, m[0], m[1], m[0].weight.shape[0])
-            L["out"] = _Layer(lib, 0, un.conv, None, _C)
-        self._layers, self._stamp = L, stamp
+                L[f"up{k}"] = mk(2, m[0], m[1], m[0].weight.shape[0])
+            L["out"] = mk(0, un.conv, None, _C)
+        self._layers[prec] = L
         return L
 
     # ---------------------------------------------------------------- forward
@@ -199,43 +224,50 @@ class IFNet(nn.Module):
             raise RuntimeError(f"ECCV IFNet: H and W must be multiples of {need} for scale list {list(scale)} (got {H}x{W})")
         lib = _lib.load()
         dev = x.device
-        L = self._pack(dev)
+        mode = self.precision
+        if mode == "auto":
+            mode = "fp16" if x.dtype == torch.float16 else "fp32"
+        h16 = mode == "fp16"
+        L = self._pack(dev, _lib.PRECISION_FP16 if h16 else _lib.PRECISION_FP32)
+        pc = lambda c: _padc(c, h16)
+        adt = torch.float16 if h16 else torch.float32       # conv activations
         x = x.contiguous()
         io = _lib.RIFE_F32 if x.dtype == torch.float32 else _lib.RIFE_F16
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
-            z = lambda h, w, p: torch.zeros((B, h, w, p), dtype=torch.float32, device=dev)
-            e = lambda h, w, p: torch.empty((B, h, w, p), dtype=torch.float32, device=dev)
+            z = lambda h, w, p, dt=adt: torch.zeros((B, h, w, p), dtype=dt, device=dev)
+            e = lambda h, w, p, dt=adt: torch.empty((B, h, w, p), dtype=dt, device=dev)
+            f32 = torch.float32
             chk = _lib.check
 
             def resize(src, soff, c, dst, doff, mul=1.0, acc=0):
-                chk(lib.rife_nhwc_resize(src.data_ptr(), src.shape[-1], soff, dst.data_ptr(), dst.shape[-1], doff, B, c,
-                                         src.shape[1], src.shape[2], dst.shape[1], dst.shape[2], mul, acc, st))
+                chk(lib.rife_nhwc_resize(src.data_ptr(), _dt(src), src.shape[-1], soff, dst.data_ptr(), _dt(dst), dst.shape[-1],
+                                         doff, B, c, src.shape[1], src.shape[2], dst.shape[1], dst.shape[2], mul, acc, st))
 
             def warp(src, soff, c, fl, foff, dst, doff):
                 h, w = src.shape[1], src.shape[2]
                 _, _, gx, gy = base_grids(h, w, dev)
-                chk(lib.rife_nhwc_warp(src.data_ptr(), src.shape[-1], soff, fl.data_ptr(), fl.shape[-1], foff, dst.data_ptr(),
-                                       dst.shape[-1], doff, B, c, h, w, gx.data_ptr(), gy.data_ptr(), st))
+                chk(lib.rife_nhwc_warp(src.data_ptr(), _dt(src), src.shape[-1], soff, fl.data_ptr(), _dt(fl), fl.shape[-1], foff,
+                                       dst.data_ptr(), _dt(dst), dst.shape[-1], doff, B, c, h, w, gx.data_ptr(), gy.data_ptr(), st))
 
             def s2d(src, c, cpad, soff=0):
                 h, w = src.shape[1], src.shape[2]
                 dst = e(h // 2, w // 2, 4 * cpad)
-                chk(lib.rife_nhwc_s2d(src.data_ptr(), src.shape[-1], soff, c, dst.data_ptr(), cpad, B, h, w, st))
+                chk(lib.rife_nhwc_s2d(src.data_ptr(), _dt(src), src.shape[-1], soff, c, dst.data_ptr(), _dt(dst), cpad, B, h, w, st))
                 return dst
 
             def conv2(prefix, src, c_in, dst, doff, soff=0):
                 """Conv2 (model/refine.py:24-33): stride-2 conv + PReLU, conv + PReLU; result into dst[..., doff:]."""
                 l1, l2 = L[prefix + ".1"], L[prefix + ".2"]
                 h, w = src.shape[1] // 2, src.shape[2] // 2
-                a = z(h, w, _pad8(l1.cout))
+                a = z(h, w, l2.cin_store)
                 l1.run(s2d(src, c_in, l1.cin_store, soff), a, h, w, 2, stream=st)
                 l2.run(a, dst, h, w, 2, out_off=doff, stream=st)
 
-            # full-resolution working tensor in Unet.down0's cat order (model/refine.py:73):
+            # full-resolution fp32 working tensor in Unet.down0's cat order (model/refine.py:73):
             # [img0 0:3 | img1 3:6 | warped0 6:9 | warped1 9:12 | mask 12 | flow 13:17 | pad]
-            full = z(H, W, 24)
-            chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), B, 6, H, W, 24, 0, st))
+            full = z(H, W, 24, f32)
+            chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), _dt(full), B, 6, H, W, 24, 0, st))
             flow_list, merged, mask_sig = [], [], None
             out_dt = x.dtype
             for i in range(3):                                                        # model/IFNet.py:74-86
@@ -249,37 +281,37 @@ class IFNet(nn.Module):
                     resize(full, 0, 13, xin, 0)                                       # cat(img0,img1,warped0,warped1,mask)
                     resize(full, 13, 4, xin, 13, mul=1.0 / s)                         # :42 interp(flow) * 1/scale
                 c = (240, 150, 90)[i]
-                a = z(hs // 2, ws // 2, _pad8(c // 2))
+                a = z(hs // 2, ws // 2, pc(c // 2))
                 L[f"b{i}.c00"].run(s2d(xin, cin, _pad8(cin)), a, hs // 2, ws // 2, 2, stream=st)
-                bq = z(hs // 4, ws // 4, _pad8(c))
-                L[f"b{i}.c01"].run(s2d(a, c // 2, _pad8(c // 2)), bq, hs // 4, ws // 4, 2, stream=st)
-                pp = (z(hs // 4, ws // 4, _pad8(c)), z(hs // 4, ws // 4, _pad8(c)))
+                bq = z(hs // 4, ws // 4, pc(c))
+                L[f"b{i}.c01"].run(s2d(a, pc(c // 2), pc(c // 2)), bq, hs // 4, ws // 4, 2, stream=st)
+                pp = (z(hs // 4, ws // 4, pc(c)), z(hs // 4, ws // 4, pc(c)))
                 y = bq
                 for j in range(8):                                                    # :45-46 convblock(x) + x
                     dst = pp[j & 1]
                     L[f"b{i}.cb{j}"].run(y, dst, hs // 4, ws // 4, 3 if j == 7 else 2, res=bq if j == 7 else None, stream=st)
                     y = dst
-                tmp = e(hs // 2, ws // 2, 8)
+                tmp = e(hs // 2, ws // 2, 8, f32)                                     # flow / mask head: fp32 in both modes
                 L[f"b{i}.last"].run(y, tmp, hs // 4, ws // 4, 0, stream=st)           # :47 lastconv -> 5 ch at 1/(2s)
                 resize(tmp, 0, 4, full, 13, mul=float(2 * s), acc=int(i > 0))         # :48-49,76: flow (+)= up(tmp)*scale*2
                 resize(tmp, 4, 1, full, 12, mul=1.0, acc=int(i > 0))                  # :50,77: mask (+)= up(tmp)
                 warp(full, 0, 3, full, 13, full, 6)                                   # :82
                 warp(full, 3, 3, full, 15, full, 9)                                   # :83
                 fl = torch.empty((B, 4, H, W), dtype=out_dt, device=dev)
-                chk(lib.rife_nhwc_to_nchw(full.data_ptr(), 24, 13, fl.data_ptr(), io, B, 4, H, W, 0, st))
+                chk(lib.rife_nhwc_to_nchw(full.data_ptr(), _dt(full), 24, 13, fl.data_ptr(), io, B, 4, H, W, 0, st))
                 flow_list.append(fl)
                 if i < 2:                                                             # :98-99
                     mg = torch.empty((B, 3, H, W), dtype=out_dt, device=dev)
-                    chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, None, 0, 0,
-                                            mg.data_ptr(), io, B, H, W, st))
+                    chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, _dt(full),
+                                            None, 0, 0, 0, mg.data_ptr(), io, B, H, W, st))
                     merged.append(mg)
             mask_sig = torch.empty((B, 1, H, W), dtype=out_dt, device=dev)
-            chk(lib.rife_nhwc_to_nchw(full.data_ptr(), 24, 12, mask_sig.data_ptr(), io, B, 1, H, W, 1, st))
+            chk(lib.rife_nhwc_to_nchw(full.data_ptr(), _dt(full), 24, 12, mask_sig.data_ptr(), io, B, 1, H, W, 1, st))
 
             # Contextnet on both frames (model/refine.py:44-57), features warped straight into the Unet's cat slices
             d1, d2, d3, u0 = z(H // 2, W // 2, 64), z(H // 4, W // 4, 128), z(H // 8, W // 8, 256), z(H // 16, W // 16, 512)
             for f, (img_off, flow_off) in enumerate(((0, 13), (3, 15))):
-                fl = z(H // 2, W // 2, 8)
+                fl = z(H // 2, W // 2, 8, f32)
                 resize(full, flow_off, 2, fl, 0, mul=0.5)
                 feat = e(H // 2, W // 2, 16)
                 conv2("ctx0", full, 3, feat, 0, soff=img_off)
@@ -290,7 +322,7 @@ class IFNet(nn.Module):
                     h, w = prev.shape[1] // 2, prev.shape[2] // 2
                     nxt = e(h, w, cc)
                     conv2(f"ctx{k + 1}", prev, prev_c, nxt, 0)
-                    fl2 = z(h, w, 8)
+                    fl2 = z(h, w, 8, f32)
                     resize(fl, 0, 2, fl2, 0, mul=0.5)
                     warp(nxt, 0, cc, fl2, 0, dst, base + cc * f)
                     prev, prev_c, fl = nxt, cc, fl2
@@ -309,11 +341,11 @@ class IFNet(nn.Module):
             resize(d1, 0, 32, u3, 32)
             xo = e(H, W, 16)
             L["up3"].run(u3, xo, H // 2, W // 2, 2, stream=st)
-            ref = e(H, W, 8)
+            ref = e(H, W, pc(3), f32)
             L["out"].run(xo, ref, H, W, 0, stream=st)
             mg = torch.empty((B, 3, H, W), dtype=out_dt, device=dev)
-            chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, ref.data_ptr(), 8, 0,
-                                    mg.data_ptr(), io, B, H, W, st))
+            chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, _dt(full),
+                                    ref.data_ptr(), _dt(ref), ref.shape[-1], 0, mg.data_ptr(), io, B, H, W, st))
             merged.append(mg)                                                          # :105-107
         return flow_list, mask_sig, merged, None, None, 0
 
@@ -324,12 +356,12 @@ device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 class Model:
     """Drop-in for `model.RIFE.Model` (inference side, model/RIFE.py:18-65)."""
 
-    def __init__(self, local_rank=-1, arbitrary=False):
+    def __init__(self, local_rank=-1, arbitrary=False, precision="auto"):
         if arbitrary:
             raise NotImplementedError("IFNet_m (arbitrary-timestep ECCV variant) is out of scope (SURVEY 2.1 row 6)")
         if local_rank != -1:
             raise NotImplementedError("DDP training wrapper is out of scope: inference only")
-        self.flownet = IFNet()
+        self.flownet = IFNet(precision=precision)
         self.device()
 
     def train(self):

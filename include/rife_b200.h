@@ -145,38 +145,47 @@ int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, 
                              void* stream);
 
 /* ---- generic NHWC layer / operator API: the ECCV-paper network (model/IFNet.py, model/refine.py, -------------
- *      model/RIFE.py:56-65; BASELINE config 5).  fp32 NHWC tensors [B][H][W][pitch]; an operator touches the
+ *      model/RIFE.py:56-65; BASELINE config 5).  NHWC tensors [B][H][W][pitch]; an operator touches the
  *      channel slice [off, off + C) so that torch.cat (model/IFNet.py:75-79, model/refine.py:73-80) is free. */
 typedef struct rife_layer rife_layer;
 /* kind 0: nn.Conv2d(cin,cout,3,1,1); kind 1: nn.Conv2d(cin,cout,3,2,1) reading the space-to-depth tensor produced by
  * rife_nhwc_s2d (cpad = cin_store); kind 2: nn.ConvTranspose2d(cin,cout,4,2,1).  w_host in the reference's layout
  * (OIHW / IOHW), bias_host [cout] or NULL, slope_host [cout] = nn.PReLU(cout).weight or NULL.  cin_store = channels
- * of the input slice incl. zero padding (multiple of 8). */
+ * of the input slice incl. zero padding: a multiple of 8 with RIFE_PRECISION_FP32 (fp32 tensors, FMA kernel); with
+ * RIFE_PRECISION_FP16 (fp16 tensors, tcgen05 kernel) a multiple of 16 for kinds 0 / 2 and of 8 for kind 1, and the
+ * layer then writes round_up(cout, 16) channels (kind 2: per parity round_up(cout, 8)), the padding as zeros. */
 int rife_layer_create(rife_layer** out, int kind, const float* w_host, const float* bias_host,
                       const float* slope_host, int cin, int cout, int cin_store, int precision);
 int rife_layer_destroy(rife_layer* l);
 /* act: 0 none, 1 LeakyReLU(0.2), 2 PReLU, 3 PReLU then "+ res" (convblock(x) + x, model/IFNet.py:46).
- * H, W: spatial size of the input grid (for kind 1: of the s2d tensor, i.e. of the output). */
-int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_pitch, int B, int H,
-                   int W, const void* res, int res_pitch, int act, void* stream);
-int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int B, int C, int H, int W, int pitch, int off,
-                        void* stream);
-int rife_nhwc_to_nchw(const void* src, int pitch, int off, void* dst, int io_dtype, int B, int C, int H, int W,
-                      int sigmoid, void* stream);
+ * H, W: spatial size of the input grid (for kind 1: of the s2d tensor, i.e. of the output).  in / res are of the
+ * layer's precision; out_dtype likewise, except that an fp16 layer with act 0 (the flow / mask / refine heads) may
+ * write RIFE_F32 so that its result is not rounded before it is scaled and accumulated. */
+int rife_layer_run(const rife_layer* l, const void* in, int in_pitch, void* out, int out_dtype, int out_pitch,
+                   int B, int H, int W, const void* res, int res_pitch, int act, void* stream);
+/* Every NHWC tensor carries its own element type (RIFE_F32 or RIFE_F16; the *_dtype argument after its pointer):
+ * with RIFE_PRECISION_FP16 layers the conv activations are fp16 while the full-resolution flow / mask / warped-frame
+ * tensor stays fp32.  Pitches and offsets are in elements. */
+int rife_nhwc_from_nchw(const void* src, int io_dtype, void* dst, int dst_dtype, int B, int C, int H, int W,
+                        int pitch, int off, void* stream);
+int rife_nhwc_to_nchw(const void* src, int src_dtype, int pitch, int off, void* dst, int io_dtype, int B, int C,
+                      int H, int W, int sigmoid, void* stream);
 /* F.interpolate(bilinear, align_corners=False) by a power-of-two factor; dst = (accumulate ? dst : 0) + value * mul */
-int rife_nhwc_resize(const void* src, int spitch, int soff, void* dst, int dpitch, int doff, int B, int C, int Hs,
-                     int Ws, int Hd, int Wd, float mul, int accumulate, void* stream);
+int rife_nhwc_resize(const void* src, int src_dtype, int spitch, int soff, void* dst, int dst_dtype, int dpitch,
+                     int doff, int B, int C, int Hs, int Ws, int Hd, int Wd, float mul, int accumulate,
+                     void* stream);
 /* warp() of model/warplayer.py:8-22; flow = channels [foff, foff+2) of an NHWC tensor at the same resolution */
-int rife_nhwc_warp(const void* src, int spitch, int soff, const void* flow, int fpitch, int foff, void* dst,
-                   int dpitch, int doff, int B, int C, int H, int W, const float* gridx_dev, const float* gridy_dev,
-                   void* stream);
-int rife_nhwc_s2d(const void* src, int spitch, int soff, int C, void* dst, int cpad, int B, int H, int W,
-                  void* stream);
+int rife_nhwc_warp(const void* src, int src_dtype, int spitch, int soff, const void* flow, int flow_dtype,
+                   int fpitch, int foff, void* dst, int dst_dtype, int dpitch, int doff, int B, int C, int H, int W,
+                   const float* gridx_dev, const float* gridy_dev, void* stream);
+int rife_nhwc_s2d(const void* src, int src_dtype, int spitch, int soff, int C, void* dst, int dst_dtype, int cpad,
+                  int B, int H, int W, void* stream);
 /* merged = w0*sigmoid(mask) + w1*(1-sigmoid(mask)) (model/IFNet.py:98-99); with refine (pre-sigmoid Unet output):
- * clamp(merged + sigmoid(refine)*2 - 1, 0, 1) (model/IFNet.py:105-107).  out: NCHW (B,3,H,W) of io_dtype. */
+ * clamp(merged + sigmoid(refine)*2 - 1, 0, 1) (model/IFNet.py:105-107).  w0 / w1 / mask share w_dtype.
+ * out: NCHW (B,3,H,W) of io_dtype. */
 int rife_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm,
-                    int om, const void* refine, int pr, int orf, void* out, int io_dtype, int B, int H, int W,
-                    void* stream);
+                    int om, int w_dtype, const void* refine, int refine_dtype, int pr, int orf, void* out,
+                    int io_dtype, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -217,9 +217,48 @@ def case_eccv():
     save("eccv_cases", **arrs)
 
 
+def case_eccv_ref_fp16():
+    """How far the reference's OWN half-precision mode (inference_video.py --fp16: default tensor type Half, so weights,
+    frames and the warp grid of model/warplayer.py are all fp16) lands from its fp32 result on the eccv_cases inputs.
+    Recorded so that the fp16-mode parity tests can show the B200 path is at least as accurate as that mode."""
+    from model.RIFE import Model as EccvModel
+    import model.warplayer as wl
+    torch.manual_seed(1234)
+    m = EccvModel()
+    m.eval()
+    for b in (m.flownet.block0, m.flownet.block1, m.flownet.block2):
+        b.lastconv.weight.data.mul_(AMP)
+    g = np.load(os.path.join(OUT, "eccv_cases.npz"))
+    res = {}
+    for case, kw in (("a", dict(scale_list=[4, 2, 1])), ("b", dict(scale=0.5, scale_list=[4, 2, 1])),
+                     ("c", dict(scale_list=[4, 2, 1]))):
+        i0, i1 = torch.from_numpy(g[case + "_img0"]).float(), torch.from_numpy(g[case + "_img1"]).float()
+        torch.set_default_dtype(torch.float32)
+        m.flownet.float()
+        wl.backwarp_tenGrid.clear()
+        ref = m.inference(i0, i1, **kw)
+        torch.set_default_dtype(torch.float16)
+        m.flownet.half()
+        wl.backwarp_tenGrid.clear()
+        out = m.inference(i0.half(), i1.half(), **kw).float()
+        torch.set_default_dtype(torch.float32)
+        e = (out - ref).abs()
+        ok = bool(torch.isfinite(out).all())       # case c overflows to NaN in the reference's fp16 mode
+        res[case] = {"finite": ok, "max_abs": float(e.max()) if ok else None,
+                     "psnr_db": float(-10 * torch.log10((e ** 2).mean())) if ok else None}
+    with open(os.path.join(OUT, "eccv_ref_fp16.json"), "w") as f:
+        json.dump({"what": "reference model/RIFE.py in its own fp16 mode (CPU, torch %s) vs its fp32 output" % torch.__version__,
+                   "cases": res}, f, indent=1)
+    print(res)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "eccv_fp16":
+        with torch.no_grad():
+            case_eccv_ref_fp16()
         sys.exit(0)
     weights_manifest()
     case_demo()
