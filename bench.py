@@ -261,8 +261,9 @@ def main():
 
     # ---- (2) end to end through the host-buffer C-ABI call (rife_inference_host): pinned host frames exactly as a video
     #      decoder delivers them -- uint8 HWC, true 1080 x 1920 (the library pads to 1088 and crops back) -> H2D ->
-    #      inference -> D2H of the uint8 result, every step.  Three plan slots on three streams: the PCIe copies of
-    #      one step overlap the compute of its neighbours.
+    #      inference -> D2H of the uint8 result, every step.  Three plan slots rotate over one H2D, one compute and one
+    #      D2H stream (rife_inference_host_pipelined): the PCIe copies of a step overlap the kernels of its neighbours
+    #      and the kernels of consecutive steps run back to back.
     NSLOT = 3
     FH, FW = 1080, 1920
     u8_sets = []
@@ -278,7 +279,7 @@ def main():
         for i in range(n):
             k = i % NSLOT
             a, b = u8_sets[i % NSETS]
-            model.inference_host(a, b, host_out[k], stream=streams[k], slot=k)
+            model.inference_host(a, b, host_out[k], slot=k, streams=streams)
 
     e2e_steps(2 * NSLOT)
     barrier()
@@ -354,7 +355,7 @@ def main():
                    "l2_policy": f"inputs rotate over {NSETS} distinct batches; each step streams >1 GB of intermediates (> 126 MB L2)"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": frame_bytes,
                 "ms_per_step": ms_e2e / args.steps,
-                "api": "rife_inference_host: pinned uint8 HWC 1080x1920 frames in, uint8 HWC frame out, 3 plan slots / streams"},
+                "api": "rife_inference_host: pinned uint8 HWC 1080x1920 frames in, uint8 HWC frame out, 3 plan slots over h2d / compute / d2h streams (rife_inference_host_pipelined)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librife_b200.so")
+LIB_PATH = os.environ.get("RIFE_B200_LIB") or os.path.join(_HERE, "csrc", "librife_b200.so")   # override: A/B builds
 
 RIFE_F32, RIFE_F16, RIFE_U8 = 0, 1, 2
 PRECISION_FP32, PRECISION_FP16 = 0, 1
@@ -17,7 +17,7 @@ SYMBOLS = [
     "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_destroy", "rife_plan_set_frame_size",
     "rife_plan_set_profiling",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
-    "rife_inference_host", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
+    "rife_inference_host", "rife_inference_host_pipelined", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
     "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
     "rife_nhwc_resize", "rife_nhwc_warp", "rife_nhwc_s2d", "rife_eccv_merge",
 ]
@@ -62,6 +62,7 @@ def load():
     lib.rife_inference.argtypes = [vp, vp, vp, fp, vp, i, vp]
     lib.rife_ifnet_forward.argtypes = [vp, vp, vp, fp, C.POINTER(IFNetOutputs), i, vp]
     lib.rife_inference_host.argtypes = [vp, vp, vp, fp, vp, i, vp]
+    lib.rife_inference_host_pipelined.argtypes = [vp, vp, vp, fp, vp, i, vp, vp, vp]
     lib.rife_warp.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.rife_resize_bilinear.argtypes = [vp, vp, i, i, i, i, i, i, f, vp]
     lib.rife_conv3x3.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]

@@ -14,6 +14,10 @@
 namespace rife {
 
 std::atomic<uint64_t> g_launch_count{0};
+bool pdl_enabled() {
+  static const bool on = !(getenv("RIFE_NO_PDL") && atoi(getenv("RIFE_NO_PDL")));
+  return on;
+}
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 
@@ -326,7 +330,11 @@ struct rife_plan {
   };
   std::vector<Stage> stages;
   size_t n_stage = 0;  // stages recorded by the last run
+  // rife_inference_host_pipelined: "staging-in filled", "compute done", "staging-out drained"
+  cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_out = nullptr;
   ~rife_plan() {
+    for (cudaEvent_t e : {ev_in, ev_compute, ev_out})
+      if (e) cudaEventDestroy(e);
     for (auto& s : stages) {
       if (s.e0) cudaEventDestroy(s.e0);
       if (s.e1) cudaEventDestroy(s.e1);
@@ -569,6 +577,39 @@ int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_ho
   RIFE_TRY(rife_inference(p, p->at(p->L.stage_in0), p->at(p->L.stage_in1), timestep_host, p->at(p->L.stage_out), io_dtype,
                           stream));
   RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), bytes, cudaMemcpyDeviceToHost, st));
+  return RIFE_OK;
+}
+
+int rife_inference_host_pipelined(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,
+                                  void* out_host, int io_dtype, void* stream_h2d, void* stream_compute, void* stream_d2h) {
+  if (!p || !img0_host || !img1_host || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host_pipelined: null argument");
+  if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host_pipelined: bad io_dtype");
+  cudaStream_t s_in = (cudaStream_t)stream_h2d, s_c = (cudaStream_t)stream_compute, s_out = (cudaStream_t)stream_d2h;
+  if (!p->ev_in) {
+    RIFE_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    RIFE_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_compute, cudaEventDisableTiming));
+    RIFE_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+    // first use: nothing to wait for
+    RIFE_CUDA_TRY(cudaEventRecord(p->ev_compute, s_c));
+    RIFE_CUDA_TRY(cudaEventRecord(p->ev_out, s_out));
+  }
+  const size_t esz = io_dtype == RIFE_F32 ? 4 : (io_dtype == RIFE_F16 ? 2 : 1);
+  const size_t bytes = (size_t)p->B * p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
+  // H2D: the previous inference on this plan must have consumed its staging-in buffers
+  RIFE_CUDA_TRY(cudaStreamWaitEvent(s_in, p->ev_compute, 0));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, bytes, cudaMemcpyHostToDevice, s_in));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, bytes, cudaMemcpyHostToDevice, s_in));
+  RIFE_CUDA_TRY(cudaEventRecord(p->ev_in, s_in));
+  // compute: frames resident, previous result of this plan already copied out
+  RIFE_CUDA_TRY(cudaStreamWaitEvent(s_c, p->ev_in, 0));
+  RIFE_CUDA_TRY(cudaStreamWaitEvent(s_c, p->ev_out, 0));
+  RIFE_TRY(rife_inference(p, p->at(p->L.stage_in0), p->at(p->L.stage_in1), timestep_host, p->at(p->L.stage_out), io_dtype,
+                          stream_compute));
+  RIFE_CUDA_TRY(cudaEventRecord(p->ev_compute, s_c));
+  // D2H
+  RIFE_CUDA_TRY(cudaStreamWaitEvent(s_out, p->ev_compute, 0));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), bytes, cudaMemcpyDeviceToHost, s_out));
+  RIFE_CUDA_TRY(cudaEventRecord(p->ev_out, s_out));
   return RIFE_OK;
 }
 

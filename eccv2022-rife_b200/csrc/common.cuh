@@ -41,6 +41,30 @@ extern std::atomic<uint64_t> g_launch_count;
     RIFE_CUDA_TRY(cudaGetLastError());                   \
   } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Pipeline kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may become
+// resident and run their prologue (barrier init, TMEM allocation, weight loads, index math) while the previous kernel
+// of the stream drains.  Contract: EVERY kernel launched through launch_pdl() executes pdl_wait() before it touches
+// memory written (or still being read) by earlier kernels -- the wait returns once the preceding grid has completed
+// and flushed, which also makes completion order transitive along the stream.  RIFE_NO_PDL=1 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ layouts
 // Full-resolution "source" tensor per frame: [B][H][W][8]: ch 0..3 = Head feature f, 4..6 = image
 // channels 0..2, 7 = image channel 3 (alpha; 0 when C == 3).  One 16 B (fp16) / 32 B (fp32) vector

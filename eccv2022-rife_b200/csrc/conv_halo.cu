@@ -45,6 +45,7 @@ struct HaloParams {
   const float* beta;
   const __half* res;
   __half* out;
+  int pdl_trig;    // launch_dependents: 0 implicit at CTA exit (default; measured best), 1 after the prologue, 2 after the last MMA
   long long* dbg;  // RIFE_HK_DEBUG=1: per-CTA role timers (8 x int64), else null
   signed char e_dy[MAX_ENTRIES], e_dx[MAX_ENTRIES];
   unsigned char e_col16[MAX_ENTRIES], e_first[MAX_ENTRIES];
@@ -408,6 +409,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.pdl_trig == 1) pdl_trigger();  // the next kernel's CTAs may start their prologue as SMs free up (they block in pdl_wait())
   const uint32_t tmem_base = tmem_slot;
   const int pitch = TW + p.R;  // halo row pitch in pixels
   const int n_mma = p.nentries * p.ksteps;
@@ -423,6 +425,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
           bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wb);
         }
       }
+      // weights are constants; the activations are the previous kernel's output.  Everything else in this CTA
+      // (MMAs, epilogue loads from the smem tile, output stores) is downstream of these loads.
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0;
@@ -506,6 +511,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
         umma_commit(smem_u32(&t_full[buf]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (p.pdl_trig == 2) pdl_trigger();  // only the last epilogue is left: let the next kernel's CTAs set up meanwhile
       if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 1] = t_w;
         p.dbg[blockIdx.x * 8 + 2] = t_te;
@@ -868,6 +874,8 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   if (grid > p.ntiles) grid = p.ntiles;
   static const bool debug = getenv("RIFE_HK_DEBUG") != nullptr;
   p.dbg = nullptr;
+  static const int pdl_trig = getenv("RIFE_PDL_HALO_TRIGGER") ? atoi(getenv("RIFE_PDL_HALO_TRIGGER")) : 0;
+  p.pdl_trig = pdl_trig;
   if (debug) {
     cudaMalloc((void**)&p.dbg, (size_t)grid * 64);
     cudaMemsetAsync(p.dbg, 0, (size_t)grid * 64, st);
@@ -877,7 +885,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #define RIFE_HK_CASE(K, KS, N_, MT_, E_)                                                                     \
   if (!done && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {                   \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_>));                              \
-    conv_halo_kernel<K, KS, N_, MT_, E_><<<grid, 64 + 32 * EpiWarps<E_>::value, smem, st>>>(tm_a, p);                         \
+    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<K, KS, N_, MT_, E_>, dim3(grid), dim3(64 + 32 * EpiWarps<E_>::value), smem, st, tm_a, p)); \
     done = true;                                                                                             \
   }
   RIFE_HK_CASE(1, 1, 16, 2, EPI_LRELU)      // Head.cnn0            (s2d, cin 16 -> 16)
@@ -895,7 +903,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #define RIFE_HK_STREAM(K, KS, N_, MT_, E_)                                                                   \
   if (!done && L.stream && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {       \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_, true>));                        \
-    conv_halo_kernel<K, KS, N_, MT_, E_, true><<<grid, 96 + 32 * EpiWarps<E_>::value, smem, st>>>(tm_a, p);  \
+    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<K, KS, N_, MT_, E_, true>, dim3(grid), dim3(96 + 32 * EpiWarps<E_>::value), smem, st, tm_a, p)); \
     done = true;                                                                                             \
   }
   RIFE_HK_STREAM(0, 6, 96, 2, EPI_RES)      // block2 ResConv       (3x3, 96 -> 96), two stacked M-tiles
@@ -907,7 +915,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   if (!done && L.stream) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no streamed instantiation for this layer / epilogue");
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
-    conv_halo_kernel<-1, 0, 0, 0, -1><<<grid, 64 + 32 * EpiWarps<-1>::value, smem, st>>>(tm_a, p);
+    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<-1, 0, 0, 0, -1>, dim3(grid), dim3(64 + 32 * EpiWarps<-1>::value), smem, st, tm_a, p));
   }
   RIFE_LAUNCH_CHECK();
   if (debug) {

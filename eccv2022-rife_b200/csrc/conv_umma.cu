@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // no explicit launch_dependents: measured on B200, early-resident dependents of the conv kernels unbalance the next
+  // kernel's CTA placement (-10 % at 8 pairs); the implicit trigger at CTA exit keeps the launch-latency overlap.
+  pdl_wait();  // activations and residual come from the previous kernel (bias / slope / weights are constants)
   const uint32_t tmem_base = tmem_slot;
   const int ksteps = p.ntaps * p.nchunks;
 
@@ -554,7 +557,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
       RIFE_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr_set[dev] = true;                                                                                    \
     }                                                                                                          \
-    conv_umma_kernel<E_><<<grid, NUM_THREADS, smem, st>>>(tm_a, tm_b, p);                                      \
+    RIFE_CUDA_TRY(launch_pdl(conv_umma_kernel<E_>, grid, dim3(NUM_THREADS), smem, st, tm_a, tm_b, p));          \
   } break;
   switch (io.epi) {
     RIFE_UMMA_LAUNCH(EPI_LRELU)

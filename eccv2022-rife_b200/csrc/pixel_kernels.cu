@@ -14,6 +14,11 @@
 
 #include "common.cuh"
 
+#ifdef RIFE_PDL_NO_EARLY_PIX
+#define RIFE_PIX_TRIGGER()
+#else
+#define RIFE_PIX_TRIGGER() pdl_trigger()
+#endif
 namespace rife {
 
 namespace {
@@ -175,6 +180,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
                                                    T* __restrict__ src0, T* __restrict__ src1,
                                                    T* __restrict__ head_in, int B, int C, int H, int W,
                                                    int planar, int write_src, ImgLayout lay) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)B * H2 * W2;
@@ -226,6 +233,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 template <typename Tio>
 __global__ void __launch_bounds__(256) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                           __half* __restrict__ head_in, int B, int C, int H, int W) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;  // strip index along x (8 pixels)
   const int y2 = blockIdx.y, fb = blockIdx.z;            // fb = frame * B + b
@@ -279,6 +288,8 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
                                                           const float* __restrict__ tstep, T* __restrict__ xin, int B,
                                                           int H, int W, WarpGeom geom, int planar,
                                                           float* __restrict__ fbuf, int fbuf_levels, int fbuf_store) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   const int Hs = H / s, Ws = W / s;
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, b = blockIdx.z;
@@ -420,6 +431,8 @@ __global__ void __launch_bounds__(128) block_input_h_kernel(LevelsArg L, int lev
                                                             const float* __restrict__ tstep, __half* __restrict__ xin,
                                                             int B, int H, int W, WarpGeom geom, int planar,
                                                             float* __restrict__ fbuf, int fbuf_levels, int fbuf_store) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   constexpr int NQ = NS * NS;
   const int Hs = H / s, Ws = W / s;
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
@@ -541,6 +554,8 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
                                                    Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
                                                    int H, int W, WarpGeom geom, const float* __restrict__ fbuf,
                                                    int fbuf_levels, ImgLayout lay) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= lay.w || y >= lay.h) return;   // outputs are cropped to the caller's frame
@@ -600,6 +615,8 @@ __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__
                                                       const float* __restrict__ gridy, const float* __restrict__ fbuf,
                                                       Tio* __restrict__ omerged, int C, int H, int W, WarpGeom geom,
                                                       ImgLayout lay) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= lay.w || y >= lay.h) return;
@@ -731,9 +748,9 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   if (c.planar_head && c.half_act && c.W % 8 == 0 && fh == c.H && fw == c.W && io_dtype != RIFE_U8) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)(2 * c.B));
     if (io_dtype == RIFE_F16)
-      prep_planar_kernel<__half><<<g, 256, 0, st>>>((const __half*)img0, (const __half*)img1, (__half*)head_in, c.B, c.C, c.H, c.W);
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.B, c.C, c.H, c.W));
     else if (io_dtype == RIFE_F32)
-      prep_planar_kernel<float><<<g, 256, 0, st>>>((const float*)img0, (const float*)img1, (__half*)head_in, c.B, c.C, c.H, c.W);
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.B, c.C, c.H, c.W));
     else
       RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
     RIFE_LAUNCH_CHECK();
@@ -742,8 +759,8 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   const size_t nq = (size_t)c.B * (c.H / 2) * (c.W / 2);
   dim3 grid(nblk(nq, 256), 2);
 #define RIFE_PREP(TIO, T)                                                                                        \
-  prep_kernel<TIO, T><<<grid, 256, 0, st>>>((const TIO*)img0, (const TIO*)img1, (T*)src0, (T*)src1, (T*)head_in, \
-                                            c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1, lay)
+  RIFE_CUDA_TRY(launch_pdl(prep_kernel<TIO, T>, grid, dim3(256), 0, st, (const TIO*)img0, (const TIO*)img1, (T*)src0, \
+                           (T*)src1, (T*)head_in, c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1, lay))
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
@@ -775,16 +792,16 @@ int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int
   WarpGeom g = make_geom(c.H, c.W);
   const dim3 grid(nblk((size_t)(c.W / s), 128), (unsigned)(c.H / s), (unsigned)c.B);
 #define RIFE_BI(T, NS_, L0_)                                                                                       \
-  block_input_kernel<T, T, NS_, L0_><<<grid, 128, 0, st>>>(L, level, s, (const T*)c.src0, (const T*)c.src1, c.gridx,   \
-                                                           c.gridy, c.tstep, (T*)xin, c.B, c.H, c.W, g, planar ? 1 : 0, \
-                                                           fbuf, fbuf_levels, fbuf_store ? 1 : 0)
+  RIFE_CUDA_TRY(launch_pdl(block_input_kernel<T, T, NS_, L0_>, grid, dim3(128), 0, st, L, level, s, (const T*)c.src0, \
+                           (const T*)c.src1, c.gridx, c.gridy, c.tstep, (T*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,   \
+                           fbuf, fbuf_levels, fbuf_store ? 1 : 0))
   const bool l0 = level == 0, s1 = s == 1;
   static const bool no_fast = getenv("RIFE_NO_FAST_INPUT") != nullptr;
   if (c.half_act && !l0 && !no_fast) {
 #define RIFE_BIH(NS_)                                                                                                 \
-  block_input_h_kernel<NS_><<<grid, 128, 0, st>>>(L, level, s, (const __half*)c.src0, (const __half*)c.src1, c.gridx, \
-                                                  c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g, planar ? 1 : 0,   \
-                                                  fbuf, fbuf_levels, fbuf_store ? 1 : 0)
+  RIFE_CUDA_TRY(launch_pdl(block_input_h_kernel<NS_>, grid, dim3(128), 0, st, L, level, s, (const __half*)c.src0,    \
+                           (const __half*)c.src1, c.gridx, c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g,          \
+                           planar ? 1 : 0, fbuf, fbuf_levels, fbuf_store ? 1 : 0))
     if (s1) RIFE_BIH(1); else RIFE_BIH(2);
 #undef RIFE_BIH
   } else if (c.half_act) {
@@ -813,8 +830,8 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
       fbuf_levels == nlev - 1 && levels[nlev - 1].s == 1) {
     const __half* tmp = (const __half*)levels[nlev - 1].ptr;
 #define RIFE_MERGE(TIO)                                                                                              \
-  merge_h_kernel<TIO><<<egrid, 256, 0, st>>>(tmp, (const __half*)c.src0, (const __half*)c.src1, c.gridx, c.gridy, fbuf, \
-                                             (TIO*)o.merged, c.C, c.H, c.W, g, lay)
+  RIFE_CUDA_TRY(launch_pdl(merge_h_kernel<TIO>, egrid, dim3(256), 0, st, tmp, (const __half*)c.src0,                  \
+                           (const __half*)c.src1, c.gridx, c.gridy, fbuf, (TIO*)o.merged, c.C, c.H, c.W, g, lay))
     if (io_dtype == RIFE_F32) RIFE_MERGE(float);
     else if (io_dtype == RIFE_F16) RIFE_MERGE(__half);
     else RIFE_MERGE(uint8_t);
@@ -823,10 +840,9 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
     return RIFE_OK;
   }
 #define RIFE_EVAL(T, TIO)                                                                                         \
-  eval_kernel<T, T, TIO><<<egrid, 256, 0, st>>>(L, nlev, (const T*)c.src0, (const T*)c.src1, c.gridx,      \
-                                                       c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,      \
-                                                       (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, \
-                                                       fbuf_levels, lay)
+  RIFE_CUDA_TRY(launch_pdl(eval_kernel<T, T, TIO>, egrid, dim3(256), 0, st, L, nlev, (const T*)c.src0,            \
+                           (const T*)c.src1, c.gridx, c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,       \
+                           (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, fbuf_levels, lay))
   if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
   else if (!c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(float, __half);
   else if (c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(__half, float);

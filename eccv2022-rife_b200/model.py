@@ -52,12 +52,14 @@ class Model:
         this call happen inside the first / last kernel); uint8 tensors are taken as HWC (B,H,W,C) frames."""
         return self.flownet.run(img0, img1, timestep, scale, want_all=False, pad=pad)
 
-    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0):
+    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0, streams=None):
         """End-to-end call on HOST (ideally pinned) tensors -- NCHW float16/float32, or HWC uint8 frames exactly as a
         video decoder delivers them (any H, W): H2D copies, inference and the D2H copy of the result are enqueued on
         `stream` (default: current) by rife_inference_host; returns without syncing.
-        `slot` selects an independent plan (workspace + staging buffers): calls with different slots on different
-        streams overlap their PCIe copies with each other's compute."""
+        `slot` selects an independent plan (workspace + staging buffers).  With `streams=(h2d, compute, d2h)` the call
+        becomes one stage set of a software pipeline (rife_inference_host_pipelined): rotate two or three slots over the
+        same three streams and the PCIe copies of one call overlap the kernels of its neighbours, while the kernels
+        of consecutive calls run back to back on the single compute stream."""
         net = self.flownet
         if img0_host.is_cuda or out_host.is_cuda:
             raise ValueError("inference_host takes host tensors")
@@ -72,6 +74,11 @@ class Model:
         io = net._io(img0_host.dtype)
         ts = net._timesteps(timestep, b)
         with torch.cuda.device(device):
+            if streams is not None:
+                s_in, s_c, s_out = (x.cuda_stream for x in streams)
+                _lib.check(lib.rife_inference_host_pipelined(pl.handle, img0_host.data_ptr(), img1_host.data_ptr(), ts,
+                                                             out_host.data_ptr(), io, s_in, s_c, s_out))
+                return out_host
             st = (stream or torch.cuda.current_stream()).cuda_stream
             _lib.check(lib.rife_inference_host(pl.handle, img0_host.data_ptr(), img1_host.data_ptr(), ts,
                                                out_host.data_ptr(), io, st))

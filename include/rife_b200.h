@@ -119,6 +119,14 @@ int rife_ifnet_forward(rife_plan* p, const void* img0, const void* img1,
  * on `stream`; returns without synchronising. */
 int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host,
                         const float* timestep_host, void* out_host, int io_dtype, void* stream);
+/* Same, as a three-stage software pipeline for a frame server (inference_video.py:139-143,253-270 keeps a reader
+ * thread, the model and a writer thread busy at once): H2D copies on stream_h2d, kernels on stream_compute, the D2H
+ * copy on stream_d2h, ordered by plan-owned events (including re-use of this plan's staging buffers by its next
+ * call).  Rotate >= 2 plans over ONE compute stream: the kernels of consecutive calls then run back to back and never
+ * interleave (which would evict each other's L2-resident activations) while their PCIe copies overlap the compute. */
+int rife_inference_host_pipelined(rife_plan* p, const void* img0_host, const void* img1_host,
+                                  const float* timestep_host, void* out_host, int io_dtype,
+                                  void* stream_h2d, void* stream_compute, void* stream_d2h);
 
 /* ---- single operators (op-level parity tests; drop-in for the reference's helpers) ------ */
 /* warp(tenInput, tenFlow), model/warplayer.py:8-22.  input (B,C,H,W), flow (B,2,H,W) in pixels,

@@ -130,6 +130,27 @@ def test_inference_host_e2e(pkg):
     assert np.abs(out.numpy() - g["e_out"]).max() < TOL32
 
 
+def test_inference_host_pipelined(pkg):
+    """rife_inference_host_pipelined: three plan slots rotating over (h2d, compute, d2h) streams give, for every call,
+    exactly what the single-stream host call gives -- including when a slot's staging buffers are re-used."""
+    m = seeded_model(pkg, AMP, "fp16")
+    rng = np.random.default_rng(21)
+    frames = [torch.from_numpy(rng.integers(0, 256, (2, 72, 100, 3), dtype=np.uint8)).pin_memory() for _ in range(8)]
+    ref = []
+    for i in range(7):
+        o = torch.empty((2, 72, 100, 3), dtype=torch.uint8).pin_memory()
+        m.inference_host(frames[i], frames[i + 1], o)
+        torch.cuda.synchronize()
+        ref.append(o.clone())
+    streams = tuple(torch.cuda.Stream(device=DEV) for _ in range(3))
+    outs = [torch.empty((2, 72, 100, 3), dtype=torch.uint8).pin_memory() for _ in range(7)]
+    for i in range(7):
+        m.inference_host(frames[i], frames[i + 1], outs[i], slot=i % 3, streams=streams)
+    torch.cuda.synchronize()
+    for i in range(7):
+        assert torch.equal(outs[i], ref[i]), i
+
+
 def test_dropin_import_paths(pkg):
     """`from train_log.RIFE_HDv3 import Model` / `from model.warplayer import warp` resolve to this package when
     eccv2022-rife_b200/dropin precedes the reference on sys.path."""
