@@ -266,8 +266,11 @@ struct PlanLayout {
   int s[5];
 };
 
-static int plan_layout(int B, int C, int H, int W, float scale, int precision, PlanLayout* L) {
-  if (B < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: B, H, W must be positive");
+// P frame pairs, T timesteps per pair (outputs B = P*T, pair-major), `seq`: the pairs are the P consecutive pairs of
+// ONE run of P+1 frames (Head features computed once per frame instead of twice)
+static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, int precision, PlanLayout* L) {
+  if (P < 1 || T < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: pairs, timesteps, H, W must be positive");
+  const int B = P * T, F = seq ? P + 1 : 2 * P;
   if (C != 3 && C != 4) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: C must be 3 or 4 (IFNet_HDv3.py:121-123 splits an RGB/RGBA pair)");
   if (!(scale == 1.f || scale == 0.5f || scale == 0.25f))
     RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be 1, 0.5 or 0.25 (scale > 1 up-samples the block input; not built)");
@@ -280,17 +283,17 @@ static int plan_layout(int B, int C, int H, int W, float scale, int precision, P
     RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale = " + std::to_string(mult) + " (got " +
                                   std::to_string(H) + "x" + std::to_string(W) + ")");
   const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
-  const size_t N = (size_t)B * H * W;
+  const size_t N = (size_t)B * H * W, NF = (size_t)F * H * W;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off = align_up(off + bytes, 1024);
     return o;
   };
-  L->src = take(2 * N * SRC_C * E);
-  L->head_in = take(2 * (N / 4) * 16 * E);
-  L->head_a = take(2 * (N / 4) * 16 * E);
-  L->head_b = take(2 * (N / 4) * 16 * E);
+  L->src = take(NF * SRC_C * E);
+  L->head_in = take((NF / 4) * 16 * E);
+  L->head_a = take((NF / 4) * 16 * E);
+  L->head_b = take((NF / 4) * 16 * E);
   size_t xin = 0, c0 = 0, act = 0;
   for (int i = 0; i < 5; ++i) {
     const size_t n = N / ((size_t)L->s[i] * L->s[i]);
@@ -308,8 +311,8 @@ static int plan_layout(int B, int C, int H, int W, float scale, int precision, P
   L->gridx = take((size_t)W * 4);
   L->gridy = take((size_t)H * 4);
   L->tstep = take((size_t)B * 4);
-  L->stage_in0 = take(N * C * 4);
-  L->stage_in1 = take(N * C * 4);
+  L->stage_in0 = take((size_t)(seq ? P + 1 : P) * H * W * C * 4);
+  L->stage_in1 = take((size_t)(seq ? 0 : P) * H * W * C * 4);
   L->stage_out = take(N * C * 4);
   L->total = off;
   return RIFE_OK;
@@ -317,7 +320,10 @@ static int plan_layout(int B, int C, int H, int W, float scale, int precision, P
 
 struct rife_plan {
   const rife_weights* w = nullptr;
-  int B = 0, C = 0, H = 0, W = 0, precision = 0, device = 0;
+  int B = 0, C = 0, H = 0, W = 0, precision = 0, device = 0;   // B = P * T outputs per call
+  int P = 0, T = 1, seq = 0;                                    // frame pairs, timesteps per pair, sequence mode
+  int nf0() const { return seq ? P + 1 : P; }                   // frames the caller passes in img0 / img1
+  int nf1() const { return seq ? 0 : P; }
   int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
   PlanLayout L{};
   char* ws = nullptr;
@@ -371,16 +377,27 @@ struct StageTimer {
 extern "C" {
 
 size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int precision) {
+  return rife_plan_workspace_bytes_ex(B, 1, 0, C, H, W, scale, precision);
+}
+
+size_t rife_plan_workspace_bytes_ex(int pairs, int timesteps, int sequence, int C, int H, int W, float scale, int precision) {
   PlanLayout L;
-  if (plan_layout(B, C, H, W, scale, precision, &L) != RIFE_OK) return 0;
+  if (plan_layout(pairs, timesteps, sequence, C, H, W, scale, precision, &L) != RIFE_OK) return 0;
   return L.total;
 }
 
 int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H, int W, float scale, void* workspace,
                      size_t workspace_bytes, const float* gridx_host, const float* gridy_host) {
+  return rife_plan_create_ex(out, w, B, 1, 0, C, H, W, scale, workspace, workspace_bytes, gridx_host, gridy_host);
+}
+
+int rife_plan_create_ex(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C, int H, int W,
+                        float scale, void* workspace, size_t workspace_bytes, const float* gridx_host,
+                        const float* gridy_host) {
   if (!out || !w || !workspace) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: null argument");
   PlanLayout L;
-  RIFE_TRY(plan_layout(B, C, H, W, scale, w->precision, &L));
+  RIFE_TRY(plan_layout(pairs, timesteps, sequence ? 1 : 0, C, H, W, scale, w->precision, &L));
+  const int B = pairs * timesteps;
   if (workspace_bytes < L.total)
     RIFE_FAIL(RIFE_ERR_WORKSPACE, "rife_plan_create: workspace has " + std::to_string(workspace_bytes) + " bytes, need " +
                                       std::to_string(L.total));
@@ -391,6 +408,7 @@ int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H
   if (dev != w->device) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: weights live on another device");
   auto* p = new rife_plan();
   p->w = w; p->B = B; p->C = C; p->H = H; p->W = W; p->precision = w->precision; p->device = dev;
+  p->P = pairs; p->T = timesteps; p->seq = sequence ? 1 : 0;
   p->L = L;
   // 1024-byte alignment for TMA/UMMA-facing buffers: offsets are 1024-aligned, so align the base too
   p->ws = (char*)workspace;
@@ -457,7 +475,7 @@ static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, boo
 
 static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
                         const rife_ifnet_outputs* outs, int io_dtype, cudaStream_t st) {
-  if (!p || !img0 || !img1 || !timestep_host || !outs) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: null argument");
+  if (!p || !img0 || (!img1 && !p->seq) || !timestep_host || !outs) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: null argument");
   if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8)
     RIFE_FAIL(RIFE_ERR_DTYPE, "rife: io_dtype must be RIFE_F32, RIFE_F16 or RIFE_U8");
   int dev = 0;
@@ -478,17 +496,20 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.gridx = (const float*)p->at(L.gridx);
   c.gridy = (const float*)p->at(L.gridy);
   c.tstep = (const float*)p->at(L.tstep);
+  // SRC frames: [img0's frames | img1's frames]; output b = pair * T + t warps frames (pair, pair + P), or in sequence
+  // mode (one run of P + 1 frames) the neighbours (pair, pair + 1)
+  c.F = p->nf0() + p->nf1(); c.nf0 = p->nf0(); c.src_div = p->T;
   c.src0 = p->at(L.src);
-  c.src1 = (char*)p->at(L.src) + N * SRC_C * E;
+  c.src1 = (char*)p->at(L.src) + (size_t)(p->seq ? 1 : p->P) * H * W * SRC_C * E;
   c.half_act = half_act;
   c.planar_head = half_act && w->head_hk;
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
   p->n_stage = 0;
-  RIFE_STAGE("prep", launch_prep(c, img0, img1, io_dtype, (void*)c.src0, (void*)c.src1, p->at(L.head_in), st));
+  RIFE_STAGE("prep", launch_prep(c, img0, img1, io_dtype, p->at(L.src), p->at(L.head_in), st));
   {
     ConvIO io;
-    io.B = 2 * B; io.H = H / 2; io.W = W / 2;
+    io.B = c.F; io.H = H / 2; io.W = W / 2;
     io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;
     RIFE_STAGE("head.cnn0", run_conv(p, w->head[0], io, c.planar_head, st));
     io.in = p->at(L.head_a); io.out = p->at(L.head_b);
@@ -567,22 +588,22 @@ int rife_inference(rife_plan* p, const void* img0, const void* img1, const float
 
 int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,
                         void* out_host, int io_dtype, void* stream) {
-  if (!p || !img0_host || !img1_host || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host: null argument");
+  if (!p || !img0_host || (!img1_host && !p->seq) || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host: null argument");
   if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host: bad io_dtype");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = io_dtype == RIFE_F32 ? 4 : (io_dtype == RIFE_F16 ? 2 : 1);
-  const size_t bytes = (size_t)p->B * p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
-  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, bytes, cudaMemcpyHostToDevice, st));
-  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, bytes, cudaMemcpyHostToDevice, st));
+  const size_t frame = (size_t)p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, frame * p->nf0(), cudaMemcpyHostToDevice, st));
+  if (p->nf1()) RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, frame * p->nf1(), cudaMemcpyHostToDevice, st));
   RIFE_TRY(rife_inference(p, p->at(p->L.stage_in0), p->at(p->L.stage_in1), timestep_host, p->at(p->L.stage_out), io_dtype,
                           stream));
-  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), bytes, cudaMemcpyDeviceToHost, st));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), frame * p->B, cudaMemcpyDeviceToHost, st));
   return RIFE_OK;
 }
 
 int rife_inference_host_pipelined(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,
                                   void* out_host, int io_dtype, void* stream_h2d, void* stream_compute, void* stream_d2h) {
-  if (!p || !img0_host || !img1_host || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host_pipelined: null argument");
+  if (!p || !img0_host || (!img1_host && !p->seq) || !out_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference_host_pipelined: null argument");
   if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8) RIFE_FAIL(RIFE_ERR_DTYPE, "rife_inference_host_pipelined: bad io_dtype");
   cudaStream_t s_in = (cudaStream_t)stream_h2d, s_c = (cudaStream_t)stream_compute, s_out = (cudaStream_t)stream_d2h;
   if (!p->ev_in) {
@@ -594,11 +615,11 @@ int rife_inference_host_pipelined(rife_plan* p, const void* img0_host, const voi
     RIFE_CUDA_TRY(cudaEventRecord(p->ev_out, s_out));
   }
   const size_t esz = io_dtype == RIFE_F32 ? 4 : (io_dtype == RIFE_F16 ? 2 : 1);
-  const size_t bytes = (size_t)p->B * p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
+  const size_t frame = (size_t)p->C * (p->fh ? p->fh : p->H) * (p->fw ? p->fw : p->W) * esz;
   // H2D: the previous inference on this plan must have consumed its staging-in buffers
   RIFE_CUDA_TRY(cudaStreamWaitEvent(s_in, p->ev_compute, 0));
-  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, bytes, cudaMemcpyHostToDevice, s_in));
-  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, bytes, cudaMemcpyHostToDevice, s_in));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in0), img0_host, frame * p->nf0(), cudaMemcpyHostToDevice, s_in));
+  if (p->nf1()) RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(p->L.stage_in1), img1_host, frame * p->nf1(), cudaMemcpyHostToDevice, s_in));
   RIFE_CUDA_TRY(cudaEventRecord(p->ev_in, s_in));
   // compute: frames resident, previous result of this plan already copied out
   RIFE_CUDA_TRY(cudaStreamWaitEvent(s_c, p->ev_in, 0));
@@ -608,7 +629,7 @@ int rife_inference_host_pipelined(rife_plan* p, const void* img0_host, const voi
   RIFE_CUDA_TRY(cudaEventRecord(p->ev_compute, s_c));
   // D2H
   RIFE_CUDA_TRY(cudaStreamWaitEvent(s_out, p->ev_compute, 0));
-  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), bytes, cudaMemcpyDeviceToHost, s_out));
+  RIFE_CUDA_TRY(cudaMemcpyAsync(out_host, p->at(p->L.stage_out), frame * p->B, cudaMemcpyDeviceToHost, s_out));
   RIFE_CUDA_TRY(cudaEventRecord(p->ev_out, s_out));
   return RIFE_OK;
 }

@@ -206,7 +206,9 @@ inline ImgLayout make_layout(int io_dtype, int C, int h, int w) {
 }
 
 struct PixelCtx {
-  int B, C, H, W;
+  int B, C, H, W;      // B = outputs (virtual pairs) = frame pairs x timesteps per pair
+  int F = 0, nf0 = 0;  // SRC frames in total / of them taken from img0 (the rest from img1)
+  int src_div = 1;     // output b warps SRC frames b / src_div of src0 and src1
   int h = 0, w = 0;    // frame size seen by the caller (0 = H, W)
   const float* gridx;  // device, W entries (model/warplayer.py:11)
   const float* gridy;  // device, H entries (model/warplayer.py:13)
@@ -218,8 +220,8 @@ struct PixelCtx {
 };
 
 // NCHW image (io dtype) -> SRC tensor channels 4..7 (+ zeros in 0..3) and the s2d Head input [2B][H/2][W/2][16]
-int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
-                void* head_in, cudaStream_t st);
+int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src_all, void* head_in,
+                cudaStream_t st);
 // builds the s2d block input of block `level` from the lazily-accumulated tmp levels [0, level)
 // `fbuf` ([B][H][W][4] fp32): full-resolution flow summed over levels [0, fbuf_levels); read when fbuf_levels > 0,
 // (re)written with the sum over [0, level) when `fbuf_store` (only valid when every pixel is sampled: s <= 2)

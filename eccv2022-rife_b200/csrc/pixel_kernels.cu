@@ -102,6 +102,7 @@ struct WarpGeom {
   float halfw, halfh;          // (W-1)/2, (H-1)/2   (model/warplayer.py:18-19)
   float inv_halfw, inv_halfh;  // reciprocals, used by the fp16-storage pipeline (1 ulp of the normalised coordinate)
   float wm1, hm1;              // W-1, H-1
+  int src_div;                 // output b reads SRC frames b / src_div (several timesteps share one frame pair)
 };
 
 
@@ -177,21 +178,20 @@ __device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int j0,
 // prep: NCHW images -> SRC tensors (ch 4..7; ch 0..3 zero until Head writes them) + s2d Head input
 template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
-                                                   T* __restrict__ src0, T* __restrict__ src1,
-                                                   T* __restrict__ head_in, int B, int C, int H, int W,
-                                                   int planar, int write_src, ImgLayout lay) {
+                                                   T* __restrict__ src_all, T* __restrict__ head_in, int F, int nf0,
+                                                   int C, int H, int W, int planar, int write_src, ImgLayout lay) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nq = (size_t)B * H2 * W2;
-  const int frame = blockIdx.y;
+  const size_t nq = (size_t)F * H2 * W2;
   if (q >= nq) return;
   const int x2 = (int)(q % W2);
   const int y2 = (int)((q / W2) % H2);
-  const int b = (int)(q / ((size_t)W2 * H2));
-  const Tio* img = frame ? img1 : img0;
-  T* src = frame ? src1 : src0;
+  const int f = (int)(q / ((size_t)W2 * H2));    // frame index: img0's nf0 frames first, then img1's
+  const int b = f < nf0 ? f : f - nf0;
+  const Tio* img = f < nf0 ? img0 : img1;
+  T* src = src_all + (size_t)(f - b) * H * W * SRC_C;
   float hv[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) hv[i] = 0.f;
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
     }
   }
   // pixel-major [2B][H/2][W/2][16] or planar-8 [2B][2][H/2][W/2][8] (conv_halo.cu)
-  T* hp = planar ? head_in + ((((size_t)frame * B + b) * 2 * H2 + y2) * W2 + x2) * 8
-                 : head_in + ((((size_t)frame * B + b) * H2 + y2) * W2 + x2) * 16;
+  T* hp = planar ? head_in + (((size_t)f * 2 * H2 + y2) * W2 + x2) * 8
+                 : head_in + (((size_t)f * H2 + y2) * W2 + x2) * 16;
   const size_t gstride = planar ? (size_t)H2 * W2 * 8 : 8;
   float a[8];
 #pragma unroll
@@ -232,15 +232,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 // by Head.cnn3's epilogue).  One thread converts a 2 x 8 pixel strip: 16-byte loads per channel row, 16-byte stores.
 template <typename Tio>
 __global__ void __launch_bounds__(256) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
-                                                          __half* __restrict__ head_in, int B, int C, int H, int W) {
+                                                          __half* __restrict__ head_in, int nf0, int C, int H, int W) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;  // strip index along x (8 pixels)
-  const int y2 = blockIdx.y, fb = blockIdx.z;            // fb = frame * B + b
+  const int y2 = blockIdx.y, fb = blockIdx.z;            // frame index: img0's nf0 frames first, then img1's
   if (xs >= W8) return;
-  const int frame = fb / B, b = fb - frame * B;
-  const Tio* img = (frame ? img1 : img0) + (size_t)b * C * H * W;
+  const Tio* img = fb < nf0 ? img0 + (size_t)fb * C * H * W : img1 + (size_t)(fb - nf0) * C * H * W;
   float px[2][4][8];  // [row][channel][x]
 #pragma unroll
   for (int r = 0; r < 2; ++r)
@@ -294,8 +293,8 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, b = blockIdx.z;
   if (X >= Ws) return;
-  const T* s0 = src0 + (size_t)b * H * W * SRC_C;
-  const T* s1 = src1 + (size_t)b * H * W * SRC_C;
+  const T* s0 = src0 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const T* s1 = src1 + (size_t)(b / geom.src_div) * H * W * SRC_C;
   const float t = tstep[b];
   constexpr int ns = NS;                      // samples per axis: F.interpolate(1/s) reads the centre 2x2 (lambda = 0.5)
   const int off = (NS == 1) ? 0 : (s / 2 - 1);
@@ -438,8 +437,8 @@ __global__ void __launch_bounds__(128) block_input_h_kernel(LevelsArg L, int lev
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, b = blockIdx.z;
   if (X >= Ws) return;
-  const __half* s0 = src0 + (size_t)b * H * W * SRC_C;
-  const __half* s1 = src1 + (size_t)b * H * W * SRC_C;
+  const __half* s0 = src0 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const __half* s1 = src1 + (size_t)(b / geom.src_div) * H * W * SRC_C;
   const int off = (NS == 1) ? 0 : (s / 2 - 1);
   const int x0 = X * s + off, y0 = Y * s + off;
   float flow[NQ][4];
@@ -572,8 +571,8 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
   if (ow0 || ow1 || omerged) {
     const float gx = gridx[x], gy = gridy[y];
     float a[8], c[8];
-    warp8<T>(src0 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);  // IFNet_HDv3.py:155
-    warp8<T>(src1 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);  // IFNet_HDv3.py:156
+    warp8<T>(src0 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);  // IFNet_HDv3.py:155
+    warp8<T>(src1 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);  // IFNet_HDv3.py:156
     const float m = 1.f / (1.f + expf(-last[4]));                                         // IFNet_HDv3.py:158
     for (int ch = 0; ch < C; ++ch) {
       const float w0 = a[4 + ch], w1 = c[4 + ch];
@@ -628,8 +627,8 @@ __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__
   for (int c = 0; c < 4; ++c) flow[c] += t8[c];                                    // IFNet_HDv3.py:152
   const float gx = gridx[x], gy = gridy[y];
   float a[4], c[4];
-  warp_img4(src0 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);   // IFNet_HDv3.py:155
-  warp_img4(src1 + (size_t)b * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);   // IFNet_HDv3.py:156
+  warp_img4(src0 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);   // IFNet_HDv3.py:155
+  warp_img4(src1 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);   // IFNet_HDv3.py:156
   const float m = 1.f / (1.f + __expf(-t8[4]));                                    // IFNet_HDv3.py:158
   for (int ch = 0; ch < C; ++ch)
     omerged[(size_t)(b * lay.sb + ch * lay.sc + y * lay.sy + x * lay.sx)] = from_f<Tio>(a[ch] * m + c[ch] * (1.f - m));
@@ -734,6 +733,7 @@ inline WarpGeom make_geom(int H, int W) {
   g.inv_halfh = 1.f / g.halfh;
   g.wm1 = (float)(W - 1);
   g.hm1 = (float)(H - 1);
+  g.src_div = 1;
   return g;
 }
 
@@ -741,26 +741,27 @@ inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
 
-int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src0, void* src1,
-                void* head_in, cudaStream_t st) {
+int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src_all, void* head_in,
+                cudaStream_t st) {
   const int fh = c.h ? c.h : c.H, fw = c.w ? c.w : c.W;
   const ImgLayout lay = make_layout(io_dtype, c.C, fh, fw);
   if (c.planar_head && c.half_act && c.W % 8 == 0 && fh == c.H && fw == c.W && io_dtype != RIFE_U8) {
-    const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)(2 * c.B));
+    const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
     if (io_dtype == RIFE_F16)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.B, c.C, c.H, c.W));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W));
     else if (io_dtype == RIFE_F32)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.B, c.C, c.H, c.W));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W));
     else
       RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
     RIFE_LAUNCH_CHECK();
     return RIFE_OK;
   }
-  const size_t nq = (size_t)c.B * (c.H / 2) * (c.W / 2);
-  dim3 grid(nblk(nq, 256), 2);
+  const size_t nq = (size_t)c.F * (c.H / 2) * (c.W / 2);
+  dim3 grid(nblk(nq, 256));
 #define RIFE_PREP(TIO, T)                                                                                        \
-  RIFE_CUDA_TRY(launch_pdl(prep_kernel<TIO, T>, grid, dim3(256), 0, st, (const TIO*)img0, (const TIO*)img1, (T*)src0, \
-                           (T*)src1, (T*)head_in, c.B, c.C, c.H, c.W, c.planar_head ? 1 : 0, c.planar_head ? 0 : 1, lay))
+  RIFE_CUDA_TRY(launch_pdl(prep_kernel<TIO, T>, grid, dim3(256), 0, st, (const TIO*)img0, (const TIO*)img1,            \
+                           (T*)src_all, (T*)head_in, c.F, c.nf0, c.C, c.H, c.W, c.planar_head ? 1 : 0,                \
+                           c.planar_head ? 0 : 1, lay))
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
@@ -790,6 +791,7 @@ int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int
                        float* fbuf, int fbuf_levels, bool fbuf_store, cudaStream_t st) {
   LevelsArg L = pack_levels(levels, level);
   WarpGeom g = make_geom(c.H, c.W);
+  g.src_div = c.src_div;
   const dim3 grid(nblk((size_t)(c.W / s), 128), (unsigned)(c.H / s), (unsigned)c.B);
 #define RIFE_BI(T, NS_, L0_)                                                                                       \
   RIFE_CUDA_TRY(launch_pdl(block_input_kernel<T, T, NS_, L0_>, grid, dim3(128), 0, st, L, level, s, (const T*)c.src0, \
@@ -821,6 +823,7 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   const size_t n = (size_t)c.B * c.H * c.W;
   LevelsArg L = pack_levels(levels, nlev);
   WarpGeom g = make_geom(c.H, c.W);
+  g.src_div = c.src_div;
   const int fh = c.h ? c.h : c.H, fw = c.w ? c.w : c.W;
   const ImgLayout lay = make_layout(io_dtype, c.C, fh, fw);
   if (io_dtype == RIFE_U8 && (o.flow || o.mask)) RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: flow / mask outputs need a float io dtype");

@@ -149,23 +149,24 @@ class IFNet(nn.Module):
         self._weights[key] = (h, stamp)
         return h
 
-    def _get_plan(self, device, prec, b, c, h, w, scale, slot=0):
+    def _get_plan(self, device, prec, b, c, h, w, scale, slot=0, nt=1, seq=False):
+        """b frame pairs x nt timesteps per pair; seq: the pairs are the b consecutive pairs of one run of b+1 frames."""
         lib = _lib.load()
         wh = self._get_weights(device, prec)
-        key = ((device.index, prec), b, c, h, w, float(scale), slot)
+        key = ((device.index, prec), b, c, h, w, float(scale), slot, nt, bool(seq))
         pl = self._plans.get(key)
         if pl is not None:
             return pl
         with torch.cuda.device(device):
-            nbytes = lib.rife_plan_workspace_bytes(b, c, h, w, float(scale), prec)
+            nbytes = lib.rife_plan_workspace_bytes_ex(b, nt, int(seq), c, h, w, float(scale), prec)
             if nbytes == 0:
                 _lib.check(-2)
             pl = _Plan()
             pl.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
             gx, gy, _, _ = base_grids(h, w, device)
             hd = C.c_void_p()
-            _lib.check(lib.rife_plan_create(C.byref(hd), wh, b, c, h, w, float(scale), pl.workspace.data_ptr(), nbytes,
-                                            gx.data_ptr(), gy.data_ptr()))
+            _lib.check(lib.rife_plan_create_ex(C.byref(hd), wh, b, nt, int(seq), c, h, w, float(scale),
+                                               pl.workspace.data_ptr(), nbytes, gx.data_ptr(), gy.data_ptr()))
             pl.handle = hd
         self._plans[key] = pl
         return pl
@@ -212,9 +213,9 @@ class IFNet(nn.Module):
         m = int(round(64 / float(scale)))
         return (h + m - 1) // m * m, (w + m - 1) // m * m
 
-    def plan_for(self, device, prec, b, c, h, w, scale, slot=0, pad=True):
+    def plan_for(self, device, prec, b, c, h, w, scale, slot=0, pad=True, nt=1, seq=False):
         hp, wp = self.padded_size(h, w, scale) if pad else (h, w)
-        pl = self._get_plan(device, prec, b, c, hp, wp, scale, slot)
+        pl = self._get_plan(device, prec, b, c, hp, wp, scale, slot, nt, seq)
         if (hp, wp) != (h, w) or getattr(pl, "frame", (hp, wp)) != (h, w):
             _lib.check(_lib.load().rife_plan_set_frame_size(pl.handle, h, w))
         pl.frame = (h, w)
@@ -261,6 +262,42 @@ class IFNet(nn.Module):
             _lib.check(lib.rife_ifnet_forward(pl.handle, img0.data_ptr(), img1.data_ptr(), ts, C.byref(o), io, stream))
         merged_list = [(w0[i], w1[i]) for i in range(4)] + [merged]
         return flows, mask, merged_list
+
+    def run_multi(self, img0, img1, timesteps, scale=1.0, pad=False):
+        """Several timesteps per frame pair with the Head features computed once per frame.
+        img0 / img1: P frame pairs -- or img1=None and img0 = one run of P+1 consecutive frames (video order; each
+        frame's features are then shared by its two pairs).  `timesteps`: T floats applied to every pair.
+        Returns (P, T, C, H, W) float or (P, T, H, W, C) uint8: out[p, t] = inference(pair p, timesteps[t])."""
+        self._check_input(img0)
+        lib = _lib.load()
+        seq = img1 is None
+        u8 = img0.dtype == torch.uint8
+        if u8:
+            n, h, w, c = img0.shape
+        else:
+            n, c, h, w = img0.shape
+        pairs = n - 1 if seq else n
+        if pairs < 1:
+            raise ValueError("sequence mode needs at least two frames")
+        if not seq and (img1.shape != img0.shape or img1.dtype != img0.dtype):
+            raise ValueError("img0 and img1 must have the same shape and dtype")
+        tl = [float(t) for t in timesteps]
+        nt = len(tl)
+        if nt < 1:
+            raise ValueError("at least one timestep")
+        img0 = img0.contiguous()
+        img1 = None if seq else img1.contiguous()
+        dev = img0.device
+        prec = self._resolve_precision(torch.float16 if u8 else img0.dtype)
+        pl = self.plan_for(dev, prec, pairs, c, h, w, scale, 0, pad or u8, nt, seq)
+        io = self._io(img0.dtype)
+        ts = (C.c_float * (pairs * nt))(*(tl * pairs))
+        shape = (pairs, nt, h, w, c) if u8 else (pairs, nt, c, h, w)
+        with torch.cuda.device(dev):
+            out = torch.empty(shape, dtype=img0.dtype, device=dev)
+            _lib.check(lib.rife_inference(pl.handle, img0.data_ptr(), None if seq else img1.data_ptr(), ts, out.data_ptr(), io,
+                                          torch.cuda.current_stream().cuda_stream))
+        return out
 
     def forward(self, x, timestep=0.5, scale_list=[8, 4, 2, 1], training=False, fastmode=True, ensemble=False):
         """Same signature / return structure as IFNet_HDv3.py:119-169 (inference branch):

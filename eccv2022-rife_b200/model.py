@@ -52,6 +52,17 @@ class Model:
         this call happen inside the first / last kernel); uint8 tensors are taken as HWC (B,H,W,C) frames."""
         return self.flownet.run(img0, img1, timestep, scale, want_all=False, pad=pad)
 
+    def inference_multi(self, img0, img1, timesteps=(0.25, 0.5, 0.75), scale=1.0, pad=False):
+        """Arbitrary-timestep nX interpolation (benchmark/HD_multi_4X.py:47 calls inference once per timestep): all
+        `timesteps` of every pair in one call, Head features computed once per frame.  Returns (P, T, C, H, W)."""
+        return self.flownet.run_multi(img0, img1, timesteps, scale, pad)
+
+    def inference_sequence(self, frames, timesteps=(0.5,), scale=1.0, pad=False):
+        """Video order (inference_video.py:215-260 walks consecutive frames): `frames` holds N consecutive frames, the
+        result the (N-1, T, ...) in-between frames; each frame's Head features are computed once and shared by the two
+        pairs it belongs to."""
+        return self.flownet.run_multi(frames, None, timesteps, scale, pad)
+
     def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0, streams=None):
         """End-to-end call on HOST (ideally pinned) tensors -- NCHW float16/float32, or HWC uint8 frames exactly as a
         video decoder delivers them (any H, W): H2D copies, inference and the D2H copy of the result are enqueued on

@@ -80,6 +80,17 @@ size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int pr
 int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H, int W,
                      float scale, void* workspace, size_t workspace_bytes,
                      const float* gridx_host, const float* gridy_host);
+/* Caller-side batching with Head-feature reuse (train_log/IFNet_HDv3.py:128-129 recomputes
+ * Head(frame) on every call): `pairs` frame pairs x `timesteps` timesteps per pair = pairs*timesteps outputs per
+ * call, pair-major (out[p*timesteps + t], timestep_host likewise) -- the arbitrary-timestep 4X / 8X case of
+ * benchmark/HD_multi_4X.py:47 computes each pair's features once.  sequence != 0: the pairs are the `pairs`
+ * consecutive pairs of ONE run of pairs+1 frames passed in img0 (img1 = NULL), as inference_video.py:215-260 walks a
+ * video: Head runs once per frame instead of twice.  rife_plan_create == (B, 1, 0). */
+size_t rife_plan_workspace_bytes_ex(int pairs, int timesteps, int sequence, int C, int H, int W, float scale,
+                                    int precision);
+int rife_plan_create_ex(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C,
+                        int H, int W, float scale, void* workspace, size_t workspace_bytes,
+                        const float* gridx_host, const float* gridy_host);
 int rife_plan_destroy(rife_plan* p);
 /* Frame size seen by the caller, (h, w) <= the plan's padded (H, W) (default: H, W).  Inputs are then (B,C,h,w) /
  * (B,h,w,C) tensors, zero-padded on the right / bottom inside the first kernel and every output is cropped back to

@@ -151,6 +151,33 @@ def test_inference_host_pipelined(pkg):
         assert torch.equal(outs[i], ref[i]), i
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_multi_timestep_and_sequence_reuse_head(pkg, precision):
+    """T timesteps per pair / consecutive-frame runs compute Head(frame) once; every output must be
+    bit-identical to the plain one-call-per-(pair, timestep) path, which is itself checked against the reference."""
+    m = seeded_model(pkg, AMP, precision)
+    dt = torch.float16 if precision == "fp16" else torch.float32
+    g = torch.Generator().manual_seed(5)
+    frames = torch.rand(4, 3, 64, 128, generator=g).to(DEV, dt)
+    ts = (0.25, 0.5, 0.75)
+    multi = m.inference_multi(frames[:3], frames[1:], ts)
+    assert multi.shape == (3, 3, 3, 64, 128)
+    for p in range(3):
+        for k, t in enumerate(ts):
+            assert torch.equal(multi[p, k], m.inference(frames[p:p + 1], frames[p + 1:p + 2], timestep=t)[0]), (p, t)
+    seq = m.inference_sequence(frames, ts)
+    assert torch.equal(seq, multi)
+    seq1 = m.inference_sequence(frames)                               # 2X: one in-between frame per pair
+    assert seq1.shape == (3, 1, 3, 64, 128) and torch.equal(seq1[:, 0], m.inference(frames[:3], frames[1:]))
+    # uint8 HWC frames of a size that needs padding, video order
+    u8 = (torch.rand(3, 70, 90, 3, generator=g) * 255).byte().to(DEV)
+    sq = m.inference_sequence(u8, (0.5,))
+    assert sq.shape == (2, 1, 70, 90, 3) and sq.dtype == torch.uint8
+    assert torch.equal(sq[:, 0], m.inference(u8[:2], u8[1:], pad=True))
+    with pytest.raises(ValueError):
+        m.inference_sequence(frames[:1])
+
+
 def test_dropin_import_paths(pkg):
     """`from train_log.RIFE_HDv3 import Model` / `from model.warplayer import warp` resolve to this package when
     eccv2022-rife_b200/dropin precedes the reference on sys.path."""
