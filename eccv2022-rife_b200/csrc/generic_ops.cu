@@ -49,28 +49,66 @@ __global__ void __launch_bounds__(256) slice_to_nchw_kernel(const T* __restrict_
   dst[i] = from_f<Tio>(v);
 }
 
+// ---- 8-channel chunks: one thread moves channels [c0, c0 + 8) of one pixel; 16-byte (fp16) / 2 x 16-byte (fp32)
+// vector accesses when the slice is 8-aligned (`vec`), scalar otherwise (raw 3 / 6 / 13 / 17-channel slices).
+template <typename T>
+__device__ __forceinline__ void load_chunk(const T* __restrict__ p, int nv, bool vec, float (&v)[8]) {
+  if (vec) {
+    ld8(p, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < nv ? to_f(p[i]) : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* __restrict__ p, int nv, bool vec, const float (&v)[8]) {
+  if (vec) {
+    st8(p, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) p[i] = from_f<T>(v[i]);
+  }
+}
+
 // F.interpolate(bilinear, align_corners=False) of a channel slice; dst = (acc ? dst : 0) + value * mul
 template <typename T, typename Td>
 __global__ void __launch_bounds__(256) resize_nhwc_kernel(const T* __restrict__ src, int sp, int so,
                                                           Td* __restrict__ dst, int dp, int dof, int B, int C, int Hs,
-                                                          int Ws, int Hd, int Wd, float ratio, float mul, int acc) {
+                                                          int Ws, int Hd, int Wd, float ratio, float mul, int acc,
+                                                          int vsrc, int vdst) {
+  const int nch = (C + 7) >> 3;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * Hd * Wd * C) return;
-  const int c = (int)(i % C), x = (int)((i / C) % Wd), y = (int)((i / ((size_t)C * Wd)) % Hd);
-  const int b = (int)(i / ((size_t)C * Wd * Hd));
-  float v;
+  if (i >= (size_t)B * Hd * Wd * nch) return;
+  const int ch = (int)(i % nch);
+  const size_t pix = i / nch;
+  const int x = (int)(pix % Wd), y = (int)((pix / Wd) % Hd), b = (int)(pix / ((size_t)Wd * Hd));
+  const int c0 = ch * 8, nv = min(8, C - c0);
+  float v[8];
   if (Hs == Hd && Ws == Wd) {
-    v = to_f(src[(((size_t)b * Hs + y) * Ws + x) * sp + so + c]);
+    load_chunk(src + (((size_t)b * Hs + y) * Ws + x) * sp + so + c0, nv, vsrc, v);
   } else {
     const Lerp ly = make_lerp(y, Hs, ratio), lx = make_lerp(x, Ws, ratio);
-    const T* p = src + (size_t)b * Hs * Ws * sp + so + c;
-    const float v00 = to_f(p[((size_t)ly.i0 * Ws + lx.i0) * sp]), v01 = to_f(p[((size_t)ly.i0 * Ws + lx.i1) * sp]);
-    const float v10 = to_f(p[((size_t)ly.i1 * Ws + lx.i0) * sp]), v11 = to_f(p[((size_t)ly.i1 * Ws + lx.i1) * sp]);
-    v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+    const T* p = src + (size_t)b * Hs * Ws * sp + so + c0;
+    float v00[8], v01[8], v10[8], v11[8];
+    load_chunk(p + ((size_t)ly.i0 * Ws + lx.i0) * sp, nv, vsrc, v00);
+    load_chunk(p + ((size_t)ly.i0 * Ws + lx.i1) * sp, nv, vsrc, v01);
+    load_chunk(p + ((size_t)ly.i1 * Ws + lx.i0) * sp, nv, vsrc, v10);
+    load_chunk(p + ((size_t)ly.i1 * Ws + lx.i1) * sp, nv, vsrc, v11);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ly.l0 * (lx.l0 * v00[k] + lx.l1 * v01[k]) + ly.l1 * (lx.l0 * v10[k] + lx.l1 * v11[k]);
   }
-  Td* d = dst + (((size_t)b * Hd + y) * Wd + x) * dp + dof + c;
-  v = v * mul;
-  *d = from_f<Td>(acc ? (to_f(*d) + v) : v);
+  Td* d = dst + (((size_t)b * Hd + y) * Wd + x) * dp + dof + c0;
+  if (acc) {
+    float o[8];
+    load_chunk(d, nv, vdst, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = o[k] + v[k] * mul;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] * mul;
+  }
+  store_chunk(d, nv, vdst, v);
 }
 
 // warp() of model/warplayer.py:8-22 on a channel slice; flow = 2 channels (x, y) of another NHWC tensor
@@ -79,11 +117,16 @@ __global__ void __launch_bounds__(256) warp_nhwc_kernel(const T* __restrict__ sr
                                                         const Tf* __restrict__ flow, int fp, int fo,
                                                         Td* __restrict__ dst, int dp, int dof, int B, int C, int H,
                                                         int W, const float* __restrict__ gridx,
-                                                        const float* __restrict__ gridy, float halfw, float halfh) {
+                                                        const float* __restrict__ gridy, float halfw, float halfh,
+                                                        int vsrc, int vdst) {
+  const int nch = (C + 7) >> 3;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * H * W) return;
-  const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((size_t)W * H));
-  const Tf* f = flow + i * fp + fo;
+  if (i >= (size_t)B * H * W * nch) return;
+  const int ch = (int)(i % nch);
+  const size_t pix = i / nch;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+  const int c0 = ch * 8, nv = min(8, C - c0);
+  const Tf* f = flow + pix * fp + fo;
   const float nx = gridx[x] + __fdiv_rn(to_f(f[0]), halfw), ny = gridy[y] + __fdiv_rn(to_f(f[1]), halfh);
   float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), (float)(W - 1));
   float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), (float)(H - 1));
@@ -94,29 +137,50 @@ __global__ void __launch_bounds__(256) warp_nhwc_kernel(const T* __restrict__ sr
   const float wsw = (x0f + 1.f - ix) * (iy - y0f), wse = (ix - x0f) * (iy - y0f);
   const int x0 = (int)x0f, y0 = (int)y0f;
   const bool xin = x0 + 1 < W, yin = y0 + 1 < H;
-  const T* p = src + (((size_t)b * H + y0) * W + x0) * sp + so;
-  Td* d = dst + i * dp + dof;
-  for (int c = 0; c < C; ++c) {
-    float r = to_f(p[c]) * wnw;
-    if (xin) r += to_f(p[sp + c]) * wne;
-    if (yin) {
-      r += to_f(p[(size_t)W * sp + c]) * wsw;
-      if (xin) r += to_f(p[(size_t)W * sp + sp + c]) * wse;
-    }
-    d[c] = from_f<Td>(r);
+  const T* p = src + (((size_t)b * H + y0) * W + x0) * sp + so + c0;
+  float r[8], t[8];
+  load_chunk(p, nv, vsrc, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = t[k] * wnw;
+  if (xin) {
+    load_chunk(p + sp, nv, vsrc, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] += t[k] * wne;
   }
+  if (yin) {
+    load_chunk(p + (size_t)W * sp, nv, vsrc, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] += t[k] * wsw;
+    if (xin) {
+      load_chunk(p + (size_t)W * sp + sp, nv, vsrc, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] += t[k] * wse;
+    }
+  }
+  store_chunk(dst + pix * dp + dof + c0, nv, vdst, r);
 }
 
-// space-to-depth of a channel slice: dst [B][H/2][W/2][4*cpad], channel = (py*2+px)*cpad + c (pad channels zero)
+// space-to-depth of a channel slice: dst [B][H/2][W/2][4*cpad], channel = (py*2+px)*cpad + c (pad channels zero);
+// cpad is a multiple of 8, so every destination chunk is one aligned vector
 template <typename T, typename Td>
 __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const T* __restrict__ src, int sp, int so, int C,
-                                                       Td* __restrict__ dst, int cpad, int B, int H, int W) {
+                                                       Td* __restrict__ dst, int cpad, int B, int H, int W, int vsrc) {
+  const int nch = cpad >> 3;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * H * W * cpad) return;
-  const int c = (int)(i % cpad), x = (int)((i / cpad) % W), y = (int)((i / ((size_t)cpad * W)) % H);
-  const int b = (int)(i / ((size_t)cpad * W * H));
-  const Td v = from_f<Td>(c < C ? to_f(src[(((size_t)b * H + y) * W + x) * sp + so + c]) : 0.f);
-  dst[((((size_t)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * cpad + c] = v;
+  if (i >= (size_t)B * H * W * nch) return;
+  const int ch = (int)(i % nch);
+  const size_t pix = i / nch;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+  const int c0 = ch * 8, nv = max(0, min(8, C - c0));
+  float v[8];
+  if (nv == 8 && vsrc) {
+    ld8(src + pix * sp + so + c0, v);
+  } else {
+    const T* p = src + pix * sp + so + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < nv ? to_f(p[k]) : 0.f;
+  }
+  st8(dst + ((((size_t)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * cpad + c0, v);
 }
 
 // merged = w0*sigmoid(mask) + w1*(1-sigmoid(mask))  (model/IFNet.py:98-99); with `refine` (pre-sigmoid Unet output):
@@ -143,6 +207,11 @@ __global__ void __launch_bounds__(256) eccv_merge_kernel(const T* __restrict__ w
 }
 
 }  // namespace
+
+// a slice can be moved in 8-channel vectors when base, pitch, offset and width are all 8-element aligned
+inline int vec_ok(const void* base, size_t esz, int pitch, int off, int C) {
+  return (pitch % 8 == 0 && off % 8 == 0 && C % 8 == 0 && ((uintptr_t)base % (8 * esz)) == 0) ? 1 : 0;
+}
 
 // dtype code -> element type tag (generic lambdas below pick the kernel instantiation)
 template <typename F>
@@ -182,14 +251,15 @@ int launch_nhwc_slice_to_nchw(const void* src, int sdt, int pitch, int off, void
 
 int launch_resize_nhwc(const void* src, int sdt, int spitch, int soff, void* dst, int ddt, int dpitch, int doff, int B,
                        int C, int Hs, int Ws, int Hd, int Wd, float mul, int accumulate, cudaStream_t st) {
-  const size_t n = (size_t)B * Hd * Wd * C;
+  const size_t n = (size_t)B * Hd * Wd * ((C + 7) / 8);
   const float ratio = (float)Hs / (float)Hd;  // power-of-two factors: exact
   return with_type(sdt, "nhwc_resize", [&](auto s) -> int {
     return with_type(ddt, "nhwc_resize", [&](auto d) -> int {
       using Ts = decltype(s);
       using Td = decltype(d);
+      const int vs = vec_ok(src, sizeof(Ts), spitch, soff, C), vd = vec_ok(dst, sizeof(Td), dpitch, doff, C);
       resize_nhwc_kernel<Ts, Td><<<nblk(n, 256), 256, 0, st>>>((const Ts*)src, spitch, soff, (Td*)dst, dpitch, doff, B, C, Hs,
-                                                               Ws, Hd, Wd, ratio, mul, accumulate);
+                                                               Ws, Hd, Wd, ratio, mul, accumulate, vs, vd);
       RIFE_LAUNCH_CHECK();
       return (int)RIFE_OK;
     });
@@ -199,7 +269,7 @@ int launch_resize_nhwc(const void* src, int sdt, int spitch, int soff, void* dst
 int launch_warp_nhwc(const void* src, int sdt, int spitch, int soff, const void* flow, int fdt, int fpitch, int foff,
                      void* dst, int ddt, int dpitch, int doff, int B, int C, int H, int W, const float* gridx,
                      const float* gridy, cudaStream_t st) {
-  const size_t n = (size_t)B * H * W;
+  const size_t n = (size_t)B * H * W * ((C + 7) / 8);
   const float hw = (float)((W - 1.0) / 2.0), hh = (float)((H - 1.0) / 2.0);
   return with_type(sdt, "nhwc_warp", [&](auto s) -> int {
     return with_type(fdt, "nhwc_warp", [&](auto f) -> int {
@@ -207,8 +277,10 @@ int launch_warp_nhwc(const void* src, int sdt, int spitch, int soff, const void*
         using Ts = decltype(s);
         using Tf = decltype(f);
         using Td = decltype(d);
+        const int vs = vec_ok(src, sizeof(Ts), spitch, soff, C), vd = vec_ok(dst, sizeof(Td), dpitch, doff, C);
         warp_nhwc_kernel<Ts, Tf, Td><<<nblk(n, 256), 256, 0, st>>>((const Ts*)src, spitch, soff, (const Tf*)flow, fpitch, foff,
-                                                                   (Td*)dst, dpitch, doff, B, C, H, W, gridx, gridy, hw, hh);
+                                                                   (Td*)dst, dpitch, doff, B, C, H, W, gridx, gridy, hw, hh,
+                                                                   vs, vd);
         RIFE_LAUNCH_CHECK();
         return (int)RIFE_OK;
       });
@@ -218,12 +290,14 @@ int launch_warp_nhwc(const void* src, int sdt, int spitch, int soff, const void*
 
 int launch_s2d_nhwc(const void* src, int sdt, int spitch, int soff, int C, void* dst, int ddt, int cpad, int B, int H,
                     int W, cudaStream_t st) {
-  const size_t n = (size_t)B * H * W * cpad;
+  if (cpad % 8 || ((uintptr_t)dst & 31)) RIFE_FAIL(RIFE_ERR_SHAPE, "nhwc_s2d: cpad must be a multiple of 8 and dst 32-byte aligned");
+  const size_t n = (size_t)B * H * W * (cpad / 8);
   return with_type(sdt, "nhwc_s2d", [&](auto s) -> int {
     return with_type(ddt, "nhwc_s2d", [&](auto d) -> int {
       using Ts = decltype(s);
       using Td = decltype(d);
-      s2d_nhwc_kernel<Ts, Td><<<nblk(n, 256), 256, 0, st>>>((const Ts*)src, spitch, soff, C, (Td*)dst, cpad, B, H, W);
+      s2d_nhwc_kernel<Ts, Td><<<nblk(n, 256), 256, 0, st>>>((const Ts*)src, spitch, soff, C, (Td*)dst, cpad, B, H, W,
+                                                            vec_ok(src, sizeof(Ts), spitch, soff, 8));
       RIFE_LAUNCH_CHECK();
       return (int)RIFE_OK;
     });

@@ -141,6 +141,7 @@ class IFNet(nn.Module):
         self.contextnet = Contextnet()
         self.unet = Unet()
         self._layers = {}      # precision -> {name: _Layer}
+        self._arenas = {}      # (device, B, H, W, fp16?, scales) -> work tensors of one forward, in call order
         self._stamp = None
         self._generation = 0
 
@@ -163,6 +164,7 @@ class IFNet(nn.Module):
             for l in layers.values():
                 l.free()
         self._layers = {}
+        self._arenas = {}
 
     def __del__(self):
         try:
@@ -235,8 +237,24 @@ class IFNet(nn.Module):
         io = _lib.RIFE_F32 if x.dtype == torch.float32 else _lib.RIFE_F16
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
-            z = lambda h, w, p, dt=adt: torch.zeros((B, h, w, p), dtype=dt, device=dev)
-            e = lambda h, w, p, dt=adt: torch.empty((B, h, w, p), dtype=dt, device=dev)
+            # work tensors come from a per-(shape, precision) arena in call order: allocated and zero-filled once, then
+            # re-used by every later forward (zero padding channels are never written, so they stay zero)
+            akey = (str(dev), B, H, W, h16, tuple(s3))
+            if akey not in self._arenas and len(self._arenas) >= 4:
+                self._arenas.pop(next(iter(self._arenas)))        # keep the work memory of a few recent shapes only
+            arena = self._arenas.setdefault(akey, [])
+            cursor = [0]
+
+            def z(h, w, p, dt=adt):
+                k = cursor[0]
+                cursor[0] += 1
+                if k == len(arena):
+                    arena.append(torch.zeros((B, h, w, p), dtype=dt, device=dev))
+                t = arena[k]
+                assert t.shape == (B, h, w, p) and t.dtype == dt
+                return t
+
+            e = z
             f32 = torch.float32
             chk = _lib.check
 

@@ -239,6 +239,36 @@ def test_720p_config2_fp16(pkg):
     _check16(out, ref, "720p")
 
 
+def _smooth_pair(seed, h, w):
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.rand(1, 3, h // 8 + 2, w // 8 + 2, generator=g)
+    big = torch.nn.functional.interpolate(lo, size=(h + 16, w + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+    return big[:, :, 8:8 + h, 8:8 + w].contiguous(), big[:, :, 5:5 + h, 11:11 + w].contiguous()
+
+
+def test_1080p_4x_config3_fp16(pkg):
+    """BASELINE config 3: 1080p 4X -- timesteps {0.25, 0.5, 0.75} of one pair in one inference_multi call -- against the
+    torch-CPU fp32 restatement run once per timestep."""
+    a, b = _smooth_pair(11, 1088, 1920)
+    m = seeded_model(pkg, AMP, "fp16")
+    out = m.inference_multi(a.to(DEV).half(), b.to(DEV).half(), (0.25, 0.5, 0.75)).float().cpu().numpy()
+    sd = torch_state_dict(m)
+    for k, t in enumerate((0.25, 0.5, 0.75)):
+        _check16(out[:, k], T.model_inference(sd, a, b, timestep=t).numpy(), f"1080p t={t}")
+
+
+def test_4k_scale_half_config4(pkg):
+    """BASELINE config 4: 4K (padded 2176x3840) 2X with scale=0.5 (scale_list [32,16,8,4,2]) against the torch-CPU fp32
+    restatement, in both precisions."""
+    a, b = _smooth_pair(12, 2176, 3840)
+    m32, m16 = seeded_model(pkg, AMP, "fp32"), seeded_model(pkg, AMP, "fp16")
+    ref = T.model_inference(torch_state_dict(m32), a, b, scale=0.5).numpy()
+    out = m32.inference(a.to(DEV), b.to(DEV), scale=0.5).cpu().numpy()
+    assert np.abs(out - ref).max() < TOL32
+    out = m16.inference(a.to(DEV).half(), b.to(DEV).half(), scale=0.5).float().cpu().numpy()
+    _check16(out, ref, "4K scale 0.5")
+
+
 def test_batch_consistency_fp16(pkg):
     rng = np.random.default_rng(4)
     a = cu(rng.random((3, 3, 128, 128), dtype=np.float32)).half()
