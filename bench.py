@@ -210,6 +210,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module("eccv2022-rife_b200")
     lib = pkg._lib.load()
+    numa_cores = pkg.sharding.bind_to_gpu_numa(local_rank) if world > 1 else 0   # pinned buffers on the GPU's NUMA node
     pkg.model.device = dev
     torch.manual_seed(1234)
     model = pkg.Model(precision=args.precision)
@@ -295,6 +296,32 @@ def main():
     e2e = world * P * args.steps / (ms_e2e / 1e3)
     frame_bytes = P * CH * FH * FW
 
+    # ---- (2b) the same PCIe traffic with no kernels: what the host <-> device link alone sustains with every rank
+    #      copying at once (explains e2e when several GPUs share the host's PCIe / memory bandwidth)
+    d_in = [torch.empty_like(u8_sets[0][0], device=dev) for _ in range(2)]
+    d_out = torch.empty((P, FH, FW, CH), dtype=torch.uint8, device=dev)
+
+    def copy_steps(n):
+        for i in range(n):
+            a, b = u8_sets[i % NSETS]
+            with torch.cuda.stream(streams[0]):
+                d_in[0].copy_(a, non_blocking=True)
+                d_in[1].copy_(b, non_blocking=True)
+            with torch.cuda.stream(streams[2]):
+                host_out[i % NSLOT].copy_(d_out, non_blocking=True)
+
+    copy_steps(3)
+    barrier()
+    e0.record()
+    for st_ in streams:
+        st_.wait_stream(cur)
+    copy_steps(args.steps)
+    for st_ in streams:
+        cur.wait_stream(st_)
+    e1.record()
+    barrier()
+    ms_copy = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
     # ---- (3) per-kernel CUDA-event timing (separate pass over the same steps so that `value` is undisturbed)
     plan = net._plans[next(k for k in net._plans if k[-1] == 0)]
     lib.rife_plan_set_frame_size(plan.handle, H, W)   # slot 0 was last used by the 1080-row e2e path
@@ -352,9 +379,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "precision": args.precision,
                    "parallelism": f"frame-pair sharding x{world}, no collective",
+                   "host_numa_cores_bound": numa_cores,
                    "l2_policy": f"inputs rotate over {NSETS} distinct batches; each step streams >1 GB of intermediates (> 126 MB L2)"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": frame_bytes,
-                "ms_per_step": ms_e2e / args.steps,
+                "ms_per_step": ms_e2e / args.steps, "copy_only_ms_per_step": ms_copy,
                 "api": "rife_inference_host: pinned uint8 HWC 1080x1920 frames in, uint8 HWC frame out, 3 plan slots over h2d / compute / d2h streams (rife_inference_host_pipelined)"},
         "gpu_launches": int(launches),
         "clocks": clocks,

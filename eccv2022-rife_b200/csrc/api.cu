@@ -890,6 +890,11 @@ int rife_nhwc_s2d(const void* src, int src_dtype, int spitch, int soff, int C, v
   if (H % 2 || W % 2 || cpad < C) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_s2d: even H, W and cpad >= C required");
   return launch_s2d_nhwc(src, src_dtype, spitch, soff, C, dst, dst_dtype, cpad, B, H, W, (cudaStream_t)stream);
 }
+int rife_nhwc_fill(void* dst, int dst_dtype, int pitch, int off, int B, int C, int H, int W, float value, void* stream) {
+  if (!dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_fill: null argument");
+  if (B < 1 || C < 1 || H < 1 || W < 1 || off < 0 || off + C > pitch) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_fill: bad slice");
+  return launch_fill_nhwc(dst, dst_dtype, pitch, off, B, C, H, W, value, (cudaStream_t)stream);
+}
 int rife_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm, int om,
                     int w_dtype, const void* refine, int refine_dtype, int pr, int orf, void* out, int io_dtype, int B,
                     int H, int W, void* stream) {

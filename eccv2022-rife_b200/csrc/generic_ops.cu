@@ -183,6 +183,14 @@ __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const T* __restrict__ src
   st8(dst + ((((size_t)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * cpad + c0, v);
 }
 
+// constant plane(s): dst[..., off : off + C] = value  (the timestep plane of model/IFNet_m.py:64)
+template <typename Td>
+__global__ void __launch_bounds__(256) fill_nhwc_kernel(Td* __restrict__ dst, int dp, int dof, size_t npix, int C, float value) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  dst[(i / C) * dp + dof + (int)(i % C)] = from_f<Td>(value);
+}
+
 // merged = w0*sigmoid(mask) + w1*(1-sigmoid(mask))  (model/IFNet.py:98-99); with `refine` (pre-sigmoid Unet output):
 // clamp(merged + sigmoid(refine)*2 - 1, 0, 1)  (model/refine.py:82, model/IFNet.py:106-107).  Output NCHW.
 template <typename Tio, typename T, typename Tr>
@@ -301,6 +309,16 @@ int launch_s2d_nhwc(const void* src, int sdt, int spitch, int soff, int C, void*
       RIFE_LAUNCH_CHECK();
       return (int)RIFE_OK;
     });
+  });
+}
+
+int launch_fill_nhwc(void* dst, int ddt, int dpitch, int doff, int B, int C, int H, int W, float value, cudaStream_t st) {
+  const size_t npix = (size_t)B * H * W;
+  return with_type(ddt, "nhwc_fill", [&](auto d) -> int {
+    using Td = decltype(d);
+    fill_nhwc_kernel<Td><<<nblk(npix * C, 256), 256, 0, st>>>((Td*)dst, dpitch, doff, npix, C, value);
+    RIFE_LAUNCH_CHECK();
+    return (int)RIFE_OK;
   });
 }
 

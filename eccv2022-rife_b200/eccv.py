@@ -131,13 +131,16 @@ class _Layer:
 class IFNet(nn.Module):
     """Drop-in for `model.IFNet.IFNet` (inference branch: `x` holds img0, img1 and no ground truth)."""
 
+    TIMESTEP_PLANE = 0      # IFNet_m adds one constant timestep channel after img1 (model/IFNet_m.py:56-59,64)
+
     def __init__(self, precision="auto"):
         super().__init__()
         self.precision = _precision_from_env(precision)
-        self.block0 = IFBlock(6, c=240)          # model/IFNet.py:56-61: same construction order => same default init
-        self.block1 = IFBlock(13 + 4, c=150)
-        self.block2 = IFBlock(13 + 4, c=90)
-        self.block_tea = IFBlock(16 + 4, c=90)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
+        tp = self.TIMESTEP_PLANE
+        self.block0 = IFBlock(6 + tp, c=240)          # model/IFNet.py:56-61: same construction order => same default init
+        self.block1 = IFBlock(13 + 4 + tp, c=150)
+        self.block2 = IFBlock(13 + 4 + tp, c=90)
+        self.block_tea = IFBlock(16 + 4 + tp, c=90)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
         self.contextnet = Contextnet()
         self.unet = Unet()
         self._layers = {}      # precision -> {name: _Layer}
@@ -208,9 +211,11 @@ class IFNet(nn.Module):
         return L
 
     # ---------------------------------------------------------------- forward
-    def forward(self, x, scale=[4, 2, 1], timestep=0.5):
+    def forward(self, x, scale=[4, 2, 1], timestep=0.5, returnflow=False):
         """model/IFNet.py:63-108, inference branch.  Returns the reference's 6-tuple
-        (flow_list[3], sigmoid(mask), merged[3], None, None, 0).  `timestep` is ignored by this network."""
+        (flow_list[3], sigmoid(mask), merged[3], None, None, 0).  `timestep` is ignored by this network; the IFNet_m
+        subclass feeds it to every block as a constant plane (float, or a (B,1,1,1) tensor) and honours `returnflow`
+        (model/IFNet_m.py:63-64,104-105)."""
         if not x.is_cuda:
             raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
         if x.dtype not in (torch.float32, torch.float16):
@@ -221,6 +226,15 @@ class IFNet(nn.Module):
         if any(v not in (1.0, 2.0, 4.0, 8.0, 16.0) for v in s3):
             raise NotImplementedError(f"scale entries must be powers of two >= 1, got {list(scale)}")
         B, _, H, W = x.shape
+        tp = self.TIMESTEP_PLANE
+        if tp:
+            if torch.is_tensor(timestep):
+                tvals = [float(v) for v in timestep.detach().reshape(-1).cpu().tolist()]
+                tvals = tvals * B if len(tvals) == 1 else tvals
+                if len(tvals) != B:
+                    raise ValueError("tensor timestep must broadcast as (B,1,1,1)")
+            else:
+                tvals = [float(timestep)] * B
         need = int(max(16, 4 * max(s3)))
         if H % need or W % need:
             raise RuntimeError(f"ECCV IFNet: H and W must be multiples of {need} for scale list {list(scale)} (got {H}x{W})")
@@ -291,9 +305,19 @@ class IFNet(nn.Module):
             for i in range(3):                                                        # model/IFNet.py:74-86
                 s = int(s3[i])
                 hs, ws = H // s, W // s
-                cin = 6 if i == 0 else 17
+                cin = (6 if i == 0 else 17) + tp
                 xin = z(hs, ws, _pad8(cin))
-                if i == 0:
+                if tp:                                                                # IFNet_m.py:78,82: [img0,img1,t,...]
+                    resize(full, 0, 6, xin, 0)
+                    if len(set(tvals)) == 1:
+                        chk(lib.rife_nhwc_fill(xin.data_ptr(), _dt(xin), xin.shape[-1], 6, B, 1, hs, ws, tvals[0], st))
+                    else:
+                        for bi, tv in enumerate(tvals):
+                            chk(lib.rife_nhwc_fill(xin[bi].data_ptr(), _dt(xin), xin.shape[-1], 6, 1, 1, hs, ws, tv, st))
+                    if i > 0:
+                        resize(full, 6, 7, xin, 7)                                    # warped0, warped1, mask
+                        resize(full, 13, 4, xin, 14, mul=1.0 / s)
+                elif i == 0:
                     resize(full, 0, 6, xin, 0)                                        # :40 (identity when scale == 1)
                 else:
                     resize(full, 0, 13, xin, 0)                                       # cat(img0,img1,warped0,warped1,mask)
@@ -323,6 +347,8 @@ class IFNet(nn.Module):
                     chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, _dt(full),
                                             None, 0, 0, 0, mg.data_ptr(), io, B, H, W, st))
                     merged.append(mg)
+            if tp and returnflow:
+                return flow_list[2]                                                   # IFNet_m.py:104-105
             mask_sig = torch.empty((B, 1, H, W), dtype=out_dt, device=dev)
             chk(lib.rife_nhwc_to_nchw(full.data_ptr(), _dt(full), 24, 12, mask_sig.data_ptr(), io, B, 1, H, W, 1, st))
 
@@ -368,6 +394,11 @@ class IFNet(nn.Module):
         return flow_list, mask_sig, merged, None, None, 0
 
 
+class IFNet_m(IFNet):
+    """Drop-in for `model.IFNet_m.IFNet_m`: the arbitrary-timestep variant (benchmark/HD_multi_4X.py:16)."""
+    TIMESTEP_PLANE = 1
+
+
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
 
@@ -375,11 +406,9 @@ class Model:
     """Drop-in for `model.RIFE.Model` (inference side, model/RIFE.py:18-65)."""
 
     def __init__(self, local_rank=-1, arbitrary=False, precision="auto"):
-        if arbitrary:
-            raise NotImplementedError("IFNet_m (arbitrary-timestep ECCV variant) is out of scope (SURVEY 2.1 row 6)")
         if local_rank != -1:
             raise NotImplementedError("DDP training wrapper is out of scope: inference only")
-        self.flownet = IFNet(precision=precision)
+        self.flownet = IFNet_m(precision=precision) if arbitrary else IFNet(precision=precision)   # model/RIFE.py:20-23
         self.device()
 
     def train(self):

@@ -9,6 +9,26 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPU cores closest to GPU `device_index` (NVML's ideal affinity mask).  Call it
+    before allocating pinned frame buffers: with one process per GPU the host side of every PCIe copy then stays on
+    the GPU's own NUMA node.  Returns the number of cores bound, or 0 when NVML / affinity calls are unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def shard_range(n_items, rank, world_size):
     """Contiguous [lo, hi) range of `rank`: sizes differ by at most one, earlier ranks take the remainder."""
     if world_size < 1 or not (0 <= rank < world_size):

@@ -199,6 +199,9 @@ int rife_nhwc_warp(const void* src, int src_dtype, int spitch, int soff, const v
                    const float* gridx_dev, const float* gridy_dev, void* stream);
 int rife_nhwc_s2d(const void* src, int src_dtype, int spitch, int soff, int C, void* dst, int dst_dtype, int cpad,
                   int B, int H, int W, void* stream);
+/* dst[..., off : off + C] = value: the constant timestep plane of model/IFNet_m.py:64 */
+int rife_nhwc_fill(void* dst, int dst_dtype, int pitch, int off, int B, int C, int H, int W, float value,
+                   void* stream);
 /* merged = w0*sigmoid(mask) + w1*(1-sigmoid(mask)) (model/IFNet.py:98-99); with refine (pre-sigmoid Unet output):
  * clamp(merged + sigmoid(refine)*2 - 1, 0, 1) (model/IFNet.py:105-107).  w0 / w1 / mask share w_dtype.
  * out: NCHW (B,3,H,W) of io_dtype. */

@@ -133,18 +133,20 @@ def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet."):
 
 
 @torch.no_grad()
-def eccv_ifnet_forward(sd, x, scale=(4, 2, 1)):
-    """model/IFNet.py:63-108, inference branch."""
+def eccv_ifnet_forward(sd, x, scale=(4, 2, 1), timestep=None):
+    """model/IFNet.py:63-108, inference branch; with `timestep` (float or (B,1,1,1) tensor) the arbitrary-timestep
+    variant model/IFNet_m.py:63-112, whose blocks take a constant timestep plane after img1."""
     img0, img1 = x[:, :3], x[:, 3:6]
+    tp = () if timestep is None else ((x[:, :1].clone() * 0 + 1) * timestep,)       # IFNet_m.py:64
     flow_list, merged, mask_list = [], [], []
     w0, w1, flow, mask = img0, img1, None, None
     for i in range(3):
         p = f"block{i}."
         if flow is not None:
-            fd, md = eccv_ifblock(sd, p, torch.cat((img0, img1, w0, w1, mask), 1), flow, scale[i])
+            fd, md = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp + (w0, w1, mask), 1), flow, scale[i])
             flow, mask = flow + fd, mask + md
         else:
-            flow, mask = eccv_ifblock(sd, p, torch.cat((img0, img1), 1), None, scale[i])
+            flow, mask = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp, 1), None, scale[i])
         mask_list.append(torch.sigmoid(mask))
         flow_list.append(flow)
         w0, w1 = warp(img0, flow[:, :2]), warp(img1, flow[:, 2:4])
@@ -158,6 +160,6 @@ def eccv_ifnet_forward(sd, x, scale=(4, 2, 1)):
 
 
 @torch.no_grad()
-def eccv_model_inference(sd, img0, img1, scale=1.0, scale_list=(4, 2, 1)):
+def eccv_model_inference(sd, img0, img1, scale=1.0, scale_list=(4, 2, 1), timestep=None):
     sl = [s * 1.0 / scale for s in scale_list]
-    return eccv_ifnet_forward(sd, torch.cat((img0, img1), 1), sl)[2][2]
+    return eccv_ifnet_forward(sd, torch.cat((img0, img1), 1), sl, timestep)[2][2]

@@ -72,6 +72,27 @@ def psnr(a, b):
 _eccv = {}
 
 
+_eccv_m = {}
+
+
+def seeded_eccv_m(pkg, amp=AMP):
+    """Arbitrary-timestep ECCV model mirror (Model(arbitrary=True) = IFNet_m), seeded like tests/golden/make_golden.py:
+    case_eccv_m (sha256 in tests/golden/weights_eccv_m_seed1234.json)."""
+    import torch
+    if amp not in _eccv_m:
+        torch.manual_seed(1234)
+        m = pkg.eccv.Model(arbitrary=True)
+        m.eval()
+        m._sha_state = {k: v.detach().cpu().clone() for k, v in m.flownet.state_dict().items()}
+        if amp != 1.0:
+            with torch.no_grad():
+                for b in (m.flownet.block0, m.flownet.block1, m.flownet.block2):
+                    b.lastconv.weight.mul_(amp)
+            m.flownet.invalidate()
+        _eccv_m[amp] = m
+    return _eccv_m[amp]
+
+
 def seeded_eccv(pkg, amp=AMP):
     """ECCV-paper model mirror under torch.manual_seed(1234) (sha256 in tests/golden/weights_eccv_seed1234.json);
     `amp` scales block{0,1,2}.lastconv.weight as tests/golden/make_golden.py:case_eccv does."""

@@ -217,6 +217,34 @@ def case_eccv():
     save("eccv_cases", **arrs)
 
 
+def case_eccv_m():
+    """model/RIFE.py Model(arbitrary=True) = model/IFNet_m.py (benchmark/HD_multi_4X.py:16): timestep plane as an
+    extra block input."""
+    from model.RIFE import Model as EccvModel
+    torch.manual_seed(1234)
+    m = EccvModel(arbitrary=True)
+    m.eval()
+    sd = m.flownet.state_dict()
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().numpy().astype(np.float32).tobytes())
+    with open(os.path.join(OUT, "weights_eccv_m_seed1234.json"), "w") as f:
+        json.dump({"seed": 1234, "sha256": h.hexdigest(), "n_tensors": len(sd),
+                   "n_params": int(sum(v.numel() for v in sd.values()))}, f, indent=1)
+    for b in (m.flownet.block0, m.flownet.block1, m.flownet.block2):
+        b.lastconv.weight.mul_(AMP)
+    arrs = {}
+    img0, img1 = rand_frames(51, 2, 3, 64, 96, smooth=True)
+    arrs["img0"], arrs["img1"] = f32(img0), f32(img1)
+    for t in (0.25, 0.5, 0.8):
+        flow_list, mask, merged, _, _, _ = m.flownet(torch.cat((img0, img1), 1), [4, 2, 1], timestep=t)
+        arrs[f"flow2_t{t}"], arrs[f"mask_t{t}"], arrs[f"out_t{t}"] = f32(flow_list[2]), f32(mask), f32(merged[2])
+    arrs["out_scale05_t0.25"] = f32(m.inference(img0, img1, scale=0.5, scale_list=[4, 2, 1], timestep=0.25))
+    arrs["flow_only_t0.5"] = f32(m.flownet(torch.cat((img0, img1), 1), [4, 2, 1], timestep=0.5, returnflow=True))
+    save("eccv_m_cases", **arrs)
+
+
 def case_eccv_ref_fp16():
     """How far the reference's OWN half-precision mode (inference_video.py --fp16: default tensor type Half, so weights,
     frames and the warp grid of model/warplayer.py are all fp16) lands from its fp32 result on the eccv_cases inputs.
@@ -255,6 +283,10 @@ def case_eccv_ref_fp16():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "eccv_m":
+        with torch.no_grad():
+            case_eccv_m()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "eccv_fp16":
         with torch.no_grad():

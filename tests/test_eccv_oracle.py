@@ -6,7 +6,7 @@ import os
 import numpy as np
 import torch
 
-from conftest import AMP, GOLDEN, load_golden, seeded_eccv
+from conftest import AMP, GOLDEN, load_golden, seeded_eccv, seeded_eccv_m
 from oracle import rife_oracle as O
 from oracle import torch_ref as T
 
@@ -37,3 +37,25 @@ def test_eccv_oracles_against_golden(pkg):
         assert np.abs(np.asarray(mask) - g["a_mask"]).max() < 1e-4, name
     out = T.eccv_model_inference(sdt, torch.from_numpy(g["b_img0"]), torch.from_numpy(g["b_img1"]), 0.5).numpy()
     assert np.abs(out - g["b_out"]).max() < 1e-4
+
+
+def test_eccv_m_mirror_weights_and_oracle(pkg):
+    """model/IFNet_m.py (Model(arbitrary=True)): the mirror regenerates the reference's seeded weights and the torch
+    restatement reproduces the reference's outputs at several timesteps."""
+    man = json.load(open(os.path.join(GOLDEN, "weights_eccv_m_seed1234.json")))
+    m = seeded_eccv_m(pkg)
+    h = hashlib.sha256()
+    for k, v in m._sha_state.items():
+        h.update(k.encode())
+        h.update(v.numpy().astype(np.float32).tobytes())
+    assert h.hexdigest() == man["sha256"] and len(m._sha_state) == man["n_tensors"]
+    g = load_golden("eccv_m_cases")
+    sdt = {k: v.detach().cpu().float() for k, v in m.flownet.state_dict().items()}
+    x = torch.from_numpy(np.concatenate([g["img0"], g["img1"]], 1))
+    for t in (0.25, 0.5, 0.8):
+        flows, mask, merged = T.eccv_ifnet_forward(sdt, x, [4, 2, 1], timestep=t)
+        assert np.abs(flows[2].numpy() - g[f"flow2_t{t}"]).max() < 5e-4
+        assert np.abs(mask.numpy() - g[f"mask_t{t}"]).max() < 1e-4
+        assert np.abs(merged[2].numpy() - g[f"out_t{t}"]).max() < 1e-4
+    out = T.eccv_model_inference(sdt, torch.from_numpy(g["img0"]), torch.from_numpy(g["img1"]), 0.5, timestep=0.25).numpy()
+    assert np.abs(out - g["out_scale05_t0.25"]).max() < 1e-4

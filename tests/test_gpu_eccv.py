@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, seeded_eccv
+from conftest import load_golden, seeded_eccv, seeded_eccv_m
 from oracle import torch_ref as T
 
 pytestmark = pytest.mark.gpu
@@ -107,3 +107,26 @@ def test_eccv_fp16_explicit_precision_and_batch(pkg):
     assert _psnr(got.cpu().numpy(), ref.cpu().numpy()) > FP16_MIN_PSNR
     for i in range(2):
         assert torch.equal(got[i:i + 1], m16.inference(a[i:i + 1], b[i:i + 1]))
+
+
+def test_eccv_m_arbitrary_timestep(pkg):
+    """Model(arbitrary=True) = IFNet_m (benchmark/HD_multi_4X.py:16) against the reference's goldens: fp32 <= 1e-4,
+    fp16 inside the reduced-precision bar; tensor timesteps; returnflow."""
+    g = load_golden("eccv_m_cases")
+    m = seeded_eccv_m(pkg)
+    a, b = cu(g["img0"]), cu(g["img1"])
+    x = torch.cat((a, b), 1)
+    for t in (0.25, 0.5, 0.8):
+        flows, mask, merged, *_ = m.flownet(x, [4, 2, 1], timestep=t)
+        assert np.abs(flows[2].cpu().numpy() - g[f"flow2_t{t}"]).max() < 1e-3
+        assert np.abs(mask.cpu().numpy() - g[f"mask_t{t}"]).max() < 1e-4
+        assert np.abs(merged[2].cpu().numpy() - g[f"out_t{t}"]).max() < 1e-4
+        o16 = m.inference(a.half(), b.half(), scale_list=[4, 2, 1], timestep=t).float().cpu().numpy()
+        assert np.abs(o16 - g[f"out_t{t}"]).max() < FP16_MAX_ABS and _psnr(o16, g[f"out_t{t}"]) > FP16_MIN_PSNR
+    out = m.inference(a, b, scale=0.5, scale_list=[4, 2, 1], timestep=0.25).cpu().numpy()
+    assert np.abs(out - g["out_scale05_t0.25"]).max() < 1e-4
+    fl = m.flownet(x, [4, 2, 1], timestep=0.5, returnflow=True)
+    assert np.abs(fl.cpu().numpy() - g["flow_only_t0.5"]).max() < 1e-3
+    tt = torch.tensor([0.25, 0.8], device=DEV).reshape(2, 1, 1, 1)                     # per-sample timesteps
+    mixed = m.inference(a, b, scale_list=[4, 2, 1], timestep=tt).cpu().numpy()
+    assert np.abs(mixed[0] - g["out_t0.25"][0]).max() < 1e-4 and np.abs(mixed[1] - g["out_t0.8"][1]).max() < 1e-4
