@@ -11,5 +11,7 @@ from .model import Model
 from .warplayer import warp
 from .sharding import shard_range, run_sharded
 from . import eccv
+from . import scene
+from .scene import scene_ssim
 
 __all__ = ["Model", "IFNet", "IFBlock", "Head", "ResConv", "warp", "RifeError", "shard_range", "run_sharded"]

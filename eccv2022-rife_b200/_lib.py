@@ -18,7 +18,7 @@ SYMBOLS = [
     "rife_plan_set_profiling",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_inference_host_pipelined", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
-    "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
+    "rife_scene_ssim", "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
     "rife_nhwc_resize", "rife_nhwc_warp", "rife_nhwc_s2d", "rife_nhwc_fill", "rife_eccv_merge",
 ]
 
@@ -78,6 +78,7 @@ def load():
     lib.rife_nhwc_resize.argtypes = [vp, i, i, i, vp, i, i, i, i, i, i, i, i, i, f, i, vp]
     lib.rife_nhwc_warp.argtypes = [vp, i, i, i, vp, i, i, i, vp, i, i, i, i, i, i, i, vp, vp, vp]
     lib.rife_nhwc_s2d.argtypes = [vp, i, i, i, i, vp, i, i, i, i, i, vp]
+    lib.rife_scene_ssim.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp]
     lib.rife_nhwc_fill.argtypes = [vp, i, i, i, i, i, i, i, f, vp]
     lib.rife_eccv_merge.argtypes = [vp, i, i, vp, i, i, vp, i, i, i, vp, i, i, i, vp, i, i, i, i, vp]
     for name in SYMBOLS:

@@ -890,6 +890,15 @@ int rife_nhwc_s2d(const void* src, int src_dtype, int spitch, int soff, int C, v
   if (H % 2 || W % 2 || cpad < C) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_s2d: even H, W and cpad >= C required");
   return launch_s2d_nhwc(src, src_dtype, spitch, soff, C, dst, dst_dtype, cpad, B, H, W, (cudaStream_t)stream);
 }
+int rife_scene_ssim(const void* img0, const void* img1, int io_dtype, int B, int C, int h, int w, int pad_multiple,
+                    float* ssim_out, void* stream) {
+  if (!img0 || !img1 || !ssim_out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_scene_ssim: null argument");
+  if (B < 1 || C < 3 || h < 1 || w < 1 || pad_multiple < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_scene_ssim: need B >= 1, C >= 3, h, w, pad_multiple >= 1");
+  if (!is_device_ptr(img0) || !is_device_ptr(img1) || !is_device_ptr(ssim_out))
+    RIFE_FAIL(RIFE_ERR_NOT_DEVICE_PTR, "rife_scene_ssim: device memory required (no CPU fallback)");
+  const int Hp = round_up(h, pad_multiple), Wp = round_up(w, pad_multiple);
+  return launch_scene_ssim(img0, img1, io_dtype, B, C, h, w, Hp, Wp, ssim_out, (cudaStream_t)stream);
+}
 int rife_nhwc_fill(void* dst, int dst_dtype, int pitch, int off, int B, int C, int H, int W, float value, void* stream) {
   if (!dst) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_nhwc_fill: null argument");
   if (B < 1 || C < 1 || H < 1 || W < 1 || off < 0 || off + C > pitch) RIFE_FAIL(RIFE_ERR_SHAPE, "rife_nhwc_fill: bad slice");

@@ -261,6 +261,9 @@ int launch_warp_nhwc(const void* src, int sdt, int spitch, int soff, const void*
                      const float* gridy, cudaStream_t st);
 int launch_s2d_nhwc(const void* src, int sdt, int spitch, int soff, int C, void* dst, int ddt, int cpad, int B, int H,
                     int W, cudaStream_t st);
+// scene_ssim.cu: ssim_matlab of the 32x32 thumbnails of B frame pairs -> out[B] (device)
+int launch_scene_ssim(const void* img0, const void* img1, int io_dtype, int B, int C, int h, int w, int Hp, int Wp,
+                      float* out, cudaStream_t st);
 int launch_fill_nhwc(void* dst, int ddt, int dpitch, int doff, int B, int C, int H, int W, float value, cudaStream_t st);
 int launch_eccv_merge(const void* w0, int p0, int o0, const void* w1, int p1, int o1, const void* mask, int pm, int om,
                       int wdt, const void* refine, int rdt, int pr, int orf, void* out, int io_dtype, int B, int H, int W,

@@ -163,6 +163,14 @@ int rife_conv_transpose4x4s2(const float* x, const float* w, const float* bias, 
                              int Cin, int H, int W, int Cout, int pixel_shuffle, int precision,
                              void* stream);
 
+/* ---- scene-change / static-frame detector of the video loop (inference_video.py:226-228,242-243) ----
+ * ssim_out[b] = ssim_matlab(F.interpolate(pad(img0[b]), (32,32), bilinear)[:3], same of img1[b])
+ * (model/pytorch_msssim/__init__.py:81-134) in one launch.  Frames: (B,C,h,w) NCHW float32/float16 in [0,1] or
+ * (B,h,w,C) uint8; they are taken as zero-padded on the right / bottom to multiples of `pad_multiple` first, as
+ * inference_video.py:199-203 pads them (max(32, 32/scale)); pad_multiple = 1 means no padding.  ssim_out: device. */
+int rife_scene_ssim(const void* img0, const void* img1, int io_dtype, int B, int C, int h, int w,
+                    int pad_multiple, float* ssim_out, void* stream);
+
 /* ---- generic NHWC layer / operator API: the ECCV-paper network (model/IFNet.py, model/refine.py, -------------
  *      model/RIFE.py:56-65; BASELINE config 5).  NHWC tensors [B][H][W][pitch]; an operator touches the
  *      channel slice [off, off + C) so that torch.cat (model/IFNet.py:75-79, model/refine.py:73-80) is free. */

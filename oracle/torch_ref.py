@@ -9,6 +9,8 @@ lives at /root/reference only in the build container and cannot travel to the GP
 use as the fp32 reference at sizes where the numpy oracle (oracle/rife_oracle.py) would take too long.  It is
 pinned against the same golden fixtures (tests/test_oracle_golden.py).  Never imported by the product.
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -163,3 +165,32 @@ def eccv_ifnet_forward(sd, x, scale=(4, 2, 1), timestep=None):
 def eccv_model_inference(sd, img0, img1, scale=1.0, scale_list=(4, 2, 1), timestep=None):
     sl = [s * 1.0 / scale for s in scale_list]
     return eccv_ifnet_forward(sd, torch.cat((img0, img1), 1), sl, timestep)[2][2]
+
+
+# ----------------------------------------------------------------------------- scene-change detector (video loop)
+def ssim_matlab(img1, img2):
+    """model/pytorch_msssim/__init__.py:81-134 for frames in [0, 1] (L = 1): colour images as 3-D volumes, 11^3 Gaussian
+    window (sigma 1.5), replicate padding, mean of the SSIM map."""
+    g = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    g = (g / g.sum()).unsqueeze(1)
+    w2 = g.mm(g.t())
+    win = (w2.unsqueeze(2) @ g.t()).expand(1, 1, 11, 11, 11).contiguous()
+    a, b = img1.unsqueeze(1), img2.unsqueeze(1)
+    f = lambda v: F.conv3d(F.pad(v, (5, 5, 5, 5, 5, 5), mode="replicate"), win)
+    mu1, mu2 = f(a), f(b)
+    s1, s2, s12 = f(a * a) - mu1 * mu1, f(b * b) - mu2 * mu2, f(a * b) - mu1 * mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    v1, v2 = 2.0 * s12 + c2, s1 + s2 + c2
+    return (((2 * mu1 * mu2 + c1) * v1) / ((mu1 * mu1 + mu2 * mu2 + c1) * v2)).mean()
+
+
+@torch.no_grad()
+def scene_ssim(i0, i1, pad_multiple=32):
+    """inference_video.py:199-203,226-228: zero-pad to the multiple, bilinear-resize to 32x32, ssim_matlab of the first
+    three channels.  i0 / i1: (1, C, h, w) float frames."""
+    h, w = i0.shape[2:]
+    ph, pw = (h + pad_multiple - 1) // pad_multiple * pad_multiple, (w + pad_multiple - 1) // pad_multiple * pad_multiple
+    p0, p1 = F.pad(i0, (0, pw - w, 0, ph - h)), F.pad(i1, (0, pw - w, 0, ph - h))
+    s0 = F.interpolate(p0, (32, 32), mode="bilinear", align_corners=False)
+    s1 = F.interpolate(p1, (32, 32), mode="bilinear", align_corners=False)
+    return float(ssim_matlab(s0[:, :3], s1[:, :3]))

@@ -30,6 +30,7 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 
 import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
 
 torch.set_grad_enabled(False)
 torch.set_num_threads(os.cpu_count() or 1)
@@ -245,6 +246,32 @@ def case_eccv_m():
     save("eccv_m_cases", **arrs)
 
 
+def case_scene_ssim():
+    """The video loop's scene-change statistic (inference_video.py:199-203,226-228): pad to 32, F.interpolate to
+    32x32, model/pytorch_msssim ssim_matlab -- on uint8 frames of a few kinds, recorded from the reference's code."""
+    from model.pytorch_msssim import ssim_matlab
+    rng = np.random.default_rng(77)
+    h, w = 135, 250                                           # not multiples of 32: exercises the padding
+    base = F.interpolate(torch.from_numpy(rng.random((1, 3, 12, 20), dtype=np.float32)), (h + 20, w + 20), mode="bicubic",
+                         align_corners=False).clamp(0, 1)
+    fr = lambda dy, dx: (base[0, :, 10 + dy:10 + dy + h, 10 + dx:10 + dx + w] * 255).byte().permute(1, 2, 0).contiguous().numpy()
+    noise = lambda: rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    pairs = [(fr(0, 0), fr(0, 0)), (fr(0, 0), fr(0, 1)), (fr(0, 0), fr(3, -5)), (fr(0, 0), fr(10, 10)), (fr(0, 0), noise()),
+             (noise(), noise()), (np.zeros((h, w, 3), np.uint8), fr(0, 0))]
+    vals = []
+    for a, b in pairs:
+        ta = torch.from_numpy(a.transpose(2, 0, 1)).unsqueeze(0).float() / 255.
+        tb = torch.from_numpy(b.transpose(2, 0, 1)).unsqueeze(0).float() / 255.
+        ph, pw = ((h - 1) // 32 + 1) * 32, ((w - 1) // 32 + 1) * 32
+        ta, tb = F.pad(ta, (0, pw - w, 0, ph - h)), F.pad(tb, (0, pw - w, 0, ph - h))          # inference_video.py:199-203
+        sa = F.interpolate(ta, (32, 32), mode="bilinear", align_corners=False)
+        sb = F.interpolate(tb, (32, 32), mode="bilinear", align_corners=False)
+        vals.append(float(ssim_matlab(sa[:, :3], sb[:, :3])))
+    print("scene ssim", vals)
+    save("scene_ssim_cases", img0=np.stack([p[0] for p in pairs]), img1=np.stack([p[1] for p in pairs]),
+         ssim=np.asarray(vals, np.float64))
+
+
 def case_eccv_ref_fp16():
     """How far the reference's OWN half-precision mode (inference_video.py --fp16: default tensor type Half, so weights,
     frames and the warp grid of model/warplayer.py are all fp16) lands from its fp32 result on the eccv_cases inputs.
@@ -283,6 +310,9 @@ def case_eccv_ref_fp16():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "scene":
+        case_scene_ssim()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "eccv_m":
         with torch.no_grad():

@@ -26,6 +26,7 @@ def test_header_symbols_exported(pkg):
 
 def test_error_paths_without_gpu(pkg):
     lib = pkg._lib.load()
+    launches = lib.rife_launch_count()
     # shape validation is pure host logic: H, W must be multiples of 64/scale
     assert lib.rife_plan_workspace_bytes(1, 3, 736, 1280, 1.0, 0) == 0
     assert b"multiples of 64" in lib.rife_last_error()
@@ -38,4 +39,6 @@ def test_error_paths_without_gpu(pkg):
     # null arguments are rejected before any CUDA call
     assert lib.rife_weights_create(None, 0, None, None, None, 0) == -1
     assert lib.rife_plan_set_profiling(None, 1) == -1
-    assert lib.rife_launch_count() == 0
+    assert lib.rife_plan_workspace_bytes_ex(3, 3, 1, 3, 64, 64, 1.0, 1) > lib.rife_plan_workspace_bytes(3, 3, 64, 64, 1.0, 1)
+    assert lib.rife_scene_ssim(None, None, 0, 1, 3, 8, 8, 32, None, None) == -1
+    assert lib.rife_launch_count() == launches                                   # none of the above launched anything
