@@ -19,6 +19,15 @@
 #else
 #define RIFE_PIX_TRIGGER() pdl_trigger()
 #endif
+// resident blocks per SM the block-input gather is compiled for (register cap): measured best on B200 at 1080p --
+// s = 1 (block 4): 9 blocks (56 regs), s >= 2: 6 blocks (80 regs); 104 / 61 regs without the cap cost 2-4 % of a step
+#ifndef RIFE_BI_MINB1
+#define RIFE_BI_MINB1 9
+#define RIFE_BI_MINB2 6
+#endif
+#ifndef RIFE_PREP_MINB
+#define RIFE_PREP_MINB 3
+#endif
 namespace rife {
 
 namespace {
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 // fp16 fused-mode input packing: NCHW frames -> planar-8 s2d Head input [2B][2][H/2][W/2][8] only (SRC is assembled
 // by Head.cnn3's epilogue).  One thread converts a 2 x 8 pixel strip: 16-byte loads per channel row, 16-byte stores.
 template <typename Tio>
-__global__ void __launch_bounds__(256) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
+__global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                           __half* __restrict__ head_in, int nf0, int C, int H, int W) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
@@ -422,7 +431,7 @@ __device__ __forceinline__ void warp8_h2(const __half* __restrict__ src, int H, 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(128) block_input_h_kernel(LevelsArg L, int level, int s,
+__global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) block_input_h_kernel(LevelsArg L, int level, int s,
                                                             const __half* __restrict__ src0,
                                                             const __half* __restrict__ src1,
                                                             const float* __restrict__ gridx,
