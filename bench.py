@@ -362,7 +362,8 @@ def main():
     traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
     tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(tp) and args.precision == "fp16":
-        traffic = json.load(open(tp)).get("traffic_bytes_per_launch") * P / 4.0   # captured at P = 4; bytes scale with P
+        tj = json.load(open(tp))
+        traffic = tj.get("traffic_bytes_per_launch") * P / float(tj.get("pairs", 4))   # bytes scale with the pairs per launch
     roofline = {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[rk], "kernel_ms": k_ms,
