@@ -261,9 +261,10 @@ int rife_weights_destroy(rife_weights* w) {
 // --------------------------------------------------------------------------------------------------
 // plan
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, stage_in0, stage_in1,
       stage_out, total;
-  int s[5];
+  int s[5];   // block i works at H / s[i] * u[i]: scale_list[i] = s[i] / u[i] (one of the two is 1)
+  int u[5];
 };
 
 // P frame pairs, T timesteps per pair (outputs B = P*T, pair-major), `seq`: the pairs are the P consecutive pairs of
@@ -272,13 +273,18 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   if (P < 1 || T < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: pairs, timesteps, H, W must be positive");
   const int B = P * T, F = seq ? P + 1 : 2 * P;
   if (C != 3 && C != 4) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: C must be 3 or 4 (IFNet_HDv3.py:121-123 splits an RGB/RGBA pair)");
-  if (!(scale == 1.f || scale == 0.5f || scale == 0.25f))
-    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be 1, 0.5 or 0.25 (scale > 1 up-samples the block input; not built)");
+  if (!(scale == 1.f || scale == 0.5f || scale == 0.25f || scale == 2.f || scale == 4.f))
+    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be one of 0.25, 0.5, 1, 2, 4 (inference_video.py:92)");
   if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16) RIFE_FAIL(RIFE_ERR_DTYPE, "plan: bad precision");
-  const int inv = (int)lroundf(1.f / scale);
   const int base[5] = {16, 8, 4, 2, 1};
-  for (int i = 0; i < 5; ++i) L->s[i] = base[i] * inv;  // scale_list, RIFE_HDv3.py:58
-  const int mult = 64 * inv;
+  bool any_up = false;
+  for (int i = 0; i < 5; ++i) {  // scale_list = [16, 8, 4, 2, 1] / scale, RIFE_HDv3.py:58
+    const float sl = (float)base[i] / scale;
+    L->s[i] = sl >= 1.f ? (int)lroundf(sl) : 1;
+    L->u[i] = sl >= 1.f ? 1 : (int)lroundf(1.f / sl);   // scale > 1: the last block(s) work above full resolution
+    any_up = any_up || L->u[i] > 1;
+  }
+  const int mult = (int)lroundf(64.f / scale);
   if (H % mult || W % mult)
     RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale = " + std::to_string(mult) + " (got " +
                                   std::to_string(H) + "x" + std::to_string(W) + ")");
@@ -296,17 +302,18 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   L->head_b = take((NF / 4) * 16 * E);
   size_t xin = 0, c0 = 0, act = 0;
   for (int i = 0; i < 5; ++i) {
-    const size_t n = N / ((size_t)L->s[i] * L->s[i]);
+    const size_t n = N / ((size_t)L->s[i] * L->s[i]) * L->u[i] * L->u[i];
     const size_t c = kBlockC[i];
     xin = xin > n * XIN_C ? xin : n * XIN_C;
     c0 = c0 > (n / 4) * (c / 2) ? c0 : (n / 4) * (c / 2);
     act = act > (n / 16) * c ? act : (n / 16) * c;
   }
   L->xin = take(xin * E);
+  L->xfull = take(any_up ? N * XIN_C * E : 0);   // full-resolution block input before its up-sampling (scale > 1 only)
   L->c0 = take(c0 * E);
   L->act_a = take(act * E);
   L->act_b = take(act * E);
-  for (int i = 0; i < 5; ++i) L->tmp[i] = take(N / ((size_t)L->s[i] * L->s[i]) * TMP_C * E);
+  for (int i = 0; i < 5; ++i) L->tmp[i] = take(N / ((size_t)L->s[i] * L->s[i]) * L->u[i] * L->u[i] * TMP_C * E);
   L->fbuf = take(N * 4 * 4);  // full-resolution fp32 flow carried between the last stages
   L->gridx = take((size_t)W * 4);
   L->gridy = take((size_t)H * 4);
@@ -503,6 +510,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.src1 = (char*)p->at(L.src) + (size_t)(p->seq ? 1 : p->P) * H * W * SRC_C * E;
   c.half_act = half_act;
   c.planar_head = half_act && w->head_hk;
+  for (int i = 0; i < 5; ++i) c.any_up = c.any_up || L.u[i] > 1;
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
   p->n_stage = 0;
@@ -526,13 +534,19 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   float* fbuf = (float*)p->at(L.fbuf);
   int fbuf_levels = 0;  // number of levels summed in fbuf (0 = nothing stored yet)
   for (int i = 0; i < 5; ++i) {
-    const int s = L.s[i], c_ = kBlockC[i];
-    const int hs = H / s, wsz = W / s;
+    const int s = L.s[i], up = L.u[i], c_ = kBlockC[i];
+    const int hs = H / s * up, wsz = W / s * up;
     const std::string bn = "b" + std::to_string(i);
     const int hkm = half_act ? w->blk_hk[i] : 0;
     const bool hk = hkm == 1;            // conv0.* on the halo kernel (planar-8 block input)
     const bool hk_tail = hkm != 0;       // ResConv x8 + lastconv on the halo kernel
-    RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
+    if (up > 1) {
+      // scale_list[i] < 1: the block input is the full-resolution one, bilinearly up-sampled (IFNet_HDv3.py:79-81)
+      RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, 1, p->at(L.xfull), false, fbuf, fbuf_levels, i > 0, st));
+      RIFE_STAGE(bn + ".upsample", launch_upsample_xin(c, p->at(L.xfull), p->at(L.xin), up, hk, st));
+    } else {
+      RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
+    }
     if (i > 0 && s <= 2) fbuf_levels = i;  // every full-resolution pixel was sampled: fbuf = flow after blocks [0, i)
     ConvIO io;
     io.B = B;
@@ -554,7 +568,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
     io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
     RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk_tail, st));
-    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = s;
+    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = up > 1 ? -up : s;
 
     EvalOut eo;
     eo.flow = outs->flow[i];

@@ -187,7 +187,8 @@ int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);
 struct TmpLevel {
   const void* ptr;  // [B][h][w][TMP_C]
   int h, w;
-  int s;            // up-sampling factor to full resolution (power of two >= 1)
+  int s;            // up-sampling factor to full resolution (power of two >= 1); negative: the level is stored at
+                    // -s times the full resolution (scale > 1) and is DOWN-sampled by -s (centre 2x2 mean)
 };
 
 // Frame tensors at the API boundary.  RIFE_F32 / RIFE_F16: NCHW (B,C,h,w); RIFE_U8: HWC (B,h,w,C) as video decoders
@@ -209,6 +210,7 @@ struct PixelCtx {
   int B, C, H, W;      // B = outputs (virtual pairs) = frame pairs x timesteps per pair
   int F = 0, nf0 = 0;  // SRC frames in total / of them taken from img0 (the rest from img1)
   int src_div = 1;     // output b warps SRC frames b / src_div of src0 and src1
+  bool any_up = false; // scale > 1: some block works above full resolution -> generic (non-fast) pixel kernels only
   int h = 0, w = 0;    // frame size seen by the caller (0 = H, W)
   const float* gridx;  // device, W entries (model/warplayer.py:11)
   const float* gridy;  // device, H entries (model/warplayer.py:13)
@@ -227,6 +229,9 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
 // (re)written with the sum over [0, level) when `fbuf_store` (only valid when every pixel is sampled: s <= 2)
 int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int s, void* xin, bool planar,
                        float* fbuf, int fbuf_levels, bool fbuf_store, cudaStream_t st);
+// scale > 1: F.interpolate(x, scale_factor=up) of the full-resolution block input `xfull` (s2d pixel-major, as
+// launch_block_input(s = 1, planar = false) wrote it) into the s2d block input `xin` at (up*H, up*W); flow channels * up
+int launch_upsample_xin(const PixelCtx& c, const void* xfull, void* xin, int up, bool planar, cudaStream_t st);
 // evaluates flow / mask / warped images / merged at full resolution after `nlev` blocks
 struct EvalOut {
   void* flow = nullptr;     // (B,4,H,W)

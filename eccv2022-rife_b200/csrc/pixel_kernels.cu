@@ -61,6 +61,33 @@ template <typename Tt, int N>
 __device__ __forceinline__ void sample_tmp(const Tt* __restrict__ base, int h, int w, int s, float rs, int c0, int y,
                                            int x, float (&out)[N]) {
   static_assert(N == 4 || N == 16, "N");
+  if (s < 0) {
+    // level stored at u = -s times the full resolution: F.interpolate(tmp, scale_factor=1/u) (IFNet_HDv3.py:86 with
+    // scale < 1) reads the centre 2x2 of each u x u cell with all lambdas = 0.5
+    const int u = -s, o = u / 2 - 1;
+    const Tt* p00 = base + ((y * u + o) * w + (x * u + o)) * TMP_C + c0;
+    float v[4][N];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const Tt* p = p00 + ((k >> 1) * w + (k & 1)) * TMP_C;
+      if constexpr (N == 4) {
+        ld4(p, v[k]);
+      } else {
+        float a[8];
+        ld8(p, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[k][i] = a[i];
+        ld8(p + 8, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[k][8 + i] = a[i];
+      }
+    }
+    // ATen: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), all weights 0.5
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+      out[c] = 0.5f * (0.5f * v[0][c] + 0.5f * v[1][c]) + 0.5f * (0.5f * v[2][c] + 0.5f * v[3][c]);
+    return;
+  }
   if (s == 1) {
     const Tt* p = base + (y * w + x) * TMP_C + c0;
     if constexpr (N == 4) {
@@ -750,6 +777,51 @@ inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
 
+// scale > 1 (block scale s < 1): xin = F.interpolate(x, scale_factor=up) of the full-resolution 32-channel block input
+// (IFNet_HDv3.py:79-81: flow channels additionally * 1/scale = up).  `xfull` is s2d pixel-major [B][H/2][W/2][4][32].
+template <typename T>
+__global__ void __launch_bounds__(128) upsample_xin_kernel(const T* __restrict__ xfull, T* __restrict__ xin, int B, int H,
+                                                           int W, int up, int planar) {
+  pdl_wait();
+  const int Hu = H * up, Wu = W * up;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Wu) return;
+  const float ratio = 1.f / (float)up;
+  const Lerp ly = make_lerp(Y, H, ratio), lx = make_lerp(X, W, ratio);
+  auto px = [&](int y, int x) -> const T* {
+    return xfull + ((((size_t)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * XIN_C;
+  };
+  const T *p00 = px(ly.i0, lx.i0), *p01 = px(ly.i0, lx.i1), *p10 = px(ly.i1, lx.i0), *p11 = px(ly.i1, lx.i1);
+  const int par = (Y & 1) * 2 + (X & 1);
+  const size_t hw2 = (size_t)(Hu >> 1) * (Wu >> 1), pix2 = (size_t)(Y >> 1) * (Wu >> 1) + (X >> 1);
+  T* dst = planar ? xin + (((size_t)b * 16 + par * 4) * hw2 + pix2) * 8 : xin + (((size_t)b * hw2 + pix2) * 4 + par) * XIN_C;
+  const size_t gstride = planar ? hw2 * 8 : 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    ld8(p00 + 8 * k, v00); ld8(p01 + 8 * k, v01); ld8(p10 + 8 * k, v10); ld8(p11 + 8 * k, v11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = ly.l0 * (lx.l0 * v00[i] + lx.l1 * v01[i]) + ly.l1 * (lx.l0 * v10[i] + lx.l1 * v11[i]);
+      if (k == 3 && i < 4) o[i] = o[i] * (float)up;      // flow: interpolate(flow, 1/s) * 1/s
+    }
+    st8(dst + k * gstride, o);
+  }
+}
+
+int launch_upsample_xin(const PixelCtx& c, const void* xfull, void* xin, int up, bool planar, cudaStream_t st) {
+  const dim3 grid(nblk((size_t)c.W * up, 128), (unsigned)(c.H * up), (unsigned)c.B);
+  if (c.half_act)
+    RIFE_CUDA_TRY(launch_pdl(upsample_xin_kernel<__half>, grid, dim3(128), 0, st, (const __half*)xfull, (__half*)xin, c.B, c.H,
+                             c.W, up, planar ? 1 : 0));
+  else
+    RIFE_CUDA_TRY(launch_pdl(upsample_xin_kernel<float>, grid, dim3(128), 0, st, (const float*)xfull, (float*)xin, c.B, c.H, c.W,
+                             up, planar ? 1 : 0));
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
 int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dtype, void* src_all, void* head_in,
                 cudaStream_t st) {
   const int fh = c.h ? c.h : c.H, fw = c.w ? c.w : c.W;
@@ -791,7 +863,7 @@ static LevelsArg pack_levels(const TmpLevel* levels, int n) {
     L.w[i] = levels[i].w;
     L.s[i] = levels[i].s;
     L.rs[i] = 1.f / (float)levels[i].s;
-    L.sc[i] = (float)levels[i].s;
+    L.sc[i] = levels[i].s > 0 ? (float)levels[i].s : 1.f / (float)(-levels[i].s);   // "* scale" of IFNet_HDv3.py:87
   }
   return L;
 }
@@ -808,7 +880,7 @@ int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int
                            fbuf, fbuf_levels, fbuf_store ? 1 : 0))
   const bool l0 = level == 0, s1 = s == 1;
   static const bool no_fast = getenv("RIFE_NO_FAST_INPUT") != nullptr;
-  if (c.half_act && !l0 && !no_fast) {
+  if (c.half_act && !l0 && !no_fast && !c.any_up) {
 #define RIFE_BIH(NS_)                                                                                                 \
   RIFE_CUDA_TRY(launch_pdl(block_input_h_kernel<NS_>, grid, dim3(128), 0, st, L, level, s, (const __half*)c.src0,    \
                            (const __half*)c.src1, c.gridx, c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g,          \
@@ -838,7 +910,7 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   if (io_dtype == RIFE_U8 && (o.flow || o.mask)) RIFE_FAIL(RIFE_ERR_DTYPE, "launch_eval: flow / mask outputs need a float io dtype");
   const dim3 egrid(nblk((size_t)fw, 256), (unsigned)fh, (unsigned)c.B);
   static const bool no_fast_merge = getenv("RIFE_NO_FAST_MERGE") != nullptr;
-  if (c.half_act && !no_fast_merge && o.merged && !o.flow && !o.mask && !o.warped0 && !o.warped1 && nlev >= 2 &&
+  if (c.half_act && !c.any_up && !no_fast_merge && o.merged && !o.flow && !o.mask && !o.warped0 && !o.warped1 && nlev >= 2 &&
       fbuf_levels == nlev - 1 && levels[nlev - 1].s == 1) {
     const __half* tmp = (const __half*)levels[nlev - 1].ptr;
 #define RIFE_MERGE(TIO)                                                                                              \

@@ -177,10 +177,10 @@ class IFNet(nn.Module):
             raise ValueError("IFNet.forward indexes scale_list[0..4] (IFNet_HDv3.py:139-148): pass 5 entries")
         s4 = float(scale_list[4])
         want = [16 * s4, 8 * s4, 4 * s4, 2 * s4, s4]
-        if [float(s) for s in scale_list[:5]] != want or s4 not in (1.0, 2.0, 4.0):
+        if [float(s) for s in scale_list[:5]] != want or s4 not in (0.25, 0.5, 1.0, 2.0, 4.0):
             raise NotImplementedError(
                 f"eccv2022-rife_b200 builds the scale_list=[16,8,4,2,1]/scale pyramid of RIFE_HDv3.py:58 with scale in "
-                f"{{1, 0.5, 0.25}}; got {list(scale_list)}")
+                f"{{0.25, 0.5, 1, 2, 4}} (inference_video.py:92); got {list(scale_list)}")
         return 1.0 / s4
 
     @staticmethod

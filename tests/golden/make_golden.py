@@ -149,6 +149,21 @@ def case_inference_variants():
     save("inference_variants", **arrs)
 
 
+def case_scale_up():
+    """--scale 2 / 4 (inference_video.py:92): scale_list = [8,4,2,1,0.5] / [4,2,1,0.5,0.25] -- the last block(s) up-sample
+    their input and work above full resolution (IFNet_HDv3.py:79-81,86-87 with scale < 1)."""
+    arrs = {}
+    img0, img1 = rand_frames(61, 2, 3, 64, 96, smooth=True)                 # multiples of 64/2 = 32
+    arrs["s2_img0"], arrs["s2_img1"] = f32(img0), f32(img1)
+    arrs["s2_out"] = f32(build_model(1234, AMP).inference(img0, img1, 0.5, 2.0))
+    fl, mk, mg = build_model(1234, AMP).flownet(torch.cat((img0, img1), 1), 0.3, [8, 4, 2, 1, 0.5])
+    arrs["s2_flow4"], arrs["s2_flow3"], arrs["s2_mask"], arrs["s2_merged_t03"] = f32(fl[4]), f32(fl[3]), f32(mk), f32(mg[4])
+    img0, img1 = rand_frames(62, 1, 3, 48, 80)                              # multiples of 64/4 = 16, white noise
+    arrs["s4_img0"], arrs["s4_img1"] = f32(img0), f32(img1)
+    arrs["s4_out"] = f32(build_model(1234, AMP).inference(img0, img1, 0.5, 4.0))
+    save("scale_up_cases", **arrs)
+
+
 def case_warp():
     """model/warplayer.py:8-22 on random data, small and large flows, C=3 and C=4."""
     arrs = {}
@@ -311,6 +326,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "scale_up":
+        case_scale_up()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "scene":
         case_scene_ssim()
         sys.exit(0)
@@ -326,6 +344,7 @@ if __name__ == "__main__":
     case_demo()
     case_full_structure()
     case_inference_variants()
+    case_scale_up()
     case_warp()
     case_ops()
     case_eccv()

@@ -32,7 +32,8 @@ def test_error_paths_without_gpu(pkg):
     assert b"multiples of 64" in lib.rife_last_error()
     assert lib.rife_plan_workspace_bytes(1, 3, 1088, 1920, 0.5, 0) == 0          # needs multiples of 128
     assert lib.rife_plan_workspace_bytes(1, 5, 64, 64, 1.0, 0) == 0              # C must be 3 or 4
-    assert lib.rife_plan_workspace_bytes(1, 3, 64, 64, 2.0, 0) == 0              # scale > 1 not built
+    assert lib.rife_plan_workspace_bytes(1, 3, 64, 64, 3.0, 0) == 0              # scale must be 0.25 / 0.5 / 1 / 2 / 4
+    assert lib.rife_plan_workspace_bytes(1, 3, 32, 96, 2.0, 0) > 0               # scale 2: multiples of 32 suffice
     n32 = lib.rife_plan_workspace_bytes(2, 3, 768, 1280, 1.0, 0)
     n16 = lib.rife_plan_workspace_bytes(2, 3, 768, 1280, 1.0, 1)
     assert n32 > n16 > 0

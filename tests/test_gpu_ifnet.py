@@ -115,7 +115,28 @@ def test_shape_and_device_errors(pkg):
     with pytest.raises(RuntimeError, match="multiples of 64/scale = 128"):
         m.inference(torch.zeros(1, 3, 64, 64, device=DEV), torch.zeros(1, 3, 64, 64, device=DEV), 0.5, 0.5)
     with pytest.raises(NotImplementedError):
-        m.flownet(torch.zeros(1, 6, 64, 64, device=DEV), 0.5, [8, 4, 2, 1, 0.5])
+        m.flownet(torch.zeros(1, 6, 64, 64, device=DEV), 0.5, [48, 24, 12, 6, 3])
+
+
+def test_scale_above_one(pkg):
+    """--scale 2 / 4 (inference_video.py:92): scale_list = [8,4,2,1,0.5] / [4,2,1,0.5,0.25]; the blocks whose scale is < 1
+    up-sample their input and work above full resolution.  fp32 <= 1e-4; fp16 inside the reduced-precision bar."""
+    g = load_golden("scale_up_cases")
+    m32, m16 = seeded_model(pkg, AMP, "fp32"), seeded_model(pkg, AMP, "fp16")
+    for tag, scale in (("s2", 2.0), ("s4", 4.0)):
+        a, b = torch.from_numpy(g[tag + "_img0"]).to(DEV), torch.from_numpy(g[tag + "_img1"]).to(DEV)
+        out = m32.inference(a, b, 0.5, scale).cpu().numpy()
+        assert np.abs(out - g[tag + "_out"]).max() < TOL32, tag
+        _check16(m16.inference(a.half(), b.half(), 0.5, scale).float().cpu().numpy(), g[tag + "_out"], tag)
+    a, b = torch.from_numpy(g["s2_img0"]).to(DEV), torch.from_numpy(g["s2_img1"]).to(DEV)
+    flows, mask, merged = m32.flownet(torch.cat((a, b), 1), 0.3, [8, 4, 2, 1, 0.5])
+    assert np.abs(flows[4].cpu().numpy() - g["s2_flow4"]).max() < 1e-3 and np.abs(flows[3].cpu().numpy() - g["s2_flow3"]).max() < 1e-3
+    assert np.abs(mask.cpu().numpy() - g["s2_mask"]).max() < 1e-3
+    assert np.abs(merged[4].cpu().numpy() - g["s2_merged_t03"]).max() < TOL32
+    # any frame size through pad=True (multiples of 64/scale = 32)
+    c, d = a[:, :, :50, :70].contiguous(), b[:, :, :50, :70].contiguous()
+    ref = m32.inference(torch.nn.functional.pad(c, (0, 26, 0, 14)), torch.nn.functional.pad(d, (0, 26, 0, 14)), 0.5, 2.0)[:, :, :50, :70]
+    assert torch.equal(m32.inference(c, d, 0.5, 2.0, pad=True), ref)
 
 
 def test_inference_host_e2e(pkg):

@@ -45,8 +45,9 @@ def test_scale_list_and_timestep_validation(pkg):
     assert f([16, 8, 4, 2, 1]) == 1.0 and f([32, 16, 8, 4, 2]) == 0.5 and f([64.0, 32.0, 16.0, 8.0, 4.0]) == 0.25
     with pytest.raises(ValueError):
         f([8, 4, 2, 1])                    # the reference's own default has 4 entries and crashes at index 4
+    assert f([8, 4, 2, 1, 0.5]) == 2.0 and f([4, 2, 1, 0.5, 0.25]) == 4.0     # --scale 2 / 4: blocks above full resolution
     with pytest.raises(NotImplementedError):
-        f([8, 4, 2, 1, 0.5])
+        f([48, 24, 12, 6, 3])
     with pytest.raises(NotImplementedError):
         f([16, 8, 4, 2, 2])
     t = pkg.IFNet._timesteps(0.25, 3)

@@ -111,6 +111,20 @@ def test_inference_variants(pkg, impl):
     assert np.abs(run(1.0, g["e_img0"], g["e_img1"]) - g["e_out"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("impl", ["numpy", "torch"])
+def test_scale_above_one(pkg, impl):
+    """--scale 2 / 4: the last block(s) run above full resolution (scale_list entries < 1)."""
+    g = load_golden("scale_up_cases")
+    m = seeded_model(pkg, AMP)
+    for tag, scale in (("s2", 2.0), ("s4", 4.0)):
+        a, b = g[tag + "_img0"], g[tag + "_img1"]
+        if impl == "numpy":
+            out = O.model_inference(numpy_state_dict(m), a, b, 0.5, scale)
+        else:
+            out = T.model_inference(torch_state_dict(m), torch.from_numpy(a), torch.from_numpy(b), 0.5, scale).numpy()
+        assert np.abs(out - g[tag + "_out"]).max() < 1e-4, tag
+
+
 def test_demo_config1(pkg):
     """BASELINE config 1: demo/I0_0.png + I0_1.png, exp=1, scale=1.0, fp32 (known answer of SURVEY 8a)."""
     g = load_golden("demo_256x448")
