@@ -71,7 +71,7 @@ int rife_weights_destroy(rife_weights* w);
 /* Bytes of device workspace a plan for this problem needs (0 on error, see rife_last_error). */
 size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int precision);
 /* B frames-pairs per call, C image channels (3, or 4 for RGBA), H and W multiples of 64/scale,
- * scale in {1, 0.5, 0.25} (scale_list = [16,8,4,2,1]/scale, train_log/RIFE_HDv3.py:58).
+ * scale in {0.25, 0.5, 1, 2, 4} (scale_list = [16,8,4,2,1]/scale, train_log/RIFE_HDv3.py:58; inference_video.py:92).
  * `workspace` is caller-owned device memory (256-byte aligned) that must outlive the plan.
  * `gridx_host` (W floats) / `gridy_host` (H floats) are the warp base grids
  * torch.linspace(-1,1,W) / (-1,1,H) of model/warplayer.py:11-14 computed by the caller on the
