@@ -63,6 +63,25 @@ class Model:
         pairs it belongs to."""
         return self.flownet.run_multi(frames, None, timesteps, scale, pad)
 
+    def interpolate_recursive(self, img0, img1, exp=1, timestep=0.5, scale=1.0, pad=False):
+        """The midpoint-of-midpoints loop of inference_img.py:95-103 (and make_inference, inference_video.py:178-188,
+        for n = 2**exp - 1): `exp` rounds of inserting the in-between frame of every adjacent pair.  The pairs of one
+        round are independent, so each round is ONE batched inference call (2**k pairs x B) instead of 2**k calls.
+        Returns the frame list [img0, ..., img1] (2**exp + 1 entries, each shaped like img0)."""
+        frames = [img0, img1]
+        b = img0.shape[0]
+        for _ in range(int(exp)):
+            left = torch.cat(frames[:-1], 0)
+            right = torch.cat(frames[1:], 0)
+            mids = self.flownet.run(left, right, timestep, scale, want_all=False, pad=pad)
+            nxt = []
+            for j in range(len(frames) - 1):
+                nxt.append(frames[j])
+                nxt.append(mids[j * b:(j + 1) * b])
+            nxt.append(frames[-1])
+            frames = nxt
+        return frames
+
     def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0, streams=None):
         """End-to-end call on HOST (ideally pinned) tensors -- NCHW float16/float32, or HWC uint8 frames exactly as a
         video decoder delivers them (any H, W): H2D copies, inference and the D2H copy of the result are enqueued on

@@ -199,6 +199,33 @@ def test_multi_timestep_and_sequence_reuse_head(pkg, precision):
         m.inference_sequence(frames[:1])
 
 
+def test_interpolate_recursive_matches_reference_loop(pkg):
+    """inference_img.py:95-103 with --exp=2 / make_inference(I0, I1, 3) of inference_video.py:178-188: the batched
+    rounds give exactly the frames of the one-call-per-pair recursion, in the reference's order."""
+    m = seeded_model(pkg, AMP, "fp16")
+    g = torch.Generator().manual_seed(6)
+    i0, i1 = torch.rand(1, 3, 64, 128, generator=g).to(DEV).half(), torch.rand(1, 3, 64, 128, generator=g).to(DEV).half()
+    img_list = [i0, i1]
+    for _ in range(2):                                                  # the reference's loop, verbatim structure
+        tmp = []
+        for j in range(len(img_list) - 1):
+            mid = m.inference(img_list[j], img_list[j + 1])
+            tmp.append(img_list[j])
+            tmp.append(mid)
+        tmp.append(i1)
+        img_list = tmp
+    got = m.interpolate_recursive(i0, i1, exp=2)
+    assert len(got) == 5 and all(torch.equal(x, y) for x, y in zip(got, img_list))
+
+    def make_inference(a, b, n):                                       # inference_video.py:178-188
+        middle = m.inference(a, b)
+        if n == 1:
+            return [middle]
+        fh, sh = make_inference(a, middle, n // 2), make_inference(middle, b, n // 2)
+        return [*fh, middle, *sh] if n % 2 else [*fh, *sh]
+    assert all(torch.equal(x, y) for x, y in zip(got[1:-1], make_inference(i0, i1, 3)))
+
+
 def test_dropin_import_paths(pkg):
     """`from train_log.RIFE_HDv3 import Model` / `from model.warplayer import warp` resolve to this package when
     eccv2022-rife_b200/dropin precedes the reference on sys.path."""
