@@ -127,6 +127,8 @@ struct rife_weights {
   DevLayer head[4];
   struct Block {
     DevLayer conv00, conv01, res[8], last;
+    HaloLayer last8;       // block 4 only, fp16 halo path: lastconv restricted to flow + mask (8-channel tmp pixel)
+    bool has_last8 = false;
     int c;
   } blk[5];
 };
@@ -239,7 +241,21 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
       for (int k = 0; k < c; ++k) L.beta[k] = be[k];
       if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
     }
-    if ((st = upload_layer(w, pack_convT(wl, bl, c, kLastCo, c), &B.last, /*ps_layout=*/true))) return fail(st);
+    const HostLayer hl = pack_convT(wl, bl, c, kLastCo, c);
+    if ((st = upload_layer(w, hl, &B.last, /*ps_layout=*/true))) return fail(st);
+    if (i == 4 && B.last.use_hk && halo_fits(hl, 2)) {
+      // nothing downstream reads the last block's feat channels (IFNet_HDv3.py:148-159): Model.inference runs a lastconv
+      // with 5 of the 13 output channels
+      std::vector<__half> packed;
+      std::vector<float> hb, hbeta;
+      void *pk = nullptr, *pkb = nullptr;
+      if ((st = halo_pack_weights(hl, 2, &packed, &hb, &hbeta, &B.last8))) return fail(st);
+      if ((st = upload(w, packed.data(), packed.size() * sizeof(__half), &pk))) return fail(st);
+      if ((st = upload(w, hb.data(), hb.size() * 4, &pkb))) return fail(st);
+      B.last8.w = (const __half*)pk;
+      B.last8.bias = (const float*)pkb;
+      B.has_last8 = true;
+    }
     bool tail = B.last.use_hk;
     for (int j = 0; j < 8; ++j) tail = tail && B.res[j].use_hk;
     w->blk_hk[i] = (tail && B.conv00.use_hk && B.conv01.use_hk) ? 1 : (tail ? 2 : 0);
@@ -475,6 +491,12 @@ int rife_plan_get_profile(rife_plan* p, const char** names, float* ms, int cap) 
 
 // --------------------------------------------------------------------------------------------------
 // pipeline
+static bool narrow_off() {
+  // test hooks: 16-channel tmp for the last block too / generic eval kernel instead of the fast merge
+  static const bool off = getenv("RIFE_NO_NARROW_LAST") != nullptr || getenv("RIFE_NO_FAST_MERGE") != nullptr;
+  return off;
+}
+
 static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
   if (p->precision == RIFE_PRECISION_FP16) return hk ? launch_conv_halo(L.hk, io, st) : launch_conv_umma(L.h16, io, st);
   return launch_conv_f32(L.f32, io, st);
@@ -567,8 +589,17 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     }
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
     io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
-    RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk_tail, st));
-    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = up > 1 ? -up : s;
+    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = up > 1 ? -up : s; lev[i].pitch = TMP_C;
+    // Model.inference (only `merged` wanted) at scale <= 1: the merge kernel needs flow + mask of the last block only
+    const bool narrow = i == 4 && hk_tail && w->blk[i].has_last8 && !narrow_off() && s == 1 && up == 1 && fbuf_levels == 4 &&
+                        !c.any_up && outs->merged && !outs->mask && !outs->flow[4] && !outs->warped0[4] && !outs->warped1[4];
+    if (narrow) {
+      io.epi = EPI_PS8; io.out_c = 8;
+      lev[i].pitch = 8;
+      RIFE_STAGE(bn + ".lastconv", launch_conv_halo(w->blk[i].last8, io, st));
+    } else {
+      RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk_tail, st));
+    }
 
     EvalOut eo;
     eo.flow = outs->flow[i];

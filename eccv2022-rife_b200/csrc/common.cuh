@@ -154,6 +154,7 @@ enum ConvEpi : int {
   EPI_PRELU = 7,        // y = prelu(acc + bias)
   EPI_PRELU_ADD = 8,    // y = prelu(acc + bias) + res        (convblock(x) + x, model/IFNet.py:46)
   EPI_CONVT_PRELU = 9,  // ConvTranspose parity scatter + prelu   (deconv(), model/refine.py:19-23)
+  EPI_PS8 = 10,         // EPI_PS of the network's last block: flow (4) + mask (1) only, 8-channel tmp pixel (halo kernel)
 };
 
 // Device-side view of one packed conv layer (fp32 FMA path).
@@ -189,6 +190,7 @@ struct TmpLevel {
   int h, w;
   int s;            // up-sampling factor to full resolution (power of two >= 1); negative: the level is stored at
                     // -s times the full resolution (scale > 1) and is DOWN-sampled by -s (centre 2x2 mean)
+  int pitch = TMP_C;  // channels per pixel: TMP_C, or 8 for the last block's flow + mask only level (EPI_PS8)
 };
 
 // Frame tensors at the API boundary.  RIFE_F32 / RIFE_F16: NCHW (B,C,h,w); RIFE_U8: HWC (B,h,w,C) as video decoders

@@ -189,7 +189,8 @@ __device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64
     constexpr int plane16 = (TH * MT + S::R) * pitch;
     constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
     constexpr int b_off = E * (2 * KSTEPS) * NE + 2 * KK * NE;
-    umma_f16_c<!(S::first(E) && KK == 0)>(acc + S::col16(E) * 16, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
+    constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;  // parity schedule: one NE-column group per output parity
+    umma_f16_c<!(S::first(E) && KK == 0)>(acc + d_col, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
     if constexpr (KK + 1 < KSTEPS) issue_tile<KIND, KSTEPS, NE, MT, E, KK + 1>(acc, a_base, b_base, idesc);
     else issue_tile<KIND, KSTEPS, NE, MT, E + 1, 0>(acc, a_base, b_base, idesc);
   }
@@ -205,7 +206,8 @@ __device__ __forceinline__ void issue_entry(uint32_t acc0, uint32_t ncols, uint6
     constexpr int pitch = TW + S::R;
     constexpr int plane16 = (TH * MT + S::R) * pitch;
     constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
-    umma_f16_c<!(S::first(E) && KK == 0)>(acc0 + (uint32_t)M * ncols + S::col16(E) * 16,
+    constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;
+    umma_f16_c<!(S::first(E) && KK == 0)>(acc0 + (uint32_t)M * ncols + d_col,
                                           a_base0 + (uint64_t)((uint32_t)M * mt_step + a_off), b_base + (uint64_t)(2 * KK * NE),
                                           idesc);
     if constexpr (KK + 1 < KSTEPS) issue_entry<KIND, KSTEPS, NE, MT, E, M, KK + 1>(acc0, ncols, a_base0, mt_step, b_base, idesc);
@@ -335,7 +337,7 @@ __device__ __forceinline__ void epi_chunk_rt(const HaloParams& p, const EpiCtx& 
 // EPI >= 0 additionally fixes the epilogue at compile time (fully unrolled over M-tiles and 16-column chunks).
 // Epilogue warps: 4 (one per SM sub-partition); the column-heavy PixelShuffle epilogue (256 columns per M-tile) uses 8,
 // warps w and w+4 sharing a TMEM lane quarter and splitting the output rows.
-template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS) ? 8 : 4; };
+template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS || EPI == EPI_PS8) ? 8 : 4; };
 
 // STREAM: the layer's weights do not fit in smem next to the activation ring (c >= 96): an extra producer warp streams
 // one weight tile per schedule entry through a ring of p.nb slots, re-using every tile for the MT stacked M-tiles.
@@ -594,6 +596,56 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
             __syncwarp();
           }
         }
+      } else if constexpr (KIND == 2 && EPI == EPI_PS8) {
+        // Last block of the network: only flow (4) + mask (1) are consumed downstream (IFNet_HDv3.py:152,158; the feat
+        // channels of block 4 are dropped by the reference too), so the tmp pixel is 8 channels = 16 B and the
+        // accumulator has 4 parities x (4 sub-pixels x 8) = 128 columns.  One staged output row (py, dy') of the warp's
+        // 4 x 8 input pixels = 4 x 512 contiguous bytes.
+        __shared__ uint4 ps8_stage[NUM_EPI_WARPS][4][32];
+        uint4(*stg)[32] = ps8_stage[warp - 2];
+        const int tyl = lane >> 3;
+        const int swz_w = tx_ >> 1;
+#pragma unroll 1
+        for (int mi = 0; mi < MT; ++mi) {
+          const int yw = (ty * MT + mi) * TH + q * 4;  // first input row of this warp
+#pragma unroll 1
+          for (int r = (4 / ESPLIT) * ehalf; r < (4 / ESPLIT) * (ehalf + 1); ++r) {
+            const int py = r >> 1, dyp = r & 1;
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {  // o = px: columns (py*2+px)*32 + dy'*16 + dx'*8 + k
+              const int j = (py * 2 + o) * 2 + dyp;
+              float v[16];
+              tmem_ld16(trow + (uint32_t)((buf * MT + mi) * 128 + j * 16), v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(s_bias + j * 16 + 4 * i);
+                v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
+                stg[tyl][(tx_ * 4 + o * 2 + h) ^ swz_w] = u;
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int idx = k * 32 + lane;
+              const int row = idx >> 5, col = idx & 31, txc = col >> 2;
+              const uint4 u = stg[row][col ^ (txc >> 1)];
+              const int y = yw + row, x = tx * TW + txc;
+              if (y < p.H && x < p.W) {
+                const int oy = 4 * y + 2 * py + dyp;
+                __half* dst = p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * 8 + col * 8;
+                *reinterpret_cast<uint4*>(dst) = u;
+              }
+            }
+            __syncwarp();
+          }
+        }
       } else if constexpr (KIND >= 0 && EPI >= 0) {
         constexpr int NCOLS = KIND == 2 ? 256 : NE;
         c.y0 = ty * MT * TH + ty_;
@@ -695,11 +747,11 @@ int num_sms() {
 
 // 0 = does not fit, 1 = weights resident in smem, 2 = weights streamed per schedule entry (templated shapes only:
 // the c = 96 / 128 ResConv and lastconv layers of IFBlock 2 / 1)
-int halo_mode(const HostLayer& h, bool ps_layout) {
+int halo_mode(const HostLayer& h, int ps_layout) {
   if (h.cin % 16) return 0;
   const int R = h.kind == CONV_3x3 ? 2 : 1;
   const int a_stage = ((h.cin / 8) * (TH + R) * (TW + R) * 16 + 1023) / 1024 * 1024;
-  const int ne = ps_layout ? 64 : h.npad;
+  const int ne = ps_layout == 2 ? 32 : (ps_layout ? 64 : h.npad);
   const int w_bytes = (ps_layout ? 16 : h.taps) * (h.cin / 8) * ne * 16;
   const int budget = SMEM_BUDGET - (ps_layout ? 32 * 1024 : 0);
   if (h.cin <= 128 && (ps_layout || h.npad <= 128) && w_bytes + 2 * a_stage + 2048 <= budget) return 1;
@@ -709,9 +761,9 @@ int halo_mode(const HostLayer& h, bool ps_layout) {
   if (templated && 2 * a_stage + 2 * wtile + 2048 <= budget) return 2;
   return 0;
 }
-bool halo_fits(const HostLayer& h, bool ps_layout) { return halo_mode(h, ps_layout) != 0; }
+bool halo_fits(const HostLayer& h, int ps_layout) { return halo_mode(h, ps_layout) != 0; }
 
-int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
+int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
                       std::vector<float>* beta, HaloLayer* L) {
   if (!halo_fits(h, ps_layout)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "halo_pack_weights: layer does not fit the halo kernel");
   const int kg = h.cin / 8;
@@ -720,27 +772,29 @@ int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
   beta->clear();
   if (ps_layout) {
     if (h.convt_co != 52 || h.kind != CONV_3x3) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "halo_pack_weights: PS layout is the 52-channel lastconv");
-    L->nentries = 16; L->ne = 64; L->ncols = 256; L->n_valid = 256; L->ps_cols = 1;
-    packed->assign((size_t)16 * kg * 64 * 8, __float2half_rn(0.f));
-    bias->assign(256, 0.f);
+    // ps_layout 2: the narrow variant for the network's last block -- flow (4) + mask (1) only, 8 channels per tmp pixel
+    const int pc = ps_layout == 2 ? 8 : 16, nk = ps_layout == 2 ? 5 : 13, ne = 4 * pc;
+    L->nentries = 16; L->ne = ne; L->ncols = 4 * ne; L->n_valid = 4 * ne; L->ps_cols = ps_layout == 2 ? 2 : 1;
+    packed->assign((size_t)16 * kg * ne * 8, __float2half_rn(0.f));
+    bias->assign(4 * ne, 0.f);
     int e = 0;
     for (int par = 0; par < 4; ++par) {
       const int py = par >> 1, px = par & 1;
       for (int sub = 0; sub < 4; ++sub)
-        for (int k = 0; k < 13; ++k) (*bias)[par * 64 + sub * 16 + k] = h.bias[par * 52 + 4 * k + sub];
+        for (int k = 0; k < nk; ++k) (*bias)[par * ne + sub * pc + k] = h.bias[par * 52 + 4 * k + sub];
       for (int dyi = 0; dyi < 2; ++dyi)
         for (int dxi = 0; dxi < 2; ++dxi, ++e) {
           const int dy = py ? dyi : dyi - 1, dx = px ? dxi : dxi - 1;  // taps that feed this output parity
           const int t = (dy + 1) * 3 + (dx + 1);
           L->e_dy[e] = (signed char)dy; L->e_dx[e] = (signed char)dx;
-          L->e_col16[e] = (unsigned char)(par * 4);
+          L->e_col16[e] = (unsigned char)(par * ne / 16);
           L->e_first[e] = (dyi == 0 && dxi == 0) ? 1 : 0;
           for (int g = 0; g < kg; ++g)
             for (int sub = 0; sub < 4; ++sub)
-              for (int k = 0; k < 13; ++k) {
-                const int n = sub * 16 + k, on = par * 52 + 4 * k + sub;
+              for (int k = 0; k < nk; ++k) {
+                const int n = sub * pc + k, on = par * 52 + 4 * k + sub;
                 for (int c = 0; c < 8; ++c)
-                  (*packed)[(((size_t)e * kg + g) * 64 + n) * 8 + c] =
+                  (*packed)[(((size_t)e * kg + g) * ne + n) * 8 + c] =
                       __float2half_rn(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + on]);
               }
         }
@@ -784,7 +838,8 @@ static int set_smem_attr(const void* fn) {
 int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if (io.epi == EPI_PS && !L.ps_cols) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
+  if (io.epi == EPI_PS && L.ps_cols != 1) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
+  if (io.epi == EPI_PS8 && L.ps_cols != 2) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS8 needs the narrow PixelShuffle layout");
   if (io.epi == EPI_RES && (!L.beta || !io.res)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES needs beta and res");
   if (io.epi == EPI_RES && L.cin != io.out_c) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_RES is the c -> c ResConv (residual = input)");
   if (io.epi == EPI_HEADT && !io.res) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_HEADT needs the s2d Head input as io.res");
@@ -802,6 +857,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
     const int nst = L.stream ? 2 : 3;
     static const int mt_max = []() { const char* e = getenv("RIFE_HK_MT"); return e ? atoi(e) : 2; }();
     int mt = mt_max < 1 ? 1 : (mt_max > 4 ? 4 : mt_max);
+    if (L.ps_cols) mt = 1;
     while (mt > 1 && (2 * mt * L.ncols > 512 || io.H < TH * mt ||
                       w_al0 + nst * (p.kgroups * (TH * mt + p.R) * (TW + p.R) * 16 + 1024) + 2048 > SMEM_BUDGET))
       mt >>= 1;
@@ -818,7 +874,9 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   p.wtile_bytes = p.kgroups * L.ne * 16;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.mt * L.ncols) p.tmem_cols <<= 1;
-  const int budget = SMEM_BUDGET - (io.epi == EPI_PS ? 32 * 1024 : 0);  // the PixelShuffle epilogue stages rows in 32 KB of static smem
+  // the PixelShuffle epilogues stage rows in static smem (8 warps x 4 KB / 2 KB)
+  const int static_extra = io.epi == EPI_PS ? 32 * 1024 : (io.epi == EPI_PS8 ? 16 * 1024 : 0);
+  const int budget = SMEM_BUDGET - static_extra;
   int w_al = (L.w_bytes + 1023) / 1024 * 1024;
   int stages;
   p.nb = 0; p.wtile_al = wtile_al;
@@ -844,8 +902,9 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   for (int k = L.stream ? 1 : persm_max; k >= 2; --k) {
     if (k * p.tmem_cols > 512) continue;
     int s2 = stages;
-    while (s2 > 3 && k * (w_al + s2 * p.a_stage_bytes + 2048) > 224 * 1024) --s2;
-    if (k * (w_al + s2 * p.a_stage_bytes + 2048) <= 224 * 1024) {
+    const int lim = static_extra ? 212 * 1024 : 224 * 1024;  // static smem is not part of `smem`: leave room for it
+    while (s2 > 3 && k * (w_al + s2 * p.a_stage_bytes + 2048 + static_extra) > lim) --s2;
+    if (k * (w_al + s2 * p.a_stage_bytes + 2048 + static_extra) <= lim) {
       per_sm = k;
       stages = s2;
       smem = w_al + stages * p.a_stage_bytes + 1024;
@@ -895,6 +954,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   RIFE_HK_CASE(1, 4, 32, 2, EPI_LRELU)      // block4.conv0.1       (s2d, 64 -> 32)
   RIFE_HK_CASE(0, 2, 32, 2, EPI_RES)        // block4 ResConv       (3x3, 32 -> 32)
   RIFE_HK_CASE(2, 2, 64, 1, EPI_PS)         // block4.lastconv      (ConvT+PS, 32 -> 4x64)
+  RIFE_HK_CASE(2, 2, 32, 1, EPI_PS8)        // block4.lastconv, flow + mask only (ConvT+PS, 32 -> 4x32)
   RIFE_HK_CASE(1, 8, 32, 1, EPI_LRELU_S2D)  // block3.conv0.0       (s2d, 128 -> 32)
   RIFE_HK_CASE(1, 8, 64, 1, EPI_LRELU)      // block3.conv0.1       (s2d, 128 -> 64)
   RIFE_HK_CASE(0, 4, 64, 2, EPI_RES)        // block3 ResConv       (3x3, 64 -> 64)
@@ -913,6 +973,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   RIFE_HK_STREAM(2, 8, 64, 1, EPI_PS)       // block1.lastconv      (ConvT+PS, 128 -> 4x64)
 #undef RIFE_HK_STREAM
   if (!done && L.stream) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no streamed instantiation for this layer / epilogue");
+  if (!done && p.epi == EPI_PS8) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no EPI_PS8 instantiation for this layer");
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
     RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<-1, 0, 0, 0, -1>, dim3(grid), dim3(64 + 32 * EpiWarps<-1>::value), smem, st, tm_a, p));
@@ -940,6 +1001,7 @@ int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st
   int oh = io.H, ow = io.W, oc = io.out_c;
   switch (io.epi) {
     case EPI_PS: nout = (size_t)io.B * 16 * io.H * io.W * TMP_C; break;
+    case EPI_PS8: nout = (size_t)io.B * 16 * io.H * io.W * 8; break;
     case EPI_HEADT:
     case EPI_CONVT: nout = (size_t)io.B * 4 * io.H * io.W * io.out_c; break;
     case EPI_LRELU_S2D: RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo_f32io: s2d store is pipeline-only");

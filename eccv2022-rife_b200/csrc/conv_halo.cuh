@@ -17,15 +17,15 @@ struct HaloLayer {
   int ncols = 0;      // accumulator columns per tile (ne, or 4 * 64 for the parity schedule)
   int n_valid = 0;
   int w_bytes = 0;
-  int ps_cols = 0;
+  int ps_cols = 0;    // 1: PixelShuffle layout (4 x 64 columns), 2: narrow PixelShuffle layout (4 x 32 columns)
   int stream = 0;     // 1: weights streamed through a smem ring (do not fit next to the activation stages)
   signed char e_dy[16] = {}, e_dx[16] = {};
   unsigned char e_col16[16] = {}, e_first[16] = {};
 };
 
-bool halo_fits(const HostLayer& h, bool ps_layout);
-int halo_mode(const HostLayer& h, bool ps_layout);  // 0 no, 1 resident weights, 2 streamed weights
-int halo_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
+bool halo_fits(const HostLayer& h, int ps_layout);  // ps_layout: 0 plain, 1 ConvT+PixelShuffle (16-ch tmp), 2 narrow (8-ch tmp: flow + mask)
+int halo_mode(const HostLayer& h, int ps_layout);  // 0 no, 1 resident weights, 2 streamed weights
+int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
                       std::vector<float>* beta, HaloLayer* L);
 // planar-8 fp16 activations [B][C/8][H][W][8] in; planar-8 (LRELU / LINEAR / RES / LRELU_S2D) or pixel-major
 // (PS / HEADT / CONVT) fp16 out

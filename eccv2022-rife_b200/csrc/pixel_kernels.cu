@@ -644,7 +644,7 @@ __device__ __forceinline__ void warp_img4(const __half* __restrict__ src, int H,
   for (int c = 0; c < 4; ++c) out[c] = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
 }
 
-template <typename Tio>
+template <typename Tio, int PITCH>
 __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__ tmp, const __half* __restrict__ src0,
                                                       const __half* __restrict__ src1, const float* __restrict__ gridx,
                                                       const float* __restrict__ gridy, const float* __restrict__ fbuf,
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__
   const size_t pix = ((size_t)b * H + y) * W + x;
   float flow[4], t8[8];
   ld4(fbuf + pix * 4, flow);
-  ld8(tmp + pix * TMP_C, t8);   // channels 0..3 flow of the last block (scale 1), 4 mask logit
+  ld8(tmp + pix * PITCH, t8);   // channels 0..3 flow of the last block (scale 1), 4 mask logit
 #pragma unroll
   for (int c = 0; c < 4; ++c) flow[c] += t8[c];                                    // IFNet_HDv3.py:152
   const float gx = gridx[x], gy = gridy[y];
@@ -913,16 +913,24 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   if (c.half_act && !c.any_up && !no_fast_merge && o.merged && !o.flow && !o.mask && !o.warped0 && !o.warped1 && nlev >= 2 &&
       fbuf_levels == nlev - 1 && levels[nlev - 1].s == 1) {
     const __half* tmp = (const __half*)levels[nlev - 1].ptr;
-#define RIFE_MERGE(TIO)                                                                                              \
-  RIFE_CUDA_TRY(launch_pdl(merge_h_kernel<TIO>, egrid, dim3(256), 0, st, tmp, (const __half*)c.src0,                  \
+#define RIFE_MERGE(TIO, PITCH)                                                                                       \
+  RIFE_CUDA_TRY(launch_pdl(merge_h_kernel<TIO, PITCH>, egrid, dim3(256), 0, st, tmp, (const __half*)c.src0,           \
                            (const __half*)c.src1, c.gridx, c.gridy, fbuf, (TIO*)o.merged, c.C, c.H, c.W, g, lay))
-    if (io_dtype == RIFE_F32) RIFE_MERGE(float);
-    else if (io_dtype == RIFE_F16) RIFE_MERGE(__half);
-    else RIFE_MERGE(uint8_t);
+    if (levels[nlev - 1].pitch == 8) {
+      if (io_dtype == RIFE_F32) RIFE_MERGE(float, 8);
+      else if (io_dtype == RIFE_F16) RIFE_MERGE(__half, 8);
+      else RIFE_MERGE(uint8_t, 8);
+    } else {
+      if (io_dtype == RIFE_F32) RIFE_MERGE(float, TMP_C);
+      else if (io_dtype == RIFE_F16) RIFE_MERGE(__half, TMP_C);
+      else RIFE_MERGE(uint8_t, TMP_C);
+    }
 #undef RIFE_MERGE
     RIFE_LAUNCH_CHECK();
     return RIFE_OK;
   }
+  for (int i = 0; i < nlev; ++i)
+    if (levels[i].pitch != TMP_C) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "launch_eval: an 8-channel tmp level needs the fast merge path");
 #define RIFE_EVAL(T, TIO)                                                                                         \
   RIFE_CUDA_TRY(launch_pdl(eval_kernel<T, T, TIO>, egrid, dim3(256), 0, st, L, nlev, (const T*)c.src0,            \
                            (const T*)c.src1, c.gridx, c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,       \
