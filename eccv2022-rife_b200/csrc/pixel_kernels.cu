@@ -21,9 +21,16 @@
 #endif
 // resident blocks per SM the block-input gather is compiled for (register cap): measured best on B200 at 1080p --
 // s = 1 (block 4): 9 blocks (56 regs), s >= 2: 6 blocks (80 regs); 104 / 61 regs without the cap cost 2-4 % of a step
+#ifndef RIFE_BI_QUNROLL
+#define RIFE_BI_QUNROLL 4
+#endif
+constexpr int kQUnroll = RIFE_BI_QUNROLL;  // samples of the 2x2 resize block whose warps are in flight together
 #ifndef RIFE_BI_MINB1
 #define RIFE_BI_MINB1 9
 #define RIFE_BI_MINB2 6
+#endif
+#ifndef RIFE_BI_MINB2R
+#define RIFE_BI_MINB2R 9
 #endif
 #ifndef RIFE_PREP_MINB
 #define RIFE_PREP_MINB 3
@@ -314,6 +321,55 @@ __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_kernel(const 
   }
 }
 
+// uint8 HWC RGB frames (B, h, w, 3) as a video decoder delivers them, h <= H rows (zero-padded below, F.pad of the
+// reference's callers), w == W: one thread converts a 2 x 8 pixel strip = 2 x 24 bytes read as 8-byte words.
+__global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_u8_kernel(const uint8_t* __restrict__ img0,
+                                                                             const uint8_t* __restrict__ img1,
+                                                                             __half* __restrict__ head_in, int nf0, int h,
+                                                                             int H, int W) {
+  pdl_wait();
+  RIFE_PIX_TRIGGER();
+  const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
+  const int xs = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y2 = blockIdx.y, fb = blockIdx.z;
+  if (xs >= W8) return;
+  const uint8_t* img = fb < nf0 ? img0 + (size_t)fb * h * W * 3 : img1 + (size_t)(fb - nf0) * h * W * 3;
+  uint32_t wd[2][6];  // [row][32-bit word]: 24 bytes = 8 RGB pixels
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = 2 * y2 + r;
+    if (y < h) {
+      const uint2* p = reinterpret_cast<const uint2*>(img + ((size_t)y * W + xs * 8) * 3);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint2 u = __ldg(p + i);
+        wd[r][2 * i] = u.x; wd[r][2 * i + 1] = u.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) wd[r][i] = 0u;
+    }
+  }
+  auto byte_at = [&](int r, int k) -> float {  // k = x*3 + c, compile-time after unrolling
+    return to_f((uint8_t)((wd[r][k >> 2] >> ((k & 3) * 8)) & 0xffu));
+  };
+  __half* o = head_in + (((size_t)fb * 2 * H2 + y2) * W2 + xs * 4) * 8;
+  const size_t gstride = (size_t)H2 * W2 * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a[8], b2[8];
+    // s2d channel = par*3 + c for par = (row, x parity); channels 12..15 (alpha) are zero for RGB frames
+    a[0] = byte_at(0, (2 * k) * 3 + 0); a[1] = byte_at(0, (2 * k) * 3 + 1); a[2] = byte_at(0, (2 * k) * 3 + 2);
+    a[3] = byte_at(0, (2 * k + 1) * 3 + 0); a[4] = byte_at(0, (2 * k + 1) * 3 + 1); a[5] = byte_at(0, (2 * k + 1) * 3 + 2);
+    a[6] = byte_at(1, (2 * k) * 3 + 0); a[7] = byte_at(1, (2 * k) * 3 + 1);
+    b2[0] = byte_at(1, (2 * k) * 3 + 2);
+    b2[1] = byte_at(1, (2 * k + 1) * 3 + 0); b2[2] = byte_at(1, (2 * k + 1) * 3 + 1); b2[3] = byte_at(1, (2 * k + 1) * 3 + 2);
+    b2[4] = b2[5] = b2[6] = b2[7] = 0.f;
+    st8(o + k * 8, a);
+    st8(o + gstride + k * 8, b2);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // block input: one thread per low-resolution pixel of the (H/s, W/s) block input.
 template <typename T, typename Tt, int NS, bool LEVEL0>
@@ -423,6 +479,11 @@ __global__ void __launch_bounds__(128) block_input_kernel(LevelsArg L, int level
 //     block never straddles a cell of a coarser level), and mask/feat averaged through the mean tap weights;
 //   * warp taps blended with packed half2 FMAs (values in [0,1], weights to 11 bits: below the fp16 storage
 //     rounding of the block input itself); coordinates and flow stay fp32.
+#define SPLIT8(e, lo, hi)                                  \
+  do {                                                     \
+    lo[0] = e[0]; lo[1] = e[1]; lo[2] = e[2]; lo[3] = e[3]; \
+    hi[0] = e[4]; hi[1] = e[5]; hi[2] = e[6]; hi[3] = e[7]; \
+  } while (0)
 struct Lerp2 {  // two adjacent positions d, d+1 sharing their taps
   int i0, i1;
   float a0, a1;  // lambda1 of position d and d+1
@@ -455,6 +516,42 @@ __device__ __forceinline__ void warp8_h2(const __half* __restrict__ src, int H, 
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     out[i] = __hfma2(w11, h11[i], __hfma2(w10, h10[i], __hfma2(w01, h01[i], __hmul2(w00, h00[i]))));
+}
+
+// One coarser tmp level, tap-major: every tap is loaded once (16 + 16 bytes for the newest level, whose mask / feat
+// channels are wanted too; 8 bytes of flow otherwise) and folded into the NQ samples' flow sums and into mf straight away,
+// in the order 00, 01, 10, 11 of the bilinear formula.  wq[q][k]: weight of tap k for sample q; am[k]: mean weight of tap k.
+template <int NQ>
+__device__ __forceinline__ void level_taps(const __half* __restrict__ r0, const __half* __restrict__ r1, int c0, int c1,
+                                           bool newest, const float (&wq)[NQ][4], const float (&am)[4], float sc,
+                                           bool first, float (&flow)[NQ][4], float (&mf)[12]) {
+  float acc[NQ][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half* p = ((k >> 1) ? r1 : r0) + ((k & 1) ? c1 : c0);
+    float e[8];
+    if (newest) {
+      float u[8];
+      ld8(p, e);
+      ld8(p + 8, u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mf[c] = k == 0 ? am[0] * e[4 + c] : fmaf(am[k], e[4 + c], mf[c]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mf[4 + c] = k == 0 ? am[0] * u[c] : fmaf(am[k], u[c], mf[4 + c]);
+    } else {
+      float v[4];
+      ld4(p, v);
+      e[0] = v[0]; e[1] = v[1]; e[2] = v[2]; e[3] = v[3];
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[q][c] = k == 0 ? wq[q][0] * e[c] : fmaf(wq[q][k], e[c], acc[q][c]);
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) flow[q][c] = first ? acc[q][c] * sc : fmaf(acc[q][c], sc, flow[q][c]);
 }
 
 template <int NS>
@@ -493,45 +590,24 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
       continue;
     }
     const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
-    if (NS == 2 && sj == s) {
-      // the newest level may be as fine as the sample spacing allows only when s_j > s; s_j == s cannot occur
-    }
-    const __half* r0 = base + ly.i0 * w * TMP_C;
-    const __half* r1 = base + ly.i1 * w * TMP_C;
-    float v00[4], v01[4], v10[4], v11[4];
-    ld4(r0 + lx.i0 * TMP_C, v00); ld4(r0 + lx.i1 * TMP_C, v01);
-    ld4(r1 + lx.i0 * TMP_C, v10); ld4(r1 + lx.i1 * TMP_C, v11);
-    float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float wq[NQ][4], am[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
-      const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
-      wsum[0] += w00; wsum[1] += w01; wsum[2] += w10; wsum[3] += w11;
+      wq[q][0] = (1.f - ay) * (1.f - ax); wq[q][1] = (1.f - ay) * ax; wq[q][2] = ay * (1.f - ax); wq[q][3] = ay * ax;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float f = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
-        flow[q][c] = (j == 0) ? f * sc : fmaf(f, sc, flow[q][c]);
-      }
+      for (int k = 0; k < 4; ++k) am[k] += wq[q][k];
     }
-    if (newest) {
-      const float inv = 1.f / (float)NQ;
-      const float a00 = wsum[0] * inv, a01 = wsum[1] * inv, a10 = wsum[2] * inv, a11 = wsum[3] * inv;
-      float t00[4], t01[4], t10[4], t11[4], u00[8], u01[8], u10[8], u11[8];
-      ld4(r0 + lx.i0 * TMP_C + 4, t00); ld4(r0 + lx.i1 * TMP_C + 4, t01);
-      ld4(r1 + lx.i0 * TMP_C + 4, t10); ld4(r1 + lx.i1 * TMP_C + 4, t11);
-      ld8(r0 + lx.i0 * TMP_C + 8, u00); ld8(r0 + lx.i1 * TMP_C + 8, u01);
-      ld8(r1 + lx.i0 * TMP_C + 8, u10); ld8(r1 + lx.i1 * TMP_C + 8, u11);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) mf[c] = fmaf(a11, t11[c], fmaf(a10, t10[c], fmaf(a01, t01[c], a00 * t00[c])));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mf[4 + c] = fmaf(a11, u11[c], fmaf(a10, u10[c], fmaf(a01, u01[c], a00 * u00[c])));
-    }
+    for (int k = 0; k < 4; ++k) am[k] *= 1.f / (float)NQ;
+    level_taps<NQ>(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, newest, wq, am, sc,
+                   j == 0, flow, mf);
   }
   // warps + accumulation over the samples
   __half2 A[4], Cc[4];
   const __half2 qw = __float2half2_rn(1.f / (float)NQ);
   float fs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll kQUnroll
   for (int q = 0; q < NQ; ++q) {
     const int y = y0 + q / NS, x = x0 + q % NS;
     if (fbuf_store) st4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow[q]);
@@ -577,6 +653,121 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
     hh[0] = o[4 * k]; hh[1] = o[4 * k + 1]; hh[2] = o[4 * k + 2]; hh[3] = o[4 * k + 3];
     *reinterpret_cast<uint4*>(dst + k * gstride) = u;
   }
+}
+
+// s >= 2 variant with the 2x2 sample block split over a lane pair: lane 2k + r evaluates COLUMN r (two samples, two pairs
+// of warps) of cell k and the pair adds its halves with 15 half2 shuffles.  For s = 2 consecutive lanes are consecutive
+// full-resolution pixels, so every 16-byte tap load of a warp covers one contiguous 512-byte span (block_input_h_kernel<2>
+// strides its lanes by two pixels: twice the L1 wavefronts, which is what bounds these kernels -- ncu: lsu data-pipe 72 %).
+__device__ __forceinline__ __half2 shfl_xor_h2(__half2 v, int m) {
+  const unsigned u = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&v), m);
+  return *reinterpret_cast<const __half2*>(&u);
+}
+__global__ void __launch_bounds__(128, RIFE_BI_MINB2R) block_input_h2c_kernel(LevelsArg L, int level, int s,
+                                                            const __half* __restrict__ src0,
+                                                            const __half* __restrict__ src1,
+                                                            const float* __restrict__ gridx,
+                                                            const float* __restrict__ gridy,
+                                                            const float* __restrict__ tstep, __half* __restrict__ xin,
+                                                            int B, int H, int W, WarpGeom geom, int planar,
+                                                            float* __restrict__ fbuf, int fbuf_levels, int fbuf_store) {
+  pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
+  RIFE_PIX_TRIGGER();
+  const int Hs = H / s, Ws = W / s;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = tid & 1;
+  const bool valid = (tid >> 1) < Ws;            // a lane pair is valid or not as a whole; nobody leaves before the shuffles
+  const int X = valid ? (tid >> 1) : Ws - 1;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const __half* s0 = src0 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const __half* s1 = src1 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const int off = s / 2 - 1;
+  const int x = X * s + off + r, y0 = Y * s + off;
+  float flow[2][4];
+  float* fp = fbuf + (((size_t)b * H + y0) * W + x) * 4;
+  if (fbuf_levels > 0) {
+    ld4(fp, flow[0]);
+    ld4(fp + (size_t)W * 4, flow[1]);
+  }
+  float mf[12];  // this column's share of channels 4..15 of the newest level (mask, feat x8, pad), weights sum to 1/2
+#pragma unroll 1
+  for (int j = fbuf_levels; j < level; ++j) {
+    const int h = L.h[j], w = L.w[j];
+    if (L.s[j] == 1) continue;
+    const __half* base = reinterpret_cast<const __half*>(L.ptr[j]) + (size_t)b * h * w * TMP_C;
+    const float sc = L.sc[j];
+    const Lerp2 ly = make_lerp2(y0, h, L.rs[j]);
+    const Lerp lx = make_lerp(x, w, L.rs[j]);
+    float wq[2][4], am[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float ay = q ? ly.a1 : ly.a0, ax = lx.l1;
+      wq[q][0] = (1.f - ay) * (1.f - ax); wq[q][1] = (1.f - ay) * ax; wq[q][2] = ay * (1.f - ax); wq[q][3] = ay * ax;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) am[k] += wq[q][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) am[k] *= 0.25f;   // this column holds two of the four samples
+    level_taps<2>(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, j == level - 1, wq, am,
+                  sc, j == 0, flow, mf);
+  }
+  __half2 A[4], Cc[4];
+  const __half2 qw = __float2half2_rn(0.25f);
+  const float gx = gridx[x];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (fbuf_store && valid) st4(fp + (size_t)q * W * 4, flow[q]);
+    const float gy = gridy[y0 + q];
+    __half2 a[4], c[4];
+    warp8_h2(s0, H, W, geom, gx, gy, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
+    warp8_h2(s1, H, W, geom, gx, gy, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (q == 0) { A[i] = __hmul2(qw, a[i]); Cc[i] = __hmul2(qw, c[i]); }
+      else { A[i] = __hfma2(qw, a[i], A[i]); Cc[i] = __hfma2(qw, c[i], Cc[i]); }
+    }
+  }
+  // interpolate(flow, 1/s) * 1/s   (IFNet_HDv3.py:81): this column's half of the 2x2 mean
+  const float fsc = 0.25f / (float)s;
+  const float t = tstep[b];
+  __half2 o[16];
+  o[7] = __floats2half2_rn(0.5f * t, mf[0]);     // timestep (exact after the pair's add), mask
+  o[8] = __floats2half2_rn(mf[1], mf[2]);        // feat 0..7
+  o[9] = __floats2half2_rn(mf[3], mf[4]);
+  o[10] = __floats2half2_rn(mf[5], mf[6]);
+  o[11] = __floats2half2_rn(mf[7], mf[8]);
+  o[12] = __floats2half2_rn((flow[0][0] + flow[1][0]) * fsc, (flow[0][1] + flow[1][1]) * fsc);
+  o[13] = __floats2half2_rn((flow[0][2] + flow[1][2]) * fsc, (flow[0][3] + flow[1][3]) * fsc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    A[i] = __hadd2(A[i], shfl_xor_h2(A[i], 1));
+    Cc[i] = __hadd2(Cc[i], shfl_xor_h2(Cc[i], 1));
+  }
+#pragma unroll
+  for (int i = 7; i < 14; ++i) o[i] = __hadd2(o[i], shfl_xor_h2(o[i], 1));
+  o[0] = A[2];                                   // warped img0 r, g
+  o[1] = __halves2half2(__low2half(A[3]), __low2half(Cc[2]));   // img0 b, img1 r
+  o[2] = __halves2half2(__high2half(Cc[2]), __low2half(Cc[3])); // img1 g, b
+  o[3] = A[0]; o[4] = A[1];                      // warped f0
+  o[5] = Cc[0]; o[6] = Cc[1];                    // warped f1
+  o[14] = __float2half2_rn(0.f);
+  o[15] = o[14];
+  if (!valid) return;
+  const int par = (Y & 1) * 2 + (X & 1);
+  const size_t hw2 = (size_t)(Hs >> 1) * (Ws >> 1), pix2 = (size_t)(Y >> 1) * (Ws >> 1) + (X >> 1);
+  __half* dst = planar ? xin + (((size_t)b * 16 + par * 4) * hw2 + pix2) * 8 : xin + (((size_t)b * hw2 + pix2) * 4 + par) * XIN_C;
+  const size_t gstride = planar ? hw2 * 8 : 8;
+  // lane r of the pair stores the 16-byte groups 2r, 2r + 1
+  uint4 u0, u1;
+  __half2* h0 = reinterpret_cast<__half2*>(&u0);
+  __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h0[i] = r ? o[8 + i] : o[i];
+    h1[i] = r ? o[12 + i] : o[4 + i];
+  }
+  *reinterpret_cast<uint4*>(dst + (2 * r) * gstride) = u0;
+  *reinterpret_cast<uint4*>(dst + (2 * r + 1) * gstride) = u1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -837,6 +1028,14 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
     RIFE_LAUNCH_CHECK();
     return RIFE_OK;
   }
+  if (c.planar_head && c.half_act && io_dtype == RIFE_U8 && c.C == 3 && fw == c.W && c.W % 8 == 0 &&
+      ((uintptr_t)img0 % 8) == 0 && ((uintptr_t)img1 % 8) == 0 && ((size_t)fh * fw * 3) % 8 == 0) {
+    const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
+    RIFE_CUDA_TRY(launch_pdl(prep_planar_u8_kernel, g, dim3(256), 0, st, (const uint8_t*)img0, (const uint8_t*)img1,
+                             (__half*)head_in, c.nf0, fh, c.H, c.W));
+    RIFE_LAUNCH_CHECK();
+    return RIFE_OK;
+  }
   const size_t nq = (size_t)c.F * (c.H / 2) * (c.W / 2);
   dim3 grid(nblk(nq, 256));
 #define RIFE_PREP(TIO, T)                                                                                        \
@@ -885,7 +1084,19 @@ int launch_block_input(const PixelCtx& c, int level, const TmpLevel* levels, int
   RIFE_CUDA_TRY(launch_pdl(block_input_h_kernel<NS_>, grid, dim3(128), 0, st, L, level, s, (const __half*)c.src0,    \
                            (const __half*)c.src1, c.gridx, c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g,          \
                            planar ? 1 : 0, fbuf, fbuf_levels, fbuf_store ? 1 : 0))
-    if (s1) RIFE_BIH(1); else RIFE_BIH(2);
+    // s = 2 (every pixel sampled; issue-bound): one thread per 2x2 block (0.36 ms vs 0.39 ms at 8 x 1080p);
+    // s >= 4 (sparse samples; L1-wavefront-bound): the lane-pair split (b1 + b2: 0.156 vs 0.171 ms)
+    static const int pair_min_s = getenv("RIFE_BI_PAIR_MIN_S") ? atoi(getenv("RIFE_BI_PAIR_MIN_S")) : 4;
+    if (s1) {
+      RIFE_BIH(1);
+    } else if (s < pair_min_s) {
+      RIFE_BIH(2);
+    } else {
+      const dim3 grid2(nblk((size_t)(c.W / s) * 2, 128), (unsigned)(c.H / s), (unsigned)c.B);
+      RIFE_CUDA_TRY(launch_pdl(block_input_h2c_kernel, grid2, dim3(128), 0, st, L, level, s, (const __half*)c.src0,
+                               (const __half*)c.src1, c.gridx, c.gridy, c.tstep, (__half*)xin, c.B, c.H, c.W, g,
+                               planar ? 1 : 0, fbuf, fbuf_levels, fbuf_store ? 1 : 0));
+    }
 #undef RIFE_BIH
   } else if (c.half_act) {
     if (l0 && s1) RIFE_BI(__half, 1, true); else if (l0) RIFE_BI(__half, 2, true);
