@@ -21,10 +21,6 @@
 #endif
 // resident blocks per SM the block-input gather is compiled for (register cap): measured best on B200 at 1080p --
 // s = 1 (block 4): 9 blocks (56 regs), s >= 2: 6 blocks (80 regs); 104 / 61 regs without the cap cost 2-4 % of a step
-#ifndef RIFE_BI_QUNROLL
-#define RIFE_BI_QUNROLL 4
-#endif
-constexpr int kQUnroll = RIFE_BI_QUNROLL;  // samples of the 2x2 resize block whose warps are in flight together
 #ifndef RIFE_BI_MINB1
 #define RIFE_BI_MINB1 9
 #define RIFE_BI_MINB2 6
@@ -589,25 +585,60 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
     if (sj == 1) {  // only possible as the newest level of a scale-1 eval; not reached from block inputs
       continue;
     }
-    const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
-    float wq[NQ][4], am[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (NS == 1) {
+      const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
+      float wq[NQ][4], am[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
-      wq[q][0] = (1.f - ay) * (1.f - ax); wq[q][1] = (1.f - ay) * ax; wq[q][2] = ay * (1.f - ax); wq[q][3] = ay * ax;
+      for (int q = 0; q < NQ; ++q) {
+        const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
+        wq[q][0] = (1.f - ay) * (1.f - ax); wq[q][1] = (1.f - ay) * ax; wq[q][2] = ay * (1.f - ax); wq[q][3] = ay * ax;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) am[k] += wq[q][k];
-    }
+        for (int k = 0; k < 4; ++k) am[k] += wq[q][k];
+      }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) am[k] *= 1.f / (float)NQ;
-    level_taps<NQ>(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, newest, wq, am, sc,
-                   j == 0, flow, mf);
+      for (int k = 0; k < 4; ++k) am[k] *= 1.f / (float)NQ;
+      level_taps<NQ>(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, newest, wq, am, sc,
+                     j == 0, flow, mf);
+      } else {
+      // four samples: per-level tap arrays kept whole (the tap-major form costs this variant registers: 0.36 vs 0.34 ms)
+      const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
+      const __half* r0 = base + ly.i0 * w * TMP_C;
+      const __half* r1 = base + ly.i1 * w * TMP_C;
+      float v00[4], v01[4], v10[4], v11[4];
+      ld4(r0 + lx.i0 * TMP_C, v00); ld4(r0 + lx.i1 * TMP_C, v01);
+      ld4(r1 + lx.i0 * TMP_C, v10); ld4(r1 + lx.i1 * TMP_C, v11);
+      float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
+        const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
+        wsum[0] += w00; wsum[1] += w01; wsum[2] += w10; wsum[3] += w11;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float f = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], w00 * v00[c])));
+          flow[q][c] = (j == 0) ? f * sc : fmaf(f, sc, flow[q][c]);
+        }
+      }
+      if (newest) {
+        const float inv = 1.f / (float)NQ;
+        const float a00 = wsum[0] * inv, a01 = wsum[1] * inv, a10 = wsum[2] * inv, a11 = wsum[3] * inv;
+        float t00[4], t01[4], t10[4], t11[4], u00[8], u01[8], u10[8], u11[8];
+        ld4(r0 + lx.i0 * TMP_C + 4, t00); ld4(r0 + lx.i1 * TMP_C + 4, t01);
+        ld4(r1 + lx.i0 * TMP_C + 4, t10); ld4(r1 + lx.i1 * TMP_C + 4, t11);
+        ld8(r0 + lx.i0 * TMP_C + 8, u00); ld8(r0 + lx.i1 * TMP_C + 8, u01);
+        ld8(r1 + lx.i0 * TMP_C + 8, u10); ld8(r1 + lx.i1 * TMP_C + 8, u11);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mf[c] = fmaf(a11, t11[c], fmaf(a10, t10[c], fmaf(a01, t01[c], a00 * t00[c])));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mf[4 + c] = fmaf(a11, u11[c], fmaf(a10, u10[c], fmaf(a01, u01[c], a00 * u00[c])));
+      }
+      }
   }
   // warps + accumulation over the samples
   __half2 A[4], Cc[4];
   const __half2 qw = __float2half2_rn(1.f / (float)NQ);
   float fs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll kQUnroll
+#pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int y = y0 + q / NS, x = x0 + q % NS;
     if (fbuf_store) st4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow[q]);

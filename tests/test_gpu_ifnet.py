@@ -226,6 +226,31 @@ def test_interpolate_recursive_matches_reference_loop(pkg):
     assert all(torch.equal(x, y) for x, y in zip(got[1:-1], make_inference(i0, i1, 3)))
 
 
+def test_app_interpolation_helpers(pkg):
+    """rife_app/utils/interpolation.py: progressive_interpolate_frames (one model.inference per adjacent pair per stage,
+    positions kept in a dict) and generate_interpolated_frames give the same frames as the batched stages here."""
+    import importlib
+    ip = importlib.import_module("eccv2022-rife_b200.interpolation")
+    m = seeded_model(pkg, AMP, "fp16")
+    g = torch.Generator().manual_seed(8)
+    i0, i1 = torch.rand(1, 3, 128, 128, generator=g).to(DEV).half(), torch.rand(1, 3, 128, 128, generator=g).to(DEV).half()
+    frames = {0.0: i0, 1.0: i1}                                         # the reference's stage loop, scale = 0.5
+    for _ in range(3):
+        pos = sorted(frames)
+        new = {}
+        for a, b in zip(pos[:-1], pos[1:]):
+            new[(a + b) / 2] = m.inference(frames[a], frames[b], scale=0.5)
+        frames.update(new)
+    want = [frames[p] for p in sorted(frames) if 0.0 < p < 1.0]
+    got = ip.progressive_interpolate_frames(i0, i1, 3, m, 0.5)
+    assert len(got) == 7 and all(torch.equal(x, y) for x, y in zip(got, want))
+    assert ip.progressive_interpolate_frames(i0, i1, 0, m, 1.0) == []
+    assert all(torch.equal(x, y) for x, y in zip(ip.recursive_interpolate_video_frames(i0, i1, 3, m, 0.5), want))
+    lst = ip.generate_interpolated_frames(i0, i1, 2, m)
+    ref = m.interpolate_recursive(i0, i1, exp=2)
+    assert len(lst) == 5 and all(torch.equal(x, y) for x, y in zip(lst, ref))
+
+
 def test_dropin_import_paths(pkg):
     """`from train_log.RIFE_HDv3 import Model` / `from model.warplayer import warp` resolve to this package when
     eccv2022-rife_b200/dropin precedes the reference on sys.path."""
