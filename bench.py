@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RIFE_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     ap.add_argument("--pairs", type=int, default=12, help="frame pairs per step per GPU (batch of one Model.inference)")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("RIFE_CHUNK_PAIRS", "0")),
+                    help="pairs per pass of the 1/2- and full-resolution stages (rife_plan_set_chunk); 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -208,6 +210,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
+    if args.chunk:
+        os.environ["RIFE_CHUNK_PAIRS"] = str(args.chunk)    # read once by the library
     pkg = importlib.import_module("eccv2022-rife_b200")
     lib = pkg._lib.load()
     numa_cores = pkg.sharding.bind_to_gpu_numa(local_rank) if world > 1 else 0   # pinned buffers on the GPU's NUMA node
@@ -357,16 +361,18 @@ def main():
     }
     top = max(stage_ms, key=lambda k: stage_ms[k])
     rk = "b4.input"
-    k_ms = stage_ms.get(rk, 0.0) / max(stage_launches.get(rk, 1), 1)
-    achieved = alg[rk] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    n_l = max(stage_launches.get(rk, 1), 1)            # launches of that kernel per step (= passes, --chunk)
+    k_ms = stage_ms.get(rk, 0.0) / n_l
+    alg_launch = alg[rk] / n_l
+    achieved = alg_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
     tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(tp) and args.precision == "fp16":
         tj = json.load(open(tp))
-        traffic = tj.get("traffic_bytes_per_launch") * P / float(tj.get("pairs", 4))   # bytes scale with the pairs per launch
+        traffic = tj.get("traffic_bytes_per_launch") * (P / n_l) / float(tj.get("pairs", 4))   # bytes scale with the pairs per launch
     roofline = {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[rk], "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_launch, "kernel_ms": k_ms, "launches_per_step": n_l,
                 "top_stage_by_time": top,
                 "pipeline_model": {"bytes_per_pair_stage_fused_model": BYTES_PER_PIXEL_MODEL * H * W * esz,
                                    "frac_of_hbm_peak": (BYTES_PER_PIXEL_MODEL * H * W * esz * value / world) / (hbm_peak * 1e9),
@@ -378,7 +384,8 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "precision": args.precision,
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "pairs_per_pass_full_res_stages": int(P / n_l + 0.5),
+                   "precision": args.precision,
                    "parallelism": f"frame-pair sharding x{world}, no collective",
                    "host_numa_cores_bound": numa_cores,
                    "l2_policy": f"inputs rotate over {NSETS} distinct batches; each step streams >1 GB of intermediates (> 126 MB L2)"},

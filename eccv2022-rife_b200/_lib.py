@@ -15,7 +15,7 @@ PRECISION_FP32, PRECISION_FP16 = 0, 1
 SYMBOLS = [
     "rife_abi_version", "rife_last_error", "rife_launch_count", "rife_weights_create", "rife_weights_destroy",
     "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_workspace_bytes_ex", "rife_plan_create_ex", "rife_plan_destroy", "rife_plan_set_frame_size",
-    "rife_plan_set_profiling",
+    "rife_plan_set_profiling", "rife_plan_set_chunk",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_inference_host_pipelined", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
     "rife_scene_ssim", "rife_layer_create", "rife_layer_destroy", "rife_layer_run", "rife_nhwc_from_nchw", "rife_nhwc_to_nchw",
@@ -61,6 +61,7 @@ def load():
     lib.rife_plan_destroy.argtypes = [vp]
     lib.rife_plan_set_frame_size.argtypes = [vp, i, i]
     lib.rife_plan_set_profiling.argtypes = [vp, i]
+    lib.rife_plan_set_chunk.argtypes = [vp, i]
     lib.rife_plan_get_profile.argtypes = [vp, C.POINTER(C.c_char_p), fp, i]
     lib.rife_inference.argtypes = [vp, vp, vp, fp, vp, i, vp]
     lib.rife_ifnet_forward.argtypes = [vp, vp, vp, fp, C.POINTER(IFNetOutputs), i, vp]

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -348,6 +349,7 @@ struct rife_plan {
   int nf0() const { return seq ? P + 1 : P; }                   // frames the caller passes in img0 / img1
   int nf1() const { return seq ? 0 : P; }
   int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
+  int chunk = 0;       // pairs per pass of the full-resolution stages (rife_plan_set_chunk); 0 = default
   PlanLayout L{};
   char* ws = nullptr;
   void* at(size_t off) const { return ws + off; }
@@ -467,6 +469,13 @@ int rife_plan_set_frame_size(rife_plan* p, int h, int w) {
   return RIFE_OK;
 }
 
+int rife_plan_set_chunk(rife_plan* p, int pairs) {
+  if (!p) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_chunk: null plan");
+  if (pairs < 0) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_chunk: pairs must be >= 0 (0 = default)");
+  p->chunk = pairs;
+  return RIFE_OK;
+}
+
 int rife_plan_set_profiling(rife_plan* p, int enable) {
   if (!p) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_set_profiling: null plan");
   p->profile = enable != 0;
@@ -495,6 +504,12 @@ static bool narrow_off() {
   // test hooks: 16-channel tmp for the last block too / generic eval kernel instead of the fast merge
   static const bool off = getenv("RIFE_NO_NARROW_LAST") != nullptr || getenv("RIFE_NO_FAST_MERGE") != nullptr;
   return off;
+}
+
+static int default_chunk_pairs() {
+  // pairs per pass of the 1/2- and full-resolution stages; measured on B200 at 1080p
+  static const int v = getenv("RIFE_CHUNK_PAIRS") ? atoi(getenv("RIFE_CHUNK_PAIRS")) : 0;
+  return v;
 }
 
 static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
@@ -552,26 +567,44 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   }
 
   // ---- 5 IFBlocks (IFNet_HDv3.py:139-157)
+  // The blocks that work at <= 1/4 resolution touch < 7 % of the pixels and are bound by per-layer latency: they run once
+  // over the whole batch.  The stages at 1/2 and full resolution are bound by HBM / L2 and run in passes of `chunk` pairs
+  // through the same (chunk-sized, L2-friendlier) work buffers.  One pass = the whole batch unless the caller asked for
+  // per-level outputs.
   TmpLevel lev[5];
   float* fbuf = (float*)p->at(L.fbuf);
+  const bool per_level_outputs = outs->mask || outs->flow[0] || outs->flow[1] || outs->flow[2] || outs->flow[3] ||
+                                 outs->flow[4] || outs->warped0[0] || outs->warped0[1] || outs->warped0[2] ||
+                                 outs->warped0[3] || outs->warped0[4] || outs->warped1[0] || outs->warped1[1] ||
+                                 outs->warped1[2] || outs->warped1[3] || outs->warped1[4];
+  int chunk_pairs = p->chunk > 0 ? p->chunk : default_chunk_pairs();
+  if (per_level_outputs || c.any_up || chunk_pairs <= 0 || chunk_pairs > p->P) chunk_pairs = p->P;
+  int first_chunked = 5;  // blocks [first_chunked, 5) run per pass
+  if (chunk_pairs < p->P)
+    for (int i = 4; i >= 1 && L.s[i] <= 2 && L.u[i] == 1; --i) first_chunked = i;
+  const size_t io_esz = io_dtype == RIFE_F32 ? 4 : (io_dtype == RIFE_F16 ? 2 : 1);
+  const size_t out_frame = (size_t)p->C * (p->fh ? p->fh : H) * (p->fw ? p->fw : W) * io_esz;
+
   int fbuf_levels = 0;  // number of levels summed in fbuf (0 = nothing stored yet)
-  for (int i = 0; i < 5; ++i) {
+  auto run_block = [&](int i, const PixelCtx& cc, int b0, bool last_pass) -> int {
+    // block i for the outputs [b0, b0 + cc.B): cc is the (sub-)batch view, lev[j < i] already point at its tmp levels
     const int s = L.s[i], up = L.u[i], c_ = kBlockC[i];
     const int hs = H / s * up, wsz = W / s * up;
+    const int Bc = cc.B;
     const std::string bn = "b" + std::to_string(i);
     const int hkm = half_act ? w->blk_hk[i] : 0;
     const bool hk = hkm == 1;            // conv0.* on the halo kernel (planar-8 block input)
     const bool hk_tail = hkm != 0;       // ResConv x8 + lastconv on the halo kernel
     if (up > 1) {
       // scale_list[i] < 1: the block input is the full-resolution one, bilinearly up-sampled (IFNet_HDv3.py:79-81)
-      RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, 1, p->at(L.xfull), false, fbuf, fbuf_levels, i > 0, st));
-      RIFE_STAGE(bn + ".upsample", launch_upsample_xin(c, p->at(L.xfull), p->at(L.xin), up, hk, st));
+      RIFE_STAGE(bn + ".input", launch_block_input(cc, i, lev, 1, p->at(L.xfull), false, fbuf, fbuf_levels, i > 0, st));
+      RIFE_STAGE(bn + ".upsample", launch_upsample_xin(cc, p->at(L.xfull), p->at(L.xin), up, hk, st));
     } else {
-      RIFE_STAGE(bn + ".input", launch_block_input(c, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
+      RIFE_STAGE(bn + ".input", launch_block_input(cc, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
     }
     if (i > 0 && s <= 2) fbuf_levels = i;  // every full-resolution pixel was sampled: fbuf = flow after blocks [0, i)
     ConvIO io;
-    io.B = B;
+    io.B = Bc;
     // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
     io.H = hs / 2; io.W = wsz / 2; io.in = p->at(L.xin); io.out = p->at(L.c0); io.epi = EPI_LRELU_S2D; io.out_c = c_ / 2;
     RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, hk, st));
@@ -587,12 +620,16 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
       RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk_tail, st));
       void* t = cur; cur = nxt; nxt = t;
     }
-    // lastconv + PixelShuffle -> tmp_i at (hs, wsz)
-    io.in = cur; io.res = nullptr; io.out = p->at(L.tmp[i]); io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
-    lev[i].ptr = p->at(L.tmp[i]); lev[i].h = hs; lev[i].w = wsz; lev[i].s = up > 1 ? -up : s; lev[i].pitch = TMP_C;
+    // lastconv + PixelShuffle -> tmp_i at (hs, wsz): the batch's own slice for a whole-batch block, the front of the
+    // buffer for a per-pass block
+    const bool chunked = i >= first_chunked;
+    const size_t tmp_item = (size_t)hs * wsz * TMP_C * E;
+    char* tmp_ptr = (char*)p->at(L.tmp[i]) + (chunked ? 0 : (size_t)b0 * tmp_item);
+    io.in = cur; io.res = nullptr; io.out = tmp_ptr; io.epi = EPI_PS; io.out_c = TMP_C; io.co_per_par = kLastCo;
+    lev[i].ptr = tmp_ptr; lev[i].h = hs; lev[i].w = wsz; lev[i].s = up > 1 ? -up : s; lev[i].pitch = TMP_C;
     // Model.inference (only `merged` wanted) at scale <= 1: the merge kernel needs flow + mask of the last block only
     const bool narrow = i == 4 && hk_tail && w->blk[i].has_last8 && !narrow_off() && s == 1 && up == 1 && fbuf_levels == 4 &&
-                        !c.any_up && outs->merged && !outs->mask && !outs->flow[4] && !outs->warped0[4] && !outs->warped1[4];
+                        !c.any_up && outs->merged && !per_level_outputs;
     if (narrow) {
       io.epi = EPI_PS8; io.out_c = 8;
       lev[i].pitch = 8;
@@ -607,10 +644,32 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     eo.warped1 = outs->warped1[i];
     if (i == 4) {
       eo.mask = outs->mask;
-      eo.merged = outs->merged;
+      eo.merged = outs->merged ? (char*)outs->merged + (size_t)b0 * out_frame : nullptr;
     }
     if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged)
-      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(c, i + 1, lev, eo, io_dtype, fbuf, fbuf_levels, st));
+      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(cc, i + 1, lev, eo, io_dtype, fbuf, fbuf_levels, st));
+    (void)last_pass;
+    return RIFE_OK;
+  };
+
+  for (int i = 0; i < first_chunked; ++i) RIFE_TRY(run_block(i, c, 0, true));
+  if (first_chunked < 5) {
+    const int fb0 = fbuf_levels;
+    const void* lev_base[5];
+    for (int j = 0; j < first_chunked; ++j) lev_base[j] = lev[j].ptr;
+    for (int p0 = 0; p0 < p->P; p0 += chunk_pairs) {
+      const int np = std::min(chunk_pairs, p->P - p0);
+      PixelCtx cc = c;
+      cc.B = np * p->T;
+      const int b0 = p0 * p->T;
+      cc.tstep = c.tstep + b0;
+      cc.src0 = (const char*)c.src0 + (size_t)p0 * H * W * SRC_C * E;
+      cc.src1 = (const char*)c.src1 + (size_t)p0 * H * W * SRC_C * E;
+      for (int j = 0; j < first_chunked; ++j)
+        lev[j].ptr = (const char*)lev_base[j] + (size_t)b0 * lev[j].h * lev[j].w * TMP_C * E;
+      fbuf_levels = fb0;
+      for (int i = first_chunked; i < 5; ++i) RIFE_TRY(run_block(i, cc, b0, p0 + np >= p->P));
+    }
   }
   return RIFE_OK;
 }

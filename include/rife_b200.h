@@ -97,6 +97,10 @@ int rife_plan_destroy(rife_plan* p);
  * (h, w) -- the F.pad / [:h, :w] the reference's callers wrap around Model.inference (inference_img.py:62-67,111,
  * inference_video.py:199-202,267). */
 int rife_plan_set_frame_size(rife_plan* p, int h, int w);
+/* Batch scheduling of one call: the blocks working at <= 1/4 resolution (latency-bound, < 7 % of the pixels) always run
+ * over the whole batch; the 1/2- and full-resolution stages (HBM / L2-bound) run in passes of `pairs` frame pairs through
+ * the same work buffers.  0 = library default (env RIFE_CHUNK_PAIRS, else the whole batch).  Results do not depend on it. */
+int rife_plan_set_chunk(rife_plan* p, int pairs);
 /* Per-kernel timing: when enabled, every launch of the pipeline is bracketed by CUDA events on the launch
  * stream.  After the stream has been synchronised, rife_plan_get_profile returns (up to `cap`) the stage names
  * (pointers valid until the next run) and durations in ms of the LAST run; return value = number of stages. */

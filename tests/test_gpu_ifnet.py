@@ -380,6 +380,32 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
     assert (merged[4].float().cpu() - outs[0].float()).abs().max() < 4e-3
 
 
+def test_chunked_passes_are_bit_identical(pkg):
+    """rife_plan_set_chunk: the 1/2- and full-resolution stages run in passes of n pairs (ragged last pass included),
+    the coarse blocks over the whole batch; the frames do not change by a bit.  Also with several timesteps per pair."""
+    lib = pkg._lib.load()
+    m = seeded_model(pkg, AMP, "fp16")
+    g = torch.Generator().manual_seed(33)
+    a, b = torch.rand(5, 3, 128, 192, generator=g).to(DEV).half(), torch.rand(5, 3, 128, 192, generator=g).to(DEV).half()
+    net = m.flownet
+    want = m.inference(a, b, 0.3).clone()
+    want_multi = m.inference_multi(a, b, (0.25, 0.75)).clone()
+    for n in (1, 2, 4):
+        for pl in net._plans.values():
+            pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, n))
+        assert torch.equal(m.inference(a, b, 0.3), want), n
+        assert torch.equal(m.inference_multi(a, b, (0.25, 0.75)), want_multi), n
+    for pl in net._plans.values():
+        pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, 0))
+    m32 = seeded_model(pkg, AMP, "fp32")
+    w32 = m32.inference(a.float(), b.float(), 0.3).clone()
+    for pl in m32.flownet._plans.values():
+        pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, 2))
+    assert torch.equal(m32.inference(a.float(), b.float(), 0.3), w32)
+    for pl in m32.flownet._plans.values():
+        pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, 0))
+
+
 def test_unpadded_frames_pad_and_crop(pkg):
     """Callers of the reference pad to a multiple of 32/64 and crop (inference_img.py:62-67,111); pad=True does both
     inside the kernels and must equal the explicit pad -> inference -> crop."""

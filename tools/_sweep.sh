@@ -1,8 +1,10 @@
-python bench.py > gpurun_out/bench_v18.json 2> gpurun_out/bench_v18.err
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_pre_ncu.json 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v18.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-python tools/ncu_target.py hdv3 8 > gpurun_out/ncu_target.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -o /tmp/full_v18 -f python tools/ncu_target.py hdv3 8 > gpurun_out/ncu_full.log 2>&1
-ncu -i /tmp/full_v18.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/full_v18_raw.csv.gz
-gzip -c /tmp/full_v18.ncu-rep > gpurun_out/full_v18.ncu-rep.gz
-du -sh gpurun_out; ls -la gpurun_out | tail -8
+python -m pytest tests -m gpu -x -q > gpurun_out/t_gpu.log 2>&1; tail -3 gpurun_out/t_gpu.log
+run() { tag=$1; shift; python bench.py --steps 10 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/ck_$tag.json 2> gpurun_out/ck_$tag.err; }
+run p12 --pairs 12
+run p24c12 --pairs 24 --chunk 12
+run p24c8 --pairs 24 --chunk 8
+run p24c6 --pairs 24 --chunk 6
+run p24c4 --pairs 24 --chunk 4
+run p32c8 --pairs 32 --chunk 8
+run p12c6 --pairs 12 --chunk 6
+run p12c4 --pairs 12 --chunk 4
