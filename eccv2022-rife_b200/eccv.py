@@ -34,9 +34,9 @@ def _deconv_prelu(cin, cout):
 class IFBlock(nn.Module):
     """Parameters of model/IFNet.py:20-37."""
 
-    def __init__(self, in_planes, c=64):
+    def __init__(self, in_planes, c=64, stride0=2):
         super().__init__()
-        self.conv0 = nn.Sequential(_conv_prelu(in_planes, c // 2, 2), _conv_prelu(c // 2, c, 2))
+        self.conv0 = nn.Sequential(_conv_prelu(in_planes, c // 2, stride0), _conv_prelu(c // 2, c, 2))
         self.convblock = nn.Sequential(*[_conv_prelu(c, c) for _ in range(8)])
         self.lastconv = nn.ConvTranspose2d(c, 5, 4, 2, 1)
 
@@ -56,9 +56,9 @@ _C = 16
 class Contextnet(nn.Module):
     """Parameters of model/refine.py:36-42."""
 
-    def __init__(self):
+    def __init__(self, stride1=2):
         super().__init__()
-        self.conv1 = Conv2(3, _C)
+        self.conv1 = Conv2(3, _C, stride1)
         self.conv2 = Conv2(_C, 2 * _C)
         self.conv3 = Conv2(2 * _C, 4 * _C)
         self.conv4 = Conv2(4 * _C, 8 * _C)
@@ -67,9 +67,9 @@ class Contextnet(nn.Module):
 class Unet(nn.Module):
     """Parameters of model/refine.py:59-70."""
 
-    def __init__(self):
+    def __init__(self, two_r=False):
         super().__init__()
-        self.down0 = Conv2(17, 2 * _C)
+        self.down0 = Conv2(17, 2 * _C, 1 if two_r else 2)
         self.down1 = Conv2(4 * _C, 4 * _C)
         self.down2 = Conv2(8 * _C, 8 * _C)
         self.down3 = Conv2(16 * _C, 16 * _C)
@@ -77,7 +77,7 @@ class Unet(nn.Module):
         self.up1 = _deconv_prelu(16 * _C, 4 * _C)
         self.up2 = _deconv_prelu(8 * _C, 2 * _C)
         self.up3 = _deconv_prelu(4 * _C, _C)
-        self.conv = nn.Conv2d(_C, 3, 3, 1, 1)
+        self.conv = nn.Conv2d(_C, 3, 3, 2 if two_r else 1, 1)
 
 
 def _pad8(c):
@@ -132,17 +132,19 @@ class IFNet(nn.Module):
     """Drop-in for `model.IFNet.IFNet` (inference branch: `x` holds img0, img1 and no ground truth)."""
 
     TIMESTEP_PLANE = 0      # IFNet_m adds one constant timestep channel after img1 (model/IFNet_m.py:56-59,64)
+    TWO_R = False           # IFNet_2R: the stride variant of model/IFNet_2R.py + model/refine_2R.py
 
     def __init__(self, precision="auto"):
         super().__init__()
         self.precision = _precision_from_env(precision)
         tp = self.TIMESTEP_PLANE
-        self.block0 = IFBlock(6 + tp, c=240)          # model/IFNet.py:56-61: same construction order => same default init
-        self.block1 = IFBlock(13 + 4 + tp, c=150)
-        self.block2 = IFBlock(13 + 4 + tp, c=90)
-        self.block_tea = IFBlock(16 + 4 + tp, c=90)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
-        self.contextnet = Contextnet()
-        self.unet = Unet()
+        s0 = 1 if self.TWO_R else 2                   # model/IFNet_2R.py:24
+        self.block0 = IFBlock(6 + tp, c=240, stride0=s0)   # model/IFNet.py:56-61: same construction order => same default init
+        self.block1 = IFBlock(13 + 4 + tp, c=150, stride0=s0)
+        self.block2 = IFBlock(13 + 4 + tp, c=90, stride0=s0)
+        self.block_tea = IFBlock(16 + 4 + tp, c=90, stride0=s0)   # teacher: parameters only (training branch, model/IFNet.py:88-97)
+        self.contextnet = Contextnet(s0)
+        self.unet = Unet(self.TWO_R)
         self._layers = {}      # precision -> {name: _Layer}
         self._arenas = {}      # (device, B, H, W, fp16?, scales) -> work tensors of one forward, in call order
         self._stamp = None
@@ -191,22 +193,25 @@ class IFNet(nn.Module):
             for i, blk in enumerate((self.block0, self.block1, self.block2)):
                 c = blk.lastconv.weight.shape[0]
                 cin = blk.conv0[0][0].weight.shape[1]
-                L[f"b{i}.c00"] = mk(1, blk.conv0[0][0], blk.conv0[0][1], _pad8(cin))
+                L[f"b{i}.c00"] = (mk(0, blk.conv0[0][0], blk.conv0[0][1], pc(cin)) if self.TWO_R
+                                  else mk(1, blk.conv0[0][0], blk.conv0[0][1], _pad8(cin)))
                 L[f"b{i}.c01"] = mk(1, blk.conv0[1][0], blk.conv0[1][1], pc(c // 2))
                 for j in range(8):
                     L[f"b{i}.cb{j}"] = mk(0, blk.convblock[j][0], blk.convblock[j][1], pc(c))
                 L[f"b{i}.last"] = mk(2, blk.lastconv, None, pc(c))
             cn = self.contextnet
             for k, (m, cin) in enumerate(((cn.conv1, 3), (cn.conv2, _C), (cn.conv3, 2 * _C), (cn.conv4, 4 * _C))):
-                L[f"ctx{k}.1"] = mk(1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"ctx{k}.1"] = (mk(0, m.conv1[0], m.conv1[1], pc(cin)) if (self.TWO_R and k == 0)
+                                  else mk(1, m.conv1[0], m.conv1[1], _pad8(cin)))
                 L[f"ctx{k}.2"] = mk(0, m.conv2[0], m.conv2[1], pc(m.conv2[0].weight.shape[1]))
             un = self.unet
             for k, (m, cin) in enumerate(((un.down0, 17), (un.down1, 4 * _C), (un.down2, 8 * _C), (un.down3, 16 * _C))):
-                L[f"dn{k}.1"] = mk(1, m.conv1[0], m.conv1[1], _pad8(cin))
+                L[f"dn{k}.1"] = (mk(0, m.conv1[0], m.conv1[1], pc(cin)) if (self.TWO_R and k == 0)
+                                  else mk(1, m.conv1[0], m.conv1[1], _pad8(cin)))
                 L[f"dn{k}.2"] = mk(0, m.conv2[0], m.conv2[1], pc(m.conv2[0].weight.shape[1]))
             for k, m in enumerate((un.up0, un.up1, un.up2, un.up3)):
                 L[f"up{k}"] = mk(2, m[0], m[1], m[0].weight.shape[0])
-            L["out"] = mk(0, un.conv, None, _C)
+            L["out"] = mk(1 if self.TWO_R else 0, un.conv, None, _C)      # refine_2R.py:71: stride 2 (from 2x resolution)
         self._layers[prec] = L
         return L
 
@@ -235,7 +240,8 @@ class IFNet(nn.Module):
                     raise ValueError("tensor timestep must broadcast as (B,1,1,1)")
             else:
                 tvals = [float(timestep)] * B
-        need = int(max(16, 4 * max(s3)))
+        two_r = self.TWO_R
+        need = int(max(8, 2 * max(s3))) if two_r else int(max(16, 4 * max(s3)))
         if H % need or W % need:
             raise RuntimeError(f"ECCV IFNet: H and W must be multiples of {need} for scale list {list(scale)} (got {H}x{W})")
         lib = _lib.load()
@@ -288,9 +294,18 @@ class IFNet(nn.Module):
                 chk(lib.rife_nhwc_s2d(src.data_ptr(), _dt(src), src.shape[-1], soff, c, dst.data_ptr(), _dt(dst), cpad, B, h, w, st))
                 return dst
 
-            def conv2(prefix, src, c_in, dst, doff, soff=0):
-                """Conv2 (model/refine.py:24-33): stride-2 conv + PReLU, conv + PReLU; result into dst[..., doff:]."""
+            def conv2(prefix, src, c_in, dst, doff, soff=0, stride1=False):
+                """Conv2 (model/refine.py:24-33): stride-2 conv + PReLU, conv + PReLU; result into dst[..., doff:].
+                stride1: the first conv of refine_2R.py's Contextnet.conv1 / Unet.down0."""
                 l1, l2 = L[prefix + ".1"], L[prefix + ".2"]
+                if stride1:
+                    h, w = src.shape[1], src.shape[2]
+                    xi = z(h, w, l1.cin_store)
+                    resize(src, soff, c_in, xi, 0)                                    # same size: a copy into the conv's
+                    a = z(h, w, l2.cin_store)                                         # own (padded, activation-dtype) tensor
+                    l1.run(xi, a, h, w, 2, stream=st)
+                    l2.run(a, dst, h, w, 2, out_off=doff, stream=st)
+                    return
                 h, w = src.shape[1] // 2, src.shape[2] // 2
                 a = z(h, w, l2.cin_store)
                 l1.run(s2d(src, c_in, l1.cin_store, soff), a, h, w, 2, stream=st)
@@ -306,7 +321,7 @@ class IFNet(nn.Module):
                 s = int(s3[i])
                 hs, ws = H // s, W // s
                 cin = (6 if i == 0 else 17) + tp
-                xin = z(hs, ws, _pad8(cin))
+                xin = z(hs, ws, pc(cin) if two_r else _pad8(cin))
                 if tp:                                                                # IFNet_m.py:78,82: [img0,img1,t,...]
                     resize(full, 0, 6, xin, 0)
                     if len(set(tvals)) == 1:
@@ -323,19 +338,26 @@ class IFNet(nn.Module):
                     resize(full, 0, 13, xin, 0)                                       # cat(img0,img1,warped0,warped1,mask)
                     resize(full, 13, 4, xin, 13, mul=1.0 / s)                         # :42 interp(flow) * 1/scale
                 c = (240, 150, 90)[i]
-                a = z(hs // 2, ws // 2, pc(c // 2))
-                L[f"b{i}.c00"].run(s2d(xin, cin, _pad8(cin)), a, hs // 2, ws // 2, 2, stream=st)
-                bq = z(hs // 4, ws // 4, pc(c))
-                L[f"b{i}.c01"].run(s2d(a, pc(c // 2), pc(c // 2)), bq, hs // 4, ws // 4, 2, stream=st)
-                pp = (z(hs // 4, ws // 4, pc(c)), z(hs // 4, ws // 4, pc(c)))
+                if two_r:                                                             # IFNet_2R.py:24: conv0[0] at stride 1
+                    a = z(hs, ws, pc(c // 2))
+                    L[f"b{i}.c00"].run(xin, a, hs, ws, 2, stream=st)
+                    hb, wb = hs // 2, ws // 2
+                else:
+                    a = z(hs // 2, ws // 2, pc(c // 2))
+                    L[f"b{i}.c00"].run(s2d(xin, cin, _pad8(cin)), a, hs // 2, ws // 2, 2, stream=st)
+                    hb, wb = hs // 4, ws // 4
+                bq = z(hb, wb, pc(c))
+                L[f"b{i}.c01"].run(s2d(a, pc(c // 2), pc(c // 2)), bq, hb, wb, 2, stream=st)
+                pp = (z(hb, wb, pc(c)), z(hb, wb, pc(c)))
                 y = bq
                 for j in range(8):                                                    # :45-46 convblock(x) + x
                     dst = pp[j & 1]
-                    L[f"b{i}.cb{j}"].run(y, dst, hs // 4, ws // 4, 3 if j == 7 else 2, res=bq if j == 7 else None, stream=st)
+                    L[f"b{i}.cb{j}"].run(y, dst, hb, wb, 3 if j == 7 else 2, res=bq if j == 7 else None, stream=st)
                     y = dst
-                tmp = e(hs // 2, ws // 2, 8, f32)                                     # flow / mask head: fp32 in both modes
-                L[f"b{i}.last"].run(y, tmp, hs // 4, ws // 4, 0, stream=st)           # :47 lastconv -> 5 ch at 1/(2s)
-                resize(tmp, 0, 4, full, 13, mul=float(2 * s), acc=int(i > 0))         # :48-49,76: flow (+)= up(tmp)*scale*2
+                tmp = e(2 * hb, 2 * wb, 8, f32)                                       # flow / mask head: fp32 in both modes
+                L[f"b{i}.last"].run(y, tmp, hb, wb, 0, stream=st)                     # :47 lastconv -> 5 ch at 1/(2s) (2R: 1/s)
+                up_mul = float(s if two_r else 2 * s)                                 # :48-49 (IFNet_2R.py:48-49: scale only)
+                resize(tmp, 0, 4, full, 13, mul=up_mul, acc=int(i > 0))               # :76: flow (+)= up(tmp) * up factor
                 resize(tmp, 4, 1, full, 12, mul=1.0, acc=int(i > 0))                  # :50,77: mask (+)= up(tmp)
                 warp(full, 0, 3, full, 13, full, 6)                                   # :82
                 warp(full, 3, 3, full, 15, full, 9)                                   # :83
@@ -353,13 +375,18 @@ class IFNet(nn.Module):
             chk(lib.rife_nhwc_to_nchw(full.data_ptr(), _dt(full), 24, 12, mask_sig.data_ptr(), io, B, 1, H, W, 1, st))
 
             # Contextnet on both frames (model/refine.py:44-57), features warped straight into the Unet's cat slices
-            d1, d2, d3, u0 = z(H // 2, W // 2, 64), z(H // 4, W // 4, 128), z(H // 8, W // 8, 256), z(H // 16, W // 16, 512)
+            q = 1 if two_r else 2                         # refine_2R.py: every level of the refinement one octave finer
+            d1, d2, d3, u0 = (z(H // q, W // q, 64), z(H // (2 * q), W // (2 * q), 128), z(H // (4 * q), W // (4 * q), 256),
+                              z(H // (8 * q), W // (8 * q), 512))
             for f, (img_off, flow_off) in enumerate(((0, 13), (3, 15))):
-                fl = z(H // 2, W // 2, 8, f32)
-                resize(full, flow_off, 2, fl, 0, mul=0.5)
-                feat = e(H // 2, W // 2, 16)
-                conv2("ctx0", full, 3, feat, 0, soff=img_off)
-                warp(feat, 0, 16, fl, 0, d1, 32 + 16 * f)
+                if two_r:                                                             # refine_2R.py:45-48: full-res flow
+                    fl, foff = full, flow_off
+                else:
+                    fl, foff = z(H // 2, W // 2, 8, f32), 0
+                    resize(full, flow_off, 2, fl, 0, mul=0.5)
+                feat = e(H // q, W // q, 16)
+                conv2("ctx0", full, 3, feat, 0, soff=img_off, stride1=two_r)
+                warp(feat, 0, 16, fl, foff, d1, 32 + 16 * f)
                 prev, prev_c = feat, 16
                 for k, (dst, base) in enumerate(((d2, 64), (d3, 128), (u0, 256))):
                     cc = 32 << k
@@ -367,26 +394,29 @@ class IFNet(nn.Module):
                     nxt = e(h, w, cc)
                     conv2(f"ctx{k + 1}", prev, prev_c, nxt, 0)
                     fl2 = z(h, w, 8, f32)
-                    resize(fl, 0, 2, fl2, 0, mul=0.5)
+                    resize(fl, foff, 2, fl2, 0, mul=0.5)
                     warp(nxt, 0, cc, fl2, 0, dst, base + cc * f)
-                    prev, prev_c, fl = nxt, cc, fl2
+                    prev, prev_c, fl, foff = nxt, cc, fl2, 0
 
             # Unet (model/refine.py:72-82)
-            conv2("dn0", full, 17, d1, 0)
+            conv2("dn0", full, 17, d1, 0, stride1=two_r)
             conv2("dn1", d1, 64, d2, 0)
             conv2("dn2", d2, 128, d3, 0)
             conv2("dn3", d3, 256, u0, 0)
-            u1, u2, u3 = e(H // 8, W // 8, 256), e(H // 4, W // 4, 128), e(H // 2, W // 2, 64)
-            L["up0"].run(u0, u1, H // 16, W // 16, 2, stream=st)
+            u1, u2, u3 = e(H // (4 * q), W // (4 * q), 256), e(H // (2 * q), W // (2 * q), 128), e(H // q, W // q, 64)
+            L["up0"].run(u0, u1, H // (8 * q), W // (8 * q), 2, stream=st)
             resize(d3, 0, 128, u1, 128)                                               # cat((x, s2))
-            L["up1"].run(u1, u2, H // 8, W // 8, 2, stream=st)
+            L["up1"].run(u1, u2, H // (4 * q), W // (4 * q), 2, stream=st)
             resize(d2, 0, 64, u2, 64)
-            L["up2"].run(u2, u3, H // 4, W // 4, 2, stream=st)
+            L["up2"].run(u2, u3, H // (2 * q), W // (2 * q), 2, stream=st)
             resize(d1, 0, 32, u3, 32)
-            xo = e(H, W, 16)
-            L["up3"].run(u3, xo, H // 2, W // 2, 2, stream=st)
+            xo = e(2 * H // q, 2 * W // q, 16)
+            L["up3"].run(u3, xo, H // q, W // q, 2, stream=st)
             ref = e(H, W, pc(3), f32)
-            L["out"].run(xo, ref, H, W, 0, stream=st)
+            if two_r:
+                L["out"].run(s2d(xo, 16, 16), ref, H, W, 0, stream=st)                # refine_2R.py:71: stride 2 back to (H, W)
+            else:
+                L["out"].run(xo, ref, H, W, 0, stream=st)
             mg = torch.empty((B, 3, H, W), dtype=out_dt, device=dev)
             chk(lib.rife_eccv_merge(full.data_ptr(), 24, 6, full.data_ptr(), 24, 9, full.data_ptr(), 24, 12, _dt(full),
                                     ref.data_ptr(), _dt(ref), ref.shape[-1], 0, mg.data_ptr(), io, B, H, W, st))
@@ -397,6 +427,13 @@ class IFNet(nn.Module):
 class IFNet_m(IFNet):
     """Drop-in for `model.IFNet_m.IFNet_m`: the arbitrary-timestep variant (benchmark/HD_multi_4X.py:16)."""
     TIMESTEP_PLANE = 1
+
+
+class IFNet_2R(IFNet):
+    """Drop-in for `model.IFNet_2R.IFNet` (with `model.refine_2R`): IFBlock.conv0[0], Contextnet.conv1 and Unet.down0 at
+    stride 1, the Unet's output conv at stride 2 -- every block and the refinement work one octave finer.  Same 190
+    tensors and default init as IFNet; no Model class of the reference selects it, so it is used through forward()."""
+    TWO_R = True
 
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")

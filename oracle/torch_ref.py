@@ -90,40 +90,44 @@ def _cp(sd, p, x, stride=1):
     return F.prelu(F.conv2d(x, sd[p + "0.weight"], sd[p + "0.bias"], stride, 1), sd[p + "1.weight"])
 
 
-def eccv_ifblock(sd, p, x, flow, scale):
-    """model/IFNet.py:39-51."""
+def eccv_ifblock(sd, p, x, flow, scale, two_r=False):
+    """model/IFNet.py:39-51; two_r: model/IFNet_2R.py:24,48-49 (conv0[0] stride 1, tmp up-sampled by `scale` only)."""
     if scale != 1:
         x = F.interpolate(x, scale_factor=1. / scale, mode="bilinear", align_corners=False)
     if flow is not None:
         flow = F.interpolate(flow, scale_factor=1. / scale, mode="bilinear", align_corners=False) * 1. / scale
         x = torch.cat((x, flow), 1)
-    x = _cp(sd, p + "conv0.1.", _cp(sd, p + "conv0.0.", x, 2), 2)
+    x = _cp(sd, p + "conv0.1.", _cp(sd, p + "conv0.0.", x, 1 if two_r else 2), 2)
     y = x
     for j in range(8):
         y = _cp(sd, f"{p}convblock.{j}.", y)
     x = y + x
     tmp = F.conv_transpose2d(x, sd[p + "lastconv.weight"], sd[p + "lastconv.bias"], 2, 1)
-    tmp = F.interpolate(tmp, scale_factor=scale * 2, mode="bilinear", align_corners=False)
-    return tmp[:, :4] * scale * 2, tmp[:, 4:5]
+    up = scale if two_r else scale * 2
+    tmp = F.interpolate(tmp, scale_factor=up, mode="bilinear", align_corners=False)
+    return tmp[:, :4] * up, tmp[:, 4:5]
 
 
-def _conv2(sd, p, x):
-    return _cp(sd, p + "conv2.", _cp(sd, p + "conv1.", x, 2))
+def _conv2(sd, p, x, stride=2):
+    return _cp(sd, p + "conv2.", _cp(sd, p + "conv1.", x, stride))
 
 
-def eccv_contextnet(sd, x, flow, p="contextnet."):
+def eccv_contextnet(sd, x, flow, p="contextnet.", two_r=False):
+    """model/refine.py:44-57; two_r: model/refine_2R.py:40,45-48 (conv1 stride 1, f1 warped by the full-resolution flow)."""
     out = []
     for k in range(1, 5):
-        x = _conv2(sd, f"{p}conv{k}.", x)
-        flow = F.interpolate(flow, scale_factor=0.5, mode="bilinear", align_corners=False, recompute_scale_factor=False) * 0.5
+        x = _conv2(sd, f"{p}conv{k}.", x, 1 if (two_r and k == 1) else 2)
+        if not (two_r and k == 1):
+            flow = F.interpolate(flow, scale_factor=0.5, mode="bilinear", align_corners=False, recompute_scale_factor=False) * 0.5
         out.append(warp(x, flow))
     return out
 
 
-def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet."):
+def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet.", two_r=False):
+    """model/refine.py:72-82; two_r: model/refine_2R.py:63,71 (down0 stride 1, the output conv stride 2)."""
     def deconv(q, x):
         return F.prelu(F.conv_transpose2d(x, sd[q + "0.weight"], sd[q + "0.bias"], 2, 1), sd[q + "1.weight"])
-    s0 = _conv2(sd, p + "down0.", torch.cat((img0, img1, w0, w1, mask, flow), 1))
+    s0 = _conv2(sd, p + "down0.", torch.cat((img0, img1, w0, w1, mask, flow), 1), 1 if two_r else 2)
     s1 = _conv2(sd, p + "down1.", torch.cat((s0, c0[0], c1[0]), 1))
     s2 = _conv2(sd, p + "down2.", torch.cat((s1, c0[1], c1[1]), 1))
     s3 = _conv2(sd, p + "down3.", torch.cat((s2, c0[2], c1[2]), 1))
@@ -131,13 +135,14 @@ def eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, p="unet."):
     x = deconv(p + "up1.", torch.cat((x, s2), 1))
     x = deconv(p + "up2.", torch.cat((x, s1), 1))
     x = deconv(p + "up3.", torch.cat((x, s0), 1))
-    return torch.sigmoid(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], 1, 1))
+    return torch.sigmoid(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], 2 if two_r else 1, 1))
 
 
 @torch.no_grad()
-def eccv_ifnet_forward(sd, x, scale=(4, 2, 1), timestep=None):
+def eccv_ifnet_forward(sd, x, scale=(4, 2, 1), timestep=None, two_r=False):
     """model/IFNet.py:63-108, inference branch; with `timestep` (float or (B,1,1,1) tensor) the arbitrary-timestep
-    variant model/IFNet_m.py:63-112, whose blocks take a constant timestep plane after img1."""
+    variant model/IFNet_m.py:63-112, whose blocks take a constant timestep plane after img1; two_r: the
+    model/IFNet_2R.py + model/refine_2R.py variant (same 190 tensors, different strides)."""
     img0, img1 = x[:, :3], x[:, 3:6]
     tp = () if timestep is None else ((x[:, :1].clone() * 0 + 1) * timestep,)       # IFNet_m.py:64
     flow_list, merged, mask_list = [], [], []
@@ -145,18 +150,19 @@ def eccv_ifnet_forward(sd, x, scale=(4, 2, 1), timestep=None):
     for i in range(3):
         p = f"block{i}."
         if flow is not None:
-            fd, md = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp + (w0, w1, mask), 1), flow, scale[i])
+            fd, md = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp + (w0, w1, mask), 1), flow, scale[i], two_r)
             flow, mask = flow + fd, mask + md
         else:
-            flow, mask = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp, 1), None, scale[i])
+            flow, mask = eccv_ifblock(sd, p, torch.cat((img0, img1) + tp, 1), None, scale[i], two_r)
         mask_list.append(torch.sigmoid(mask))
         flow_list.append(flow)
         w0, w1 = warp(img0, flow[:, :2]), warp(img1, flow[:, 2:4])
         merged.append((w0, w1))
     for i in range(3):
         merged[i] = merged[i][0] * mask_list[i] + merged[i][1] * (1 - mask_list[i])
-    c0, c1 = eccv_contextnet(sd, img0, flow[:, :2]), eccv_contextnet(sd, img1, flow[:, 2:4])
-    tmp = eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1)
+    c0 = eccv_contextnet(sd, img0, flow[:, :2], two_r=two_r)
+    c1 = eccv_contextnet(sd, img1, flow[:, 2:4], two_r=two_r)
+    tmp = eccv_unet(sd, img0, img1, w0, w1, mask, flow, c0, c1, two_r=two_r)
     merged[2] = torch.clamp(merged[2] + (tmp[:, :3] * 2 - 1), 0, 1)
     return flow_list, mask_list[2], merged
 

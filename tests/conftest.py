@@ -93,6 +93,27 @@ def seeded_eccv_m(pkg, amp=AMP):
     return _eccv_m[amp]
 
 
+_eccv_2r = {}
+
+
+def seeded_eccv_2r(pkg, amp=AMP):
+    """IFNet_2R mirror (model/IFNet_2R.py + model/refine_2R.py), seeded like tests/golden/make_golden.py:case_eccv_2r.
+    Same tensors and default init as the ECCV net (sha256 in tests/golden/weights_eccv_seed1234.json)."""
+    import torch
+    if amp not in _eccv_2r:
+        torch.manual_seed(1234)
+        net = pkg.eccv.IFNet_2R().to("cuda" if torch.cuda.is_available() else "cpu")
+        net.eval()
+        net._sha_state = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+        if amp != 1.0:
+            with torch.no_grad():
+                for b in (net.block0, net.block1, net.block2):
+                    b.lastconv.weight.mul_(amp)
+            net.invalidate()
+        _eccv_2r[amp] = net
+    return _eccv_2r[amp]
+
+
 def seeded_eccv(pkg, amp=AMP):
     """ECCV-paper model mirror under torch.manual_seed(1234) (sha256 in tests/golden/weights_eccv_seed1234.json);
     `amp` scales block{0,1,2}.lastconv.weight as tests/golden/make_golden.py:case_eccv does."""

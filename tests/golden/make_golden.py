@@ -261,6 +261,30 @@ def case_eccv_m():
     save("eccv_m_cases", **arrs)
 
 
+def case_eccv_2r():
+    """model/IFNet_2R.py + model/refine_2R.py: the stride variant of the ECCV net (IFBlock.conv0[0], Contextnet.conv1 and
+    Unet.down0 at stride 1, the Unet's output conv at stride 2).  No class of the reference wires it into a Model, so the
+    fixture drives IFNet.forward directly.  Same 190 tensors / default init as model/IFNet.py."""
+    from model.IFNet_2R import IFNet as IFNet2R
+    torch.manual_seed(1234)
+    net = IFNet2R()
+    net.eval()
+    for b in (net.block0, net.block1, net.block2):
+        b.lastconv.weight.mul_(AMP)
+    arrs = {}
+    img0, img1 = rand_frames(61, 2, 3, 64, 96, smooth=True)
+    flow_list, mask, merged, _, _, _ = net(torch.cat((img0, img1), 1), [4, 2, 1])
+    arrs["a_img0"], arrs["a_img1"] = f32(img0), f32(img1)
+    for i in range(3):
+        arrs[f"a_flow{i}"] = f32(flow_list[i])
+    arrs["a_merged0"], arrs["a_merged2"], arrs["a_mask"] = f32(merged[0]), f32(merged[2]), f32(mask)
+    img0, img1 = rand_frames(62, 1, 3, 128, 128)
+    arrs["b_img0"], arrs["b_img1"] = f32(img0), f32(img1)
+    arrs["b_out"] = f32(net(torch.cat((img0, img1), 1), [8, 4, 2])[2][2])          # Model.inference(scale=0.5)'s scale list
+    print("eccv 2R |flow|max", float(flow_list[-1].abs().max()))
+    save("eccv_2r_cases", **arrs)
+
+
 def case_scene_ssim():
     """The video loop's scene-change statistic (inference_video.py:199-203,226-228): pad to 32, F.interpolate to
     32x32, model/pytorch_msssim ssim_matlab -- on uint8 frames of a few kinds, recorded from the reference's code."""
@@ -331,6 +355,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "scene":
         case_scene_ssim()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "eccv_2r":
+        with torch.no_grad():
+            case_eccv_2r()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "eccv_m":
         with torch.no_grad():

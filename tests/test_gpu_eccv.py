@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, seeded_eccv, seeded_eccv_m
+from conftest import load_golden, seeded_eccv, seeded_eccv_2r, seeded_eccv_m
 from oracle import torch_ref as T
 
 pytestmark = pytest.mark.gpu
@@ -130,3 +130,24 @@ def test_eccv_m_arbitrary_timestep(pkg):
     tt = torch.tensor([0.25, 0.8], device=DEV).reshape(2, 1, 1, 1)                     # per-sample timesteps
     mixed = m.inference(a, b, scale_list=[4, 2, 1], timestep=tt).cpu().numpy()
     assert np.abs(mixed[0] - g["out_t0.25"][0]).max() < 1e-4 and np.abs(mixed[1] - g["out_t0.8"][1]).max() < 1e-4
+
+
+def test_eccv_2r_variant(pkg):
+    """IFNet_2R (model/IFNet_2R.py + model/refine_2R.py) against outputs recorded from the reference: fp32 <= 1e-4
+    (flows 1e-3 at |flow| ~ 11 px), fp16 inside the reduced-precision bar; scale list [8, 4, 2]."""
+    g = load_golden("eccv_2r_cases")
+    net = seeded_eccv_2r(pkg)
+    x = torch.cat((cu(g["a_img0"]), cu(g["a_img1"])), 1)
+    flows, mask, merged, ft, mt, ld = net(x, [4, 2, 1])
+    assert ft is None and mt is None and ld == 0
+    for i in range(3):
+        assert np.abs(flows[i].cpu().numpy() - g[f"a_flow{i}"]).max() < 1e-3, i
+    assert np.abs(mask.cpu().numpy() - g["a_mask"]).max() < 1e-4
+    assert np.abs(merged[0].cpu().numpy() - g["a_merged0"]).max() < 1e-4
+    assert np.abs(merged[2].cpu().numpy() - g["a_merged2"]).max() < 1e-4
+    xb = torch.cat((cu(g["b_img0"]), cu(g["b_img1"])), 1)
+    assert np.abs(net(xb, [8, 4, 2])[2][2].cpu().numpy() - g["b_out"]).max() < 1e-4
+    o16 = net(x.half(), [4, 2, 1])[2][2].float().cpu().numpy()
+    assert np.abs(o16 - g["a_merged2"]).max() < FP16_MAX_ABS and _psnr(o16, g["a_merged2"]) > FP16_MIN_PSNR
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        net(torch.zeros(1, 6, 36, 64, device=DEV), [4, 2, 1])
