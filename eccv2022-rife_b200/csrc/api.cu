@@ -278,7 +278,7 @@ int rife_weights_destroy(rife_weights* w) {
 // --------------------------------------------------------------------------------------------------
 // plan
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, stage_in0, stage_in1,
       stage_out, total;
   int s[5];   // block i works at H / s[i] * u[i]: scale_list[i] = s[i] / u[i] (one of the two is 1)
   int u[5];
@@ -335,6 +335,7 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   L->gridx = take((size_t)W * 4);
   L->gridy = take((size_t)H * 4);
   L->tstep = take((size_t)B * 4);
+  L->sync = take(256);   // grid-barrier counter of the ResConv chain kernel
   L->stage_in0 = take((size_t)(seq ? P + 1 : P) * H * W * C * 4);
   L->stage_in1 = take((size_t)(seq ? 0 : P) * H * W * C * 4);
   L->stage_out = take(N * C * 4);
@@ -350,6 +351,7 @@ struct rife_plan {
   int nf1() const { return seq ? 0 : P; }
   int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
   int chunk = 0;       // pairs per pass of the full-resolution stages (rife_plan_set_chunk); 0 = default
+  unsigned int sync_host = 0;  // value of the ResConv chain's grid-barrier counter after everything enqueued so far
   PlanLayout L{};
   char* ws = nullptr;
   void* at(size_t off) const { return ws + off; }
@@ -506,6 +508,15 @@ static bool narrow_off() {
   return off;
 }
 
+static int chain_min_c() {
+  // RIFE_HK_CHAIN=c: the 8 ResConv layers of every block with >= c channels run as ONE cooperative launch with grid
+  // barriers (conv_halo.cu).  Off by default: measured on B200 at 12 x 1080p it shortens the ResConv stages by 8-20 %
+  // under per-stage event timing but the free-running pipeline gets 0.5 % slower -- programmatic dependent launch already
+  // hides most of a kernel boundary, and a cooperative grid has to wait for the previous kernel to drain completely.
+  static const int v = getenv("RIFE_HK_CHAIN") && atoi(getenv("RIFE_HK_CHAIN")) > 0 ? atoi(getenv("RIFE_HK_CHAIN")) : 1 << 30;
+  return v;
+}
+
 static int default_chunk_pairs() {
   // pairs per pass of the 1/2- and full-resolution stages; measured on B200 at 1080p
   static const int v = getenv("RIFE_CHUNK_PAIRS") ? atoi(getenv("RIFE_CHUNK_PAIRS")) : 0;
@@ -615,10 +626,27 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     io.planar_out = 0;
     void* cur = p->at(L.act_a);
     void* nxt = p->at(L.act_b);
-    for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
+    bool chained = false;
+    if (hk_tail && c_ >= chain_min_c()) {
+      // ResConv x8 (IFNet_HDv3.py:63-72) as ONE cooperative launch with grid barriers between the layers; the result
+      // of the 8th layer lands in act_a again
+      const HaloLayer* ls[8];
+      for (int j = 0; j < 8; ++j) ls[j] = &w->blk[i].res[j].hk;
       io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
-      RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk_tail, st));
-      void* t = cur; cur = nxt; nxt = t;
+      int rc;
+      {
+        StageTimer _t(p, st, bn + ".res");
+        rc = launch_conv_halo_chain(ls, 8, io, (unsigned int*)p->at(L.sync), &p->sync_host, st);
+      }
+      if (rc < 0) return rc;
+      chained = rc == 0;   // 1: this shape cannot be chained (no instantiation / not co-resident)
+    }
+    if (!chained) {
+      for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
+        io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
+        RIFE_STAGE(bn + ".res", run_conv(p, w->blk[i].res[j], io, hk_tail, st));
+        void* t = cur; cur = nxt; nxt = t;
+      }
     }
     // lastconv + PixelShuffle -> tmp_i at (hs, wsz): the batch's own slice for a whole-batch block, the front of the
     // buffer for a per-pass block

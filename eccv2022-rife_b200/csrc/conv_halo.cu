@@ -45,6 +45,15 @@ struct HaloParams {
   const float* beta;
   const __half* res;
   __half* out;
+  // ResConv chain (nlayers > 1): the same c -> c layer shape applied nlayers times inside ONE cooperative launch, ping-pong
+  // between two activation tensors, a grid-wide barrier (atomic counter + spin) instead of a kernel boundary between layers
+  int nlayers;
+  const __half* w_l[8];
+  const float* bias_l[8];
+  const float* beta_l[8];
+  __half* out_l[2];        // destination of even / odd layers
+  unsigned int* sync;      // grid barrier counter: monotonic across launches (never reset)
+  unsigned int sync_base;  // its value when this launch starts
   int pdl_trig;    // launch_dependents: 0 implicit at CTA exit (default; measured best), 1 after the prologue, 2 after the last MMA
   long long* dbg;  // RIFE_HK_DEBUG=1: per-CTA role timers (8 x int64), else null
   signed char e_dy[MAX_ENTRIES], e_dx[MAX_ENTRIES];
@@ -138,6 +147,24 @@ __device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
   st8(dst + 8, a);
 }
 
+// grid-wide barrier of the ResConv chain: every CTA adds 1 after its layer-l stores are visible; the TMA producer of
+// layer l + 1 spins until all gridDim.x CTAs have arrived (all CTAs are co-resident: cooperative launch)
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if ((int)(v - target) >= 0) break;   // wrap-safe
+    if (clock64() - t0 > 4000000000LL) __trap();
+    __nanosleep(64);
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy stores -> this CTA's TMA (async proxy) loads
+}
+
 template <int I> struct IntC { static constexpr int value = I; };
 template <int N, int I = 0, class F>
 __device__ __forceinline__ void static_for(F& f) {
@@ -220,6 +247,7 @@ struct EpiCtx {
   int b, x, y0;           // batch, pixel x, first row of this thread in the step (mi = 0)
   uint32_t res_smem;      // smem address of the residual for (mi = 0, plane 0)
   size_t plane;           // elements per planar-8 channel group of the destination
+  __half* out;            // destination tensor of this layer
 };
 
 // Fused layer tail for 16 accumulator columns [16j, 16j+16) of M-tile `mi` (bias already in smem).
@@ -247,10 +275,10 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
       const int H2 = p.H >> 1, W2 = p.W >> 1;
       const int G = (4 * p.out_c) >> 3, g = (((y & 1) * 2 + (c.x & 1)) * p.out_c + n0) >> 3;
       pl = (size_t)H2 * W2 * 8;
-      dst = p.out + ((size_t)c.b * G + g) * pl + ((size_t)(y >> 1) * W2 + (c.x >> 1)) * 8;
+      dst = c.out + ((size_t)c.b * G + g) * pl + ((size_t)(y >> 1) * W2 + (c.x >> 1)) * 8;
     } else {
       pl = c.plane;
-      dst = p.out + ((size_t)c.b * (p.out_c >> 3) + (n0 >> 3)) * pl + ((size_t)y * p.W + c.x) * 8;
+      dst = c.out + ((size_t)c.b * (p.out_c >> 3) + (n0 >> 3)) * pl + ((size_t)y * p.W + c.x) * 8;
     }
     float a[8];
 #pragma unroll
@@ -279,12 +307,12 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
       const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
-      st8(p.out + o + h * c.plane, a);
+      st8(c.out + o + h * c.plane, a);
     }
   } else if constexpr (EPI == EPI_PS) {
     const int par = j >> 2, sub = j & 3;
     const int oy = 4 * y + 2 * (par >> 1) + (sub >> 1), ox = 4 * c.x + 2 * (par & 1) + (sub & 1);
-    store16h(p.out + (((size_t)c.b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
+    store16h(c.out + (((size_t)c.b * 4 * p.H + oy) * 4 * p.W + ox) * TMP_C, v);
   } else if constexpr (EPI == EPI_HEADT) {
     // Head.cnn3 (ConvTranspose 16 -> 4): writes the complete 8-channel SRC pixel [f0..f3 | r g b a] of the four
     // full-resolution pixels (2y+py, 2x+px); the image channels come from the s2d Head input (p.res, planar-8
@@ -306,7 +334,7 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
       const int oy = 2 * y + (par >> 1), ox = 2 * c.x + (par & 1);
       float f[8] = {v[4 * par], v[4 * par + 1], v[4 * par + 2], v[4 * par + 3],
                     im[par * 3], im[par * 3 + 1], im[par * 3 + 2], im[12 + par]};
-      st8(p.out + (((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * SRC_C, f);
+      st8(c.out + (((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * SRC_C, f);
     }
   } else if constexpr (EPI == EPI_CONVT) {
     for (int i = 0; i < 16; ++i) {
@@ -314,7 +342,7 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
       if (n >= p.n_valid) break;
       const int par = n / p.cpp, co = n - par * p.cpp;
       const int oy = 2 * y + (par >> 1), ox = 2 * c.x + (par & 1);
-      p.out[(((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
+      c.out[(((size_t)c.b * 2 * p.H + oy) * 2 * p.W + ox) * p.out_c + co] = __float2half_rn(v[i]);
     }
   }
 }
@@ -343,7 +371,7 @@ template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS
 // one weight tile per schedule entry through a ring of p.nb slots, re-using every tile for the MT stacked M-tiles.
 template <int KIND, int KSTEPS, int NE, int MT, int EPI, bool STREAM = false>
 __global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value + (STREAM ? 32 : 0))
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t a_empty[MAX_STAGES];
@@ -356,9 +384,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_beta[128];
   // per-MMA operand tables, built once: the issuing thread then spends ~5 instructions per tcgen05.mma
-  __shared__ __align__(8) uint64_t tab_b[MAX_MMA];  // complete B (weights) descriptor
-  __shared__ uint32_t tab_a[MAX_MMA];               // A start-address field relative to the stage base (16-byte units)
-  __shared__ uint32_t tab_d[MAX_MMA];               // accumulator column offset | (accumulate << 31)
+  // (generic table-driven schedule only: the compile-time schedules do not spend static smem on them)
+  constexpr int NTAB = KIND < 0 ? MAX_MMA : 1;
+  __shared__ __align__(8) uint64_t tab_b[NTAB];  // complete B (weights) descriptor
+  __shared__ uint32_t tab_a[NTAB];               // A start-address field relative to the stage base (16-byte units)
+  __shared__ uint32_t tab_d[NTAB];               // accumulator column offset | (accumulate << 31)
 
   constexpr int NUM_EPI_WARPS = EpiWarps<EPI>::value;
   constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // without the optional weight-streaming warp
@@ -368,6 +398,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    if (p.nlayers > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&a_full[s]), 1);
       // ResConv epilogues read the residual (= centre tap of the input tile) from the smem stage itself, so the
@@ -399,7 +430,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
       if (p.beta && i < 128) s_beta[i] = p.beta[i];
     }
   }
-  if (warp == 1) {
+  if (KIND < 0 && warp == 1) {
     const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)p.ne * 16u, 128u);
     for (int i = lane; i < p.nentries * p.ksteps; i += 32) {
       const int e = i / p.ksteps, kk = i - e * p.ksteps;
@@ -418,9 +449,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- producer: resident weights once, then one halo box per tile
+      // ---------------- producer: resident weights (per layer), then one halo box per tile
+      const uint32_t wb = smem_u32(&w_full);
       if (!STREAM) {
-        const uint32_t wb = smem_u32(&w_full);
         mbar_expect_tx(wb, (uint32_t)p.w_bytes);
         for (int off = 0; off < p.w_bytes; off += 32768) {
           const int n = min(32768, p.w_bytes - off);
@@ -433,32 +464,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int tx = tile % p.tiles_x;
-        const int r = tile / p.tiles_x;
-        const int ty = r % p.tiles_y, b = r / p.tiles_y;
-        mbar_wait_t(smem_u32(&a_empty[stage]), phase ^ 1, t_wait);
-        const uint32_t fb = smem_u32(&a_full[stage]);
-        mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
-        tma_load_4d(a_smem + stage * p.a_stage_bytes, &tm_a, fb, (tx * TW - 1) * 8, ty * TH * p.mt - 1, 0, b);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      for (int l = 0; l < p.nlayers; ++l) {
+        if (l > 0) {
+          // every CTA has stored layer l-1 (that includes this CTA's epilogues, hence all of its MMAs: the weight
+          // buffer is free again)
+          grid_wait(p.sync, p.sync_base + (unsigned int)l * gridDim.x);
+          if (!STREAM) {
+            mbar_expect_tx(wb, (uint32_t)p.w_bytes);
+            for (int off = 0; off < p.w_bytes; off += 32768) {
+              const int n = min(32768, p.w_bytes - off);
+              bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(p.w_l[l]) + off, (uint32_t)n, wb);
+            }
+          }
+        }
+        const CUtensorMap* tm = (l & 1) ? &tm_b : &tm_a;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+          const int tx = tile % p.tiles_x;
+          const int r = tile / p.tiles_x;
+          const int ty = r % p.tiles_y, b = r / p.tiles_y;
+          mbar_wait_t(smem_u32(&a_empty[stage]), phase ^ 1, t_wait);
+          const uint32_t fb = smem_u32(&a_full[stage]);
+          mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
+          tma_load_4d(a_smem + stage * p.a_stage_bytes, tm, fb, (tx * TW - 1) * 8, ty * TH * p.mt - 1, 0, b);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = t_wait;
     }
   } else if (STREAM && warp == 2 + NUM_EPI_WARPS) {
     if (lane == 0) {
-      // ---------------- weight-tile producer: entry e of every tile -> ring slot
+      // ---------------- weight-tile producer: entry e of every tile -> ring slot (runs ahead across layers)
       int bs = 0;
       uint32_t bph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        for (int e = 0; e < p.nentries; ++e) {
-          mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
-          const uint32_t fb = smem_u32(&b_full[bs]);
-          mbar_expect_tx(fb, (uint32_t)p.wtile_bytes);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)e * p.wtile_bytes;
-          for (int off = 0; off < p.wtile_bytes; off += 32768)
-            bulk_load(w_smem + bs * p.wtile_al + off, src + off, (uint32_t)min(32768, p.wtile_bytes - off), fb);
-          if (++bs == p.nb) { bs = 0; bph ^= 1; }
+      for (int l = 0; l < p.nlayers; ++l) {
+        const uint8_t* wl = reinterpret_cast<const uint8_t*>(p.nlayers > 1 ? p.w_l[l] : p.w);
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+          for (int e = 0; e < p.nentries; ++e) {
+            mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
+            const uint32_t fb = smem_u32(&b_full[bs]);
+            mbar_expect_tx(fb, (uint32_t)p.wtile_bytes);
+            const uint8_t* src = wl + (size_t)e * p.wtile_bytes;
+            for (int off = 0; off < p.wtile_bytes; off += 32768)
+              bulk_load(w_smem + bs * p.wtile_al + off, src + off, (uint32_t)min(32768, p.wtile_bytes - off), fb);
+            if (++bs == p.nb) { bs = 0; bph ^= 1; }
+          }
         }
       }
     }
@@ -470,9 +519,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
       const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
       long long t_w = 0, t_te = 0, t_af = 0;
       const long long t_begin = clock64();
-      if (!STREAM) mbar_wait_t(smem_u32(&w_full), 0, t_w);
       int stage = 0, it = 0, bs = 0;
       uint32_t phase = 0, bph = 0;
+      for (int l = 0; l < p.nlayers; ++l) {
+      if (!STREAM) mbar_wait_t(smem_u32(&w_full), (uint32_t)(l & 1), t_w);
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait_t(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u, t_te);
@@ -513,6 +563,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
         umma_commit(smem_u32(&t_full[buf]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      }
       if (p.pdl_trig == 2) pdl_trigger();  // only the last epilogue is left: let the next kernel's CTAs set up meanwhile
       if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 1] = t_w;
@@ -536,13 +587,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
     uint32_t phase = 0;
     long long t_tf = 0;
     const long long t_begin = clock64();
+    for (int l = 0; l < p.nlayers; ++l) {
+    __half* const out_l = p.nlayers > 1 ? p.out_l[l & 1] : p.out;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int tx = tile % p.tiles_x;
       const int r = tile / p.tiles_x;
       const int ty = r % p.tiles_y, b = r / p.tiles_y;
       const int buf = it & 1;
       EpiCtx c;
-      c.b = b; c.x = tx * TW + tx_; c.plane = plane;
+      c.b = b; c.x = tx * TW + tx_; c.plane = plane; c.out = out_l;
       c.res_smem = a_smem + stage * p.a_stage_bytes + (uint32_t)(((ty_ + 1) * pitch + tx_ + 1) * 16);
       if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) mbar_wait(smem_u32(&a_full[stage]), phase);  // acquire the TMA-written tile
       mbar_wait_t(smem_u32(&t_full[buf]), ((uint32_t)it >> 1) & 1u, t_tf);
@@ -589,7 +642,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
               const int y = yw + row, x = tx * TW + txc;
               if (y < p.H && x < p.W) {
                 const int oy = 4 * y + 2 * py + dyp;
-                __half* dst = p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * TMP_C + col * 8;
+                __half* dst = out_l + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * TMP_C + col * 8;
                 *reinterpret_cast<uint4*>(dst) = u;
               }
             }
@@ -639,7 +692,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
               const int y = yw + row, x = tx * TW + txc;
               if (y < p.H && x < p.W) {
                 const int oy = 4 * y + 2 * py + dyp;
-                __half* dst = p.out + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * 8 + col * 8;
+                __half* dst = out_l + (((size_t)b * 4 * p.H + oy) * 4 * p.W + (size_t)4 * tx * TW) * 8 + col * 8;
                 *reinterpret_cast<uint4*>(dst) = u;
               }
             }
@@ -677,6 +730,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const HaloParams p) {
         if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) mbar_arrive(smem_u32(&a_empty[stage]));
       }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    if (l + 1 < p.nlayers) {
+      // layer boundary: this layer's stores published grid-wide, next layer's bias / beta loaded once every epilogue
+      // warp is done with the current ones
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * NUM_EPI_WARPS) : "memory");
+      if (threadIdx.x == 64) grid_arrive(p.sync);
+      for (int i = threadIdx.x - 64; i < p.ncols; i += NUM_THREADS - 64) {
+        s_bias[i] = p.bias_l[l + 1][i];
+        if (i < 128) s_beta[i] = p.beta_l[l + 1][i];
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * NUM_EPI_WARPS) : "memory");
+    }
     }
     if (p.dbg && warp == 2 && lane == 0) {  // timers of the first epilogue warp
       p.dbg[blockIdx.x * 8 + 5] = t_tf;
@@ -835,7 +902,67 @@ static int set_smem_attr(const void* fn) {
   return RIFE_OK;
 }
 
-int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
+namespace {
+struct HaloChain {  // nlayers ResConv layers of one shape: layer l reads (l even ? io.in : io.out), writes the other one
+  const HaloLayer* const* layers;
+  int n;
+  unsigned int* sync;
+  unsigned int* sync_host;  // host mirror of the counter's value after everything enqueued so far
+};
+
+// cooperative launch (all CTAs co-resident: the chain's grid barrier spins) -- or the usual PDL launch
+template <typename... KArgs>
+int launch_hk(void (*kernel)(KArgs...), int grid, int threads, int smem, cudaStream_t st, const CUtensorMap& tm_a,
+              const CUtensorMap& tm_b, const HaloParams& p, bool coop) {
+  if (!coop) {
+    RIFE_CUDA_TRY(launch_pdl(kernel, dim3(grid), dim3(threads), smem, st, tm_a, tm_b, p));
+    return RIFE_OK;
+  }
+  int nb = 0;
+  RIFE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+  if (grid > nb * num_sms()) return 1;  // not co-resident: the caller launches layer by layer
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  static int with_pdl = pdl_enabled() ? 1 : 0;   // cooperative + programmatic serialization; dropped if the driver refuses
+  if (with_pdl) {
+    cfg.numAttrs = 2;
+    if (cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, p) == cudaSuccess) return RIFE_OK;
+    cudaGetLastError();
+    with_pdl = 0;
+  }
+  cfg.numAttrs = 1;
+  RIFE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, p));
+  return RIFE_OK;
+}
+
+int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st, const HaloChain* chain);
+}  // namespace
+
+int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) { return launch_conv_halo_impl(L, io, st, nullptr); }
+
+int launch_conv_halo_chain(const HaloLayer* const* layers, int n, const ConvIO& io, unsigned int* sync,
+                           unsigned int* sync_host, cudaStream_t st) {
+  if (n < 2 || n > 8 || !sync || !sync_host) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo chain: 2..8 layers and a sync counter");
+  if (io.epi != EPI_RES) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo chain: ResConv layers only");
+  for (int i = 1; i < n; ++i)
+    if (layers[i]->cin != layers[0]->cin || layers[i]->ne != layers[0]->ne || layers[i]->nentries != layers[0]->nentries ||
+        layers[i]->w_bytes != layers[0]->w_bytes || layers[i]->stream != layers[0]->stream || !layers[i]->beta)
+      RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo chain: layers must share one shape");
+  HaloChain ch{layers, n, sync, sync_host};
+  return launch_conv_halo_impl(*layers[0], io, st, &ch);
+}
+
+namespace {
+int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st, const HaloChain* chain) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (io.epi == EPI_PS && L.ps_cols != 1) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: EPI_PS needs the PixelShuffle layout");
@@ -929,6 +1056,26 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed: " + std::to_string((int)r));
   }
+  CUtensorMap tm_b = tm_a;
+  p.nlayers = 1;
+  if (chain) {
+    cuuint64_t dims[4] = {(cuuint64_t)io.W * 8, (cuuint64_t)io.H, (cuuint64_t)p.kgroups, (cuuint64_t)io.B};
+    cuuint64_t strides[3] = {(cuuint64_t)io.W * 16, (cuuint64_t)io.H * io.W * 16, (cuuint64_t)p.kgroups * io.H * io.W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)((TW + p.R) * 8), (cuuint32_t)(TH * p.mt + p.R), (cuuint32_t)p.kgroups, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, io.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(halo chain) failed: " + std::to_string((int)r));
+    p.nlayers = chain->n;
+    for (int l = 0; l < chain->n; ++l) {
+      p.w_l[l] = chain->layers[l]->w; p.bias_l[l] = chain->layers[l]->bias; p.beta_l[l] = chain->layers[l]->beta;
+    }
+    p.out_l[0] = (__half*)io.out;
+    p.out_l[1] = (__half*)const_cast<void*>(io.in);
+    p.sync = chain->sync;
+    p.sync_base = *chain->sync_host;
+  }
+  const bool coop = chain != nullptr;
   int grid = num_sms() * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
   static const bool debug = getenv("RIFE_HK_DEBUG") != nullptr;
@@ -944,7 +1091,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #define RIFE_HK_CASE(K, KS, N_, MT_, E_)                                                                     \
   if (!done && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {                   \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_>));                              \
-    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<K, KS, N_, MT_, E_>, dim3(grid), dim3(64 + 32 * EpiWarps<E_>::value), smem, st, tm_a, p)); \
+    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_>, grid, 64 + 32 * EpiWarps<E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
     done = true;                                                                                             \
   }
   RIFE_HK_CASE(1, 1, 16, 2, EPI_LRELU)      // Head.cnn0            (s2d, cin 16 -> 16)
@@ -963,7 +1110,7 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
 #define RIFE_HK_STREAM(K, KS, N_, MT_, E_)                                                                   \
   if (!done && L.stream && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {       \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_, true>));                        \
-    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<K, KS, N_, MT_, E_, true>, dim3(grid), dim3(96 + 32 * EpiWarps<E_>::value), smem, st, tm_a, p)); \
+    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_, true>, grid, 96 + 32 * EpiWarps<E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
     done = true;                                                                                             \
   }
   RIFE_HK_STREAM(0, 6, 96, 2, EPI_RES)      // block2 ResConv       (3x3, 96 -> 96), two stacked M-tiles
@@ -972,11 +1119,14 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   RIFE_HK_STREAM(2, 6, 64, 1, EPI_PS)       // block2.lastconv      (ConvT+PS, 96 -> 4x64)
   RIFE_HK_STREAM(2, 8, 64, 1, EPI_PS)       // block1.lastconv      (ConvT+PS, 128 -> 4x64)
 #undef RIFE_HK_STREAM
+  if (!done && L.stream && coop) return 1;
   if (!done && L.stream) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no streamed instantiation for this layer / epilogue");
+  if (done && chain) *chain->sync_host += (unsigned int)(chain->n - 1) * (unsigned int)grid;
   if (!done && p.epi == EPI_PS8) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no EPI_PS8 instantiation for this layer");
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
-    RIFE_CUDA_TRY(launch_pdl(conv_halo_kernel<-1, 0, 0, 0, -1>, dim3(grid), dim3(64 + 32 * EpiWarps<-1>::value), smem, st, tm_a, p));
+    if (coop) return 1;  // no compile-time instantiation for this shape: the caller launches layer by layer
+    RIFE_TRY(launch_hk(conv_halo_kernel<-1, 0, 0, 0, -1>, grid, 64 + 32 * EpiWarps<-1>::value, smem, st, tm_a, tm_b, p, false));
   }
   RIFE_LAUNCH_CHECK();
   if (debug) {
@@ -992,6 +1142,8 @@ int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   }
   return RIFE_OK;
 }
+
+}  // namespace
 
 int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st) {
   // NHWC fp32 in (cin channels) -> planar-8 fp16; planar / pixel-major fp16 out -> NHWC fp32

@@ -30,6 +30,12 @@ int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* pa
 // planar-8 fp16 activations [B][C/8][H][W][8] in; planar-8 (LRELU / LINEAR / RES / LRELU_S2D) or pixel-major
 // (PS / HEADT / CONVT) fp16 out
 int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st);
+// n (2..8) ResConv layers of one shape in ONE cooperative launch: layer l reads io.in (l even) / io.out (l odd) and writes
+// the other tensor; a grid-wide barrier replaces the kernel boundary.  `sync`: one device uint32, zero-initialised once
+// and monotonic from then on; `sync_host`: the caller's mirror of its value after all launches enqueued so far.
+// Returns 1 (nothing launched) when the shape has no compile-time instantiation or its grid is not co-resident.
+int launch_conv_halo_chain(const HaloLayer* const* layers, int n, const ConvIO& io, unsigned int* sync,
+                           unsigned int* sync_host, cudaStream_t st);
 int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st);
 
 }  // namespace rife

@@ -355,9 +355,12 @@ def test_batch_consistency_fp16(pkg):
 
 # ---------------------------------------------------------------------------------------------- pad/crop + uint8 frames
 def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
-    """Model.inference runs the last block's lastconv for flow + mask only (nothing reads block 4's feat channels,
-    IFNet_HDv3.py:148-159).  Same MMAs, same merge kernel: the frame is bit-identical to the 13-channel lastconv
-    (RIFE_NO_NARROW_LAST=1 in a fresh process) and IFNet.forward (all outputs, 16-channel tmp) agrees with it."""
+    """Two launch-structure choices that must not change a bit of the frame, each against its switch in a fresh process:
+    * Model.inference runs the last block's lastconv for flow + mask only (nothing reads block 4's feat channels,
+      IFNet_HDv3.py:148-159) -- RIFE_NO_NARROW_LAST=1 restores the 13-channel lastconv;
+    * RIFE_HK_CHAIN=64: the 8 ResConv layers of blocks 1-3 run as ONE cooperative launch each, with grid barriers
+      between the layers (conv_halo.cu; optional, off by default).
+    IFNet.forward (all outputs, 16-channel tmp) agrees with the frame as well."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
@@ -365,19 +368,21 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
         "from conftest import AMP, seeded_model; pkg = importlib.import_module('eccv2022-rife_b200');"
         "m = seeded_model(pkg, AMP, 'fp16'); g = torch.Generator().manual_seed(21);"
         "a = torch.rand(2, 3, 192, 320, generator=g).cuda().half(); b = torch.rand(2, 3, 192, 320, generator=g).cuda().half();"
-        "torch.save(m.inference(a, b, 0.4).cpu(), sys.argv[1])" % (root, root))
-    outs = []
-    for tag, env in (("narrow", {}), ("wide", {"RIFE_NO_NARROW_LAST": "1"})):
+        "c = torch.rand(3, 3, 576, 1024, generator=g).cuda().half(); d = torch.rand(3, 3, 576, 1024, generator=g).cuda().half();"
+        "torch.save((m.inference(a, b, 0.4).cpu(), m.inference(c, d, 0.5).cpu()), sys.argv[1])" % (root, root))
+    outs = {}
+    for tag, env in (("default", {}), ("wide", {"RIFE_NO_NARROW_LAST": "1"}), ("chain", {"RIFE_HK_CHAIN": "64"})):
         f = str(tmp_path / (tag + ".pt"))
         subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env}, timeout=600)
-        outs.append(torch.load(f))
-    assert torch.equal(outs[0], outs[1])
+        outs[tag] = torch.load(f)
+    for tag in ("wide", "chain"):
+        assert torch.equal(outs[tag][0], outs["default"][0]) and torch.equal(outs[tag][1], outs["default"][1]), tag
     m = seeded_model(pkg, AMP, "fp16")
     g = torch.Generator().manual_seed(21)
     a, b = torch.rand(2, 3, 192, 320, generator=g).to(DEV).half(), torch.rand(2, 3, 192, 320, generator=g).to(DEV).half()
-    assert torch.equal(m.inference(a, b, 0.4).cpu(), outs[0])
+    assert torch.equal(m.inference(a, b, 0.4).cpu(), outs["default"][0])
     _, _, merged = m.flownet(torch.cat((a, b), 1), 0.4, [16, 8, 4, 2, 1])
-    assert (merged[4].float().cpu() - outs[0].float()).abs().max() < 4e-3
+    assert (merged[4].float().cpu() - outs["default"][0].float()).abs().max() < 4e-3
 
 
 def test_chunked_passes_are_bit_identical(pkg):
