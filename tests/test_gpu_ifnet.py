@@ -393,13 +393,19 @@ def test_chunked_passes_are_bit_identical(pkg):
     g = torch.Generator().manual_seed(33)
     a, b = torch.rand(5, 3, 128, 192, generator=g).to(DEV).half(), torch.rand(5, 3, 128, 192, generator=g).to(DEV).half()
     net = m.flownet
+    u0 = (torch.rand(5, 120, 180, 3, generator=g) * 255).byte().to(DEV)      # uint8 HWC frames, padded / cropped in-kernel
+    u1 = (torch.rand(5, 120, 180, 3, generator=g) * 255).byte().to(DEV)
     want = m.inference(a, b, 0.3).clone()
     want_multi = m.inference_multi(a, b, (0.25, 0.75)).clone()
+    want_seq = m.inference_sequence(a, (0.5,)).clone()                       # video order: 5 frames -> 4 pairs
+    want_u8 = net.run(u0, u1, 0.5, 1.0, False, True).clone()
     for n in (1, 2, 4):
         for pl in net._plans.values():
             pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, n))
         assert torch.equal(m.inference(a, b, 0.3), want), n
         assert torch.equal(m.inference_multi(a, b, (0.25, 0.75)), want_multi), n
+        assert torch.equal(m.inference_sequence(a, (0.5,)), want_seq), n
+        assert torch.equal(net.run(u0, u1, 0.5, 1.0, False, True), want_u8), n
     for pl in net._plans.values():
         pkg._lib.check(lib.rife_plan_set_chunk(pl.handle, 0))
     m32 = seeded_model(pkg, AMP, "fp32")

@@ -1,8 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_gpu.log 2>&1; tail -3 gpurun_out/t_gpu.log
-run() { tag=$1; shift; timeout 300 env "$@" python bench.py --steps 12 --warmup 4 --no-cpu-baseline > gpurun_out/ch_$tag.json 2> gpurun_out/ch_$tag.err; }
-run c64 A=1
-run layer RIFE_HK_CHAIN=0
-run c96 RIFE_HK_CHAIN=96
-run c32 RIFE_HK_CHAIN=32
-run c64b A=1
-run layerb RIFE_HK_CHAIN=0
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_mem.log 2>&1; echo "memcheck rc=$?" ; tail -4 gpurun_out/san_mem.log
+RIFE_HK_CHAIN=64 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_mem_chain.log 2>&1; echo "memcheck chain rc=$?"; tail -3 gpurun_out/san_mem_chain.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_race.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/san_race.log
