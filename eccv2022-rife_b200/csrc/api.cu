@@ -352,6 +352,9 @@ struct rife_plan {
   int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
   int chunk = 0;       // pairs per pass of the full-resolution stages (rife_plan_set_chunk); 0 = default
   unsigned int sync_host = 0;  // value of the ResConv chain's grid-barrier counter after everything enqueued so far
+  std::vector<float> ts_host;  // timesteps last written to the device buffer, and the stream they were written on
+  cudaStream_t ts_stream = nullptr;
+  bool ts_valid = false;
   PlanLayout L{};
   char* ws = nullptr;
   void* at(size_t off) const { return ws + off; }
@@ -543,7 +546,16 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   const size_t E = half_act ? 2 : 4;
   const size_t N = (size_t)B * H * W;
 
-  RIFE_CUDA_TRY(cudaMemcpyAsync(p->at(L.tstep), timestep_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  // timesteps: rewritten only when they (or the stream) changed since the last call on this plan, and then through kernel
+  // parameters -- a cudaMemcpyAsync here would sit on the H2D copy engine behind the next calls' frame uploads
+  // (rife_inference_host_pipelined) and stall the compute stream for up to a whole frame-batch transfer
+  if (!(p->ts_valid && p->ts_stream == st && (int)p->ts_host.size() == B &&
+        memcmp(p->ts_host.data(), timestep_host, (size_t)B * 4) == 0)) {
+    RIFE_TRY(launch_set_tstep((float*)p->at(L.tstep), timestep_host, B, st));
+    p->ts_host.assign(timestep_host, timestep_host + B);
+    p->ts_stream = st;
+    p->ts_valid = true;
+  }
 
   PixelCtx c;
   c.B = B; c.C = p->C; c.H = H; c.W = W;

@@ -250,6 +250,8 @@ int launch_warp_op(const void* input, const void* flow, void* out, int B, int C,
 int launch_resize_op(const float* x, float* out, int B, int C, int H, int W, int num, int den, float post_mul,
                      cudaStream_t st);
 int launch_fill_grid(float* g, int n, cudaStream_t st);
+// dst[0..n) = host[0..n) through kernel parameters (no copy engine involved)
+int launch_set_tstep(float* dst, const float* host, int n, cudaStream_t st);
 // layout converters for the op-level entry points
 int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, bool s2d, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st);

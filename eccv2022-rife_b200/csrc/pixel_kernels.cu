@@ -1189,6 +1189,24 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
   return RIFE_OK;
 }
 
+// timesteps of one call as kernel parameters: no copy-engine work on the compute stream (a small cudaMemcpyAsync would
+// queue behind the frame uploads of the next calls that are in flight on the H2D engine)
+struct TsArg { float v[256]; };
+__global__ void set_tstep_kernel(TsArg a, float* __restrict__ dst, int n) {
+  const int i = threadIdx.x;
+  if (i < n) dst[i] = a.v[i];
+}
+int launch_set_tstep(float* dst, const float* host, int n, cudaStream_t st) {
+  for (int o = 0; o < n; o += 256) {
+    TsArg a;
+    const int m = n - o < 256 ? n - o : 256;
+    for (int i = 0; i < m; ++i) a.v[i] = host[o + i];
+    set_tstep_kernel<<<1, 256, 0, st>>>(a, dst + o, m);
+  }
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
 int launch_warp_op(const void* input, const void* flow, void* out, int B, int C, int H, int W, int dtype,
                    const float* gridx, const float* gridy, cudaStream_t st) {
   const size_t n = (size_t)B * H * W;

@@ -106,6 +106,24 @@ def test_1080p_against_torch_cpu_fp32(pkg):
     assert np.abs(out - ref).max() < TOL32
 
 
+def test_noncontiguous_slices_and_inputs_untouched(pkg):
+    """Callers pass channel slices of one 6-channel tensor (benchmark/MiddleBury_Other.py:31-32 `imgs[:, :3]`, `imgs[:, 3:]`):
+    non-contiguous views give the same frame as contiguous copies, the inputs are not modified and the result is a fresh
+    tensor of the inputs' dtype / device (SURVEY 8b tensor conventions)."""
+    m = seeded_model(pkg, AMP, "fp32")
+    g = torch.Generator().manual_seed(12)
+    imgs = torch.rand(2, 6, 64, 128, generator=g).to(DEV)
+    keep = imgs.clone()
+    a, b = imgs[:, :3], imgs[:, 3:]
+    assert not a.is_contiguous()
+    out = m.inference(a, b)
+    assert torch.equal(imgs, keep) and out.data_ptr() not in (a.data_ptr(), b.data_ptr())
+    assert out.dtype == imgs.dtype and out.device == imgs.device and out.is_contiguous()
+    assert torch.equal(out, m.inference(a.contiguous(), b.contiguous()))
+    h = m.inference(a.half(), b.half())                                  # dtype follows the input (auto precision)
+    assert h.dtype == torch.float16 and float((h.float() - out).abs().max()) < 2e-2
+
+
 def test_shape_and_device_errors(pkg):
     m = seeded_model(pkg, 1.0, "fp32")
     with pytest.raises(RuntimeError):

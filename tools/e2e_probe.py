@@ -54,3 +54,22 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / STEPS
 print(f"P={P} uint8 HWC 1080 pinned host, pipelined: {ms:.3f} ms  {P / ms * 1e3:.0f} frames/s")
+
+# ---- interference only: device-resident uint8 inference while independent copies of the same size run on other streams
+d_in = [torch.empty_like(u8[0][0]) for _ in range(2)]
+d_out = torch.empty((P, 1080, 1920, 3), dtype=torch.uint8, device=dev)
+for mode in ("h2d", "d2h", "both"):
+    def step(i):
+        if mode in ("h2d", "both"):
+            with torch.cuda.stream(streams[0]):
+                d_in[0].copy_(h8[i % 3][0], non_blocking=True)
+                d_in[1].copy_(h8[i % 3][1], non_blocking=True)
+        if mode in ("d2h", "both"):
+            with torch.cuda.stream(streams[2]):
+                outs[i % 3].copy_(d_out, non_blocking=True)
+        m.flownet.run(u8[i % 3][0], u8[i % 3][1], 0.5, 1.0, False, True)
+    for s in streams:
+        s.wait_stream(cur)
+    ms = timed(step)
+    torch.cuda.synchronize()
+    print(f"P={P} uint8 device-resident + independent {mode} copies of one step's frames: {ms:.3f} ms  {P / ms * 1e3:.0f} frames/s")
