@@ -1,3 +1,7 @@
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_mem.log 2>&1; echo "memcheck rc=$?" ; tail -4 gpurun_out/san_mem.log
-RIFE_HK_CHAIN=64 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_mem_chain.log 2>&1; echo "memcheck chain rc=$?"; tail -3 gpurun_out/san_mem_chain.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_target.py > gpurun_out/san_race.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/san_race.log
+run() { tag=$1; shift; timeout 300 env "$@" python bench.py --steps 12 --warmup 4 --no-cpu-baseline > gpurun_out/ue_$tag.json 2> gpurun_out/ue_$tag.err; }
+run on A=1
+run off RIFE_UMMA_EARLY=0
+run on2 A=1
+run off2 RIFE_UMMA_EARLY=0
+python tools/latency_probe.py 2>&1 | tail -4
+RIFE_UMMA_EARLY=0 python tools/latency_probe.py 2>&1 | tail -4
