@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <utility>
 
 #include "conv_halo.cuh"
@@ -890,6 +891,8 @@ int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* pa
 static int set_smem_attr(const void* fn) {
   // once per (function, device): opt in to > 48 KB dynamic shared memory
   static std::vector<std::pair<const void*, int>> seen;
+  static std::mutex mu;   // one host thread per GPU may launch concurrently
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   for (auto& s : seen)
