@@ -475,3 +475,14 @@ def test_uint8_hwc_frames(pkg):
     m.inference_host(h0, h1, ho)
     torch.cuda.synchronize()
     assert int((ho.int() - out.cpu().int()).abs().max()) == 0
+
+
+def test_shape_fuzz_fp16_vs_fp32():
+    """tools/fuzz_shapes.py: 16 random (batch, size, scale, channels, frame dtype, batching mode) combinations through the
+    fp16 fast path and the fp32 path of the same weights -- finite and inside the reduced-precision bar of each other."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_shapes.py"), "7", "16"], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "worst" in r.stdout
