@@ -550,6 +550,37 @@ __device__ __forceinline__ void level_taps(const __half* __restrict__ r0, const 
     for (int c = 0; c < 4; ++c) flow[q][c] = first ? acc[q][c] * sc : fmaf(acc[q][c], sc, flow[q][c]);
 }
 
+// NS = 1 variant (block 4: one sample per pixel): mask / feat of the newest level are blended in packed half2 arithmetic
+// straight from the loaded words (they are stored as fp16 right afterwards); the flow stays fp32.  Saves the 48
+// half -> float conversions and 24 of the 48 FMAs per pixel of the float form.
+__device__ __forceinline__ void level_taps_h1(const __half* __restrict__ r0, const __half* __restrict__ r1, int c0, int c1,
+                                              bool newest, const float (&wq)[4], float sc, bool first, float (&flow)[4],
+                                              __half2 (&mfh)[6]) {
+  float acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half* p = ((k >> 1) ? r1 : r0) + ((k & 1) ? c1 : c0);
+    float e[4];
+    if (newest) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + 8);
+      const __half2* hl = reinterpret_cast<const __half2*>(&lo);
+      const __half2* hh = reinterpret_cast<const __half2*>(&hi);
+      const float2 f01 = __half22float2(hl[0]), f23 = __half22float2(hl[1]);
+      e[0] = f01.x; e[1] = f01.y; e[2] = f23.x; e[3] = f23.y;
+      const __half2 wk = __float2half2_rn(wq[k]);
+      const __half2 v[6] = {hl[2], hl[3], hh[0], hh[1], hh[2], hh[3]};   // channels 4..15
+#pragma unroll
+      for (int i = 0; i < 6; ++i) mfh[i] = k == 0 ? __hmul2(wk, v[i]) : __hfma2(wk, v[i], mfh[i]);
+    } else {
+      ld4(p, e);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = k == 0 ? wq[0] * e[c] : fmaf(wq[k], e[c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) flow[c] = first ? acc[c] * sc : fmaf(acc[c], sc, flow[c]);
+}
+
 template <int NS>
 __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) block_input_h_kernel(LevelsArg L, int level, int s,
                                                             const __half* __restrict__ src0,
@@ -576,6 +607,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
     for (int q = 0; q < NQ; ++q) ld4(fbuf + (((size_t)b * H + y0 + q / NS) * W + x0 + q % NS) * 4, flow[q]);
   }
   float mf[12];  // channels 4..15 of the newest level (mask, feat x8, pad), averaged over the samples
+  __half2 mfh[6];  // the same as packed half2 (NS = 1)
 #pragma unroll 1
   for (int j = fbuf_levels; j < level; ++j) {
     const __half* base = reinterpret_cast<const __half*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
@@ -587,18 +619,10 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
     }
     if constexpr (NS == 1) {
       const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
-      float wq[NQ][4], am[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float ay = (q / NS) ? ly.a1 : ly.a0, ax = (q % NS) ? lx.a1 : lx.a0;
-        wq[q][0] = (1.f - ay) * (1.f - ax); wq[q][1] = (1.f - ay) * ax; wq[q][2] = ay * (1.f - ax); wq[q][3] = ay * ax;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) am[k] += wq[q][k];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) am[k] *= 1.f / (float)NQ;
-      level_taps<NQ>(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, newest, wq, am, sc,
-                     j == 0, flow, mf);
+      const float ay = ly.a0, ax = lx.a0;
+      const float wq[4] = {(1.f - ay) * (1.f - ax), (1.f - ay) * ax, ay * (1.f - ax), ay * ax};
+      level_taps_h1(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, newest, wq, sc, j == 0,
+                    flow[0], mfh);
       } else {
       // four samples: per-level tap arrays kept whole (the tap-major form costs this variant registers: 0.36 vs 0.34 ms)
       const Lerp2 ly = make_lerp2(y0, h, L.rs[j]), lx = make_lerp2(x0, w, L.rs[j]);
@@ -664,11 +688,19 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
   o[2] = __halves2half2(__high2half(Cc[2]), __low2half(Cc[3])); // img1 g, b
   o[3] = A[0]; o[4] = A[1];                      // warped f0
   o[5] = Cc[0]; o[6] = Cc[1];                    // warped f1
-  o[7] = __floats2half2_rn(t, mf[0]);            // timestep, mask
-  o[8] = __floats2half2_rn(mf[1], mf[2]);        // feat 0..7
-  o[9] = __floats2half2_rn(mf[3], mf[4]);
-  o[10] = __floats2half2_rn(mf[5], mf[6]);
-  o[11] = __floats2half2_rn(mf[7], mf[8]);
+  if constexpr (NS == 1) {
+    o[7] = __halves2half2(__float2half_rn(t), __low2half(mfh[0]));      // timestep, mask
+    o[8] = __halves2half2(__high2half(mfh[0]), __low2half(mfh[1]));     // feat 0..7
+    o[9] = __halves2half2(__high2half(mfh[1]), __low2half(mfh[2]));
+    o[10] = __halves2half2(__high2half(mfh[2]), __low2half(mfh[3]));
+    o[11] = __halves2half2(__high2half(mfh[3]), __low2half(mfh[4]));
+  } else {
+    o[7] = __floats2half2_rn(t, mf[0]);            // timestep, mask
+    o[8] = __floats2half2_rn(mf[1], mf[2]);        // feat 0..7
+    o[9] = __floats2half2_rn(mf[3], mf[4]);
+    o[10] = __floats2half2_rn(mf[5], mf[6]);
+    o[11] = __floats2half2_rn(mf[7], mf[8]);
+  }
   o[12] = __floats2half2_rn(fs[0] * fsc, fs[1] * fsc);
   o[13] = __floats2half2_rn(fs[2] * fsc, fs[3] * fsc);
   o[14] = __float2half2_rn(0.f);
