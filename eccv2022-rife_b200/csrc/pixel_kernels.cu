@@ -490,12 +490,14 @@ __device__ __forceinline__ Lerp2 make_lerp2(int d, int in_size, float rs) {
   r.i0 = l0.i0; r.i1 = l0.i1; r.a0 = l0.l1; r.a1 = l1.l1;
   return r;
 }
-__device__ __forceinline__ void warp8_h2(const __half* __restrict__ src, int H, int W, const WarpGeom& g, float gx,
-                                         float gy, float fx, float fy, __half2 (&out)[4]) {
-  const float nx = gx + __fmul_rn(fx, g.inv_halfw);
-  const float ny = gy + __fmul_rn(fy, g.inv_halfh);
-  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.f), 0.5f), g.wm1);
-  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.f), 0.5f), g.hm1);
+// fp16 fast path: the sample position is x + flow_x directly.  model/warplayer.py:18-22 reaches the same number through
+// g = linspace(-1,1,W)[x] + flow_x / ((W-1)/2) and ((g+1)/2)*(W-1); the two differ by fp32 rounding only (2e-4 of a pixel
+// at 1920 wide) -- far below the fp16 storage rounding of this path.  The fp32 mode and the final merge
+// kernel keep the reference's operation order.
+__device__ __forceinline__ void warp8_h2(const __half* __restrict__ src, int H, int W, const WarpGeom& g, int x, int y,
+                                         float fx, float fy, __half2 (&out)[4]) {
+  float ix = (float)x + fx;
+  float iy = (float)y + fy;
   ix = fminf(g.wm1, fmaxf(ix, 0.f));
   iy = fminf(g.hm1, fmaxf(iy, 0.f));
   const float x0f = floorf(ix), y0f = floorf(iy);
@@ -597,8 +599,9 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, b = blockIdx.z;
   if (X >= Ws) return;
-  const __half* s0 = src0 + (size_t)(b / geom.src_div) * H * W * SRC_C;
-  const __half* s1 = src1 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const int fr = geom.src_div == 1 ? b : b / geom.src_div;   // uniform branch: no integer division in the common case
+  const __half* s0 = src0 + (size_t)fr * H * W * SRC_C;
+  const __half* s1 = src1 + (size_t)fr * H * W * SRC_C;
   const int off = (NS == 1) ? 0 : (s / 2 - 1);
   const int x0 = X * s + off, y0 = Y * s + off;
   float flow[NQ][4];
@@ -666,10 +669,9 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
   for (int q = 0; q < NQ; ++q) {
     const int y = y0 + q / NS, x = x0 + q % NS;
     if (fbuf_store) st4(fbuf + (((size_t)b * H + y) * W + x) * 4, flow[q]);
-    const float gx = gridx[x], gy = gridy[y];
     __half2 a[4], c[4];
-    warp8_h2(s0, H, W, geom, gx, gy, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
-    warp8_h2(s1, H, W, geom, gx, gy, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
+    warp8_h2(s0, H, W, geom, x, y, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
+    warp8_h2(s1, H, W, geom, x, y, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (NQ == 1) { A[i] = a[i]; Cc[i] = c[i]; }
@@ -742,8 +744,9 @@ __global__ void __launch_bounds__(128, RIFE_BI_MINB2R) block_input_h2c_kernel(Le
   const bool valid = (tid >> 1) < Ws;            // a lane pair is valid or not as a whole; nobody leaves before the shuffles
   const int X = valid ? (tid >> 1) : Ws - 1;
   const int Y = blockIdx.y, b = blockIdx.z;
-  const __half* s0 = src0 + (size_t)(b / geom.src_div) * H * W * SRC_C;
-  const __half* s1 = src1 + (size_t)(b / geom.src_div) * H * W * SRC_C;
+  const int fr = geom.src_div == 1 ? b : b / geom.src_div;   // uniform branch: no integer division in the common case
+  const __half* s0 = src0 + (size_t)fr * H * W * SRC_C;
+  const __half* s1 = src1 + (size_t)fr * H * W * SRC_C;
   const int off = s / 2 - 1;
   const int x = X * s + off + r, y0 = Y * s + off;
   float flow[2][4];
@@ -776,14 +779,12 @@ __global__ void __launch_bounds__(128, RIFE_BI_MINB2R) block_input_h2c_kernel(Le
   }
   __half2 A[4], Cc[4];
   const __half2 qw = __float2half2_rn(0.25f);
-  const float gx = gridx[x];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     if (fbuf_store && valid) st4(fp + (size_t)q * W * 4, flow[q]);
-    const float gy = gridy[y0 + q];
     __half2 a[4], c[4];
-    warp8_h2(s0, H, W, geom, gx, gy, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
-    warp8_h2(s1, H, W, geom, gx, gy, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
+    warp8_h2(s0, H, W, geom, x, y0 + q, flow[q][0], flow[q][1], a);   // IFNet_HDv3.py:145,155
+    warp8_h2(s1, H, W, geom, x, y0 + q, flow[q][2], flow[q][3], c);   // IFNet_HDv3.py:146,156
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (q == 0) { A[i] = __hmul2(qw, a[i]); Cc[i] = __hmul2(qw, c[i]); }
