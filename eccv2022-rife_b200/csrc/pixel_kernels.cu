@@ -20,10 +20,10 @@
 #define RIFE_PIX_TRIGGER() pdl_trigger()
 #endif
 // resident blocks per SM the block-input gather is compiled for (register cap): measured best on B200 at 1080p --
-// s = 1 (block 4): 9 blocks (56 regs), s >= 2: 6 blocks (80 regs); 104 / 61 regs without the cap cost 2-4 % of a step
+// s = 1 (block 4): 9 blocks (56 regs), s = 2 (block 3): 7 blocks (72 regs); 104 / 61 regs without the cap cost 2-4 % of a step
 #ifndef RIFE_BI_MINB1
 #define RIFE_BI_MINB1 9
-#define RIFE_BI_MINB2 6
+#define RIFE_BI_MINB2 7
 #endif
 #ifndef RIFE_BI_MINB2R
 #define RIFE_BI_MINB2R 9
@@ -609,8 +609,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
 #pragma unroll
     for (int q = 0; q < NQ; ++q) ld4(fbuf + (((size_t)b * H + y0 + q / NS) * W + x0 + q % NS) * 4, flow[q]);
   }
-  float mf[12];  // channels 4..15 of the newest level (mask, feat x8, pad), averaged over the samples
-  __half2 mfh[6];  // the same as packed half2 (NS = 1)
+  __half2 mfh[6];  // channels 4..15 of the newest level (mask, feat x8, pad), averaged over the samples, packed half2
 #pragma unroll 1
   for (int j = fbuf_levels; j < level; ++j) {
     const __half* base = reinterpret_cast<const __half*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
@@ -647,17 +646,28 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
         }
       }
       if (newest) {
+        // mask / feat (channels 4..15): mean-weight bilinear blend in packed half2, straight from the loaded words
         const float inv = 1.f / (float)NQ;
-        const float a00 = wsum[0] * inv, a01 = wsum[1] * inv, a10 = wsum[2] * inv, a11 = wsum[3] * inv;
-        float t00[4], t01[4], t10[4], t11[4], u00[8], u01[8], u10[8], u11[8];
-        ld4(r0 + lx.i0 * TMP_C + 4, t00); ld4(r0 + lx.i1 * TMP_C + 4, t01);
-        ld4(r1 + lx.i0 * TMP_C + 4, t10); ld4(r1 + lx.i1 * TMP_C + 4, t11);
-        ld8(r0 + lx.i0 * TMP_C + 8, u00); ld8(r0 + lx.i1 * TMP_C + 8, u01);
-        ld8(r1 + lx.i0 * TMP_C + 8, u10); ld8(r1 + lx.i1 * TMP_C + 8, u11);
+        const __half2 a00 = __float2half2_rn(wsum[0] * inv), a01 = __float2half2_rn(wsum[1] * inv);
+        const __half2 a10 = __float2half2_rn(wsum[2] * inv), a11 = __float2half2_rn(wsum[3] * inv);
+        const __half* q00 = r0 + lx.i0 * TMP_C + 4;
+        const __half* q01 = r0 + lx.i1 * TMP_C + 4;
+        const __half* q10 = r1 + lx.i0 * TMP_C + 4;
+        const __half* q11 = r1 + lx.i1 * TMP_C + 4;
+        const uint2 t00 = *reinterpret_cast<const uint2*>(q00), t01 = *reinterpret_cast<const uint2*>(q01);
+        const uint2 t10 = *reinterpret_cast<const uint2*>(q10), t11 = *reinterpret_cast<const uint2*>(q11);
+        const uint4 u00 = *reinterpret_cast<const uint4*>(q00 + 4), u01 = *reinterpret_cast<const uint4*>(q01 + 4);
+        const uint4 u10 = *reinterpret_cast<const uint4*>(q10 + 4), u11 = *reinterpret_cast<const uint4*>(q11 + 4);
+        const __half2 *h00 = reinterpret_cast<const __half2*>(&t00), *h01 = reinterpret_cast<const __half2*>(&t01);
+        const __half2 *h10 = reinterpret_cast<const __half2*>(&t10), *h11 = reinterpret_cast<const __half2*>(&t11);
+        const __half2 *g00 = reinterpret_cast<const __half2*>(&u00), *g01 = reinterpret_cast<const __half2*>(&u01);
+        const __half2 *g10 = reinterpret_cast<const __half2*>(&u10), *g11 = reinterpret_cast<const __half2*>(&u11);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mf[c] = fmaf(a11, t11[c], fmaf(a10, t10[c], fmaf(a01, t01[c], a00 * t00[c])));
+        for (int i = 0; i < 2; ++i)
+          mfh[i] = __hfma2(a11, h11[i], __hfma2(a10, h10[i], __hfma2(a01, h01[i], __hmul2(a00, h00[i]))));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mf[4 + c] = fmaf(a11, u11[c], fmaf(a10, u10[c], fmaf(a01, u01[c], a00 * u00[c])));
+        for (int i = 0; i < 4; ++i)
+          mfh[2 + i] = __hfma2(a11, g11[i], __hfma2(a10, g10[i], __hfma2(a01, g01[i], __hmul2(a00, g00[i]))));
       }
       }
   }
@@ -690,19 +700,11 @@ __global__ void __launch_bounds__(128, NS == 1 ? RIFE_BI_MINB1 : RIFE_BI_MINB2) 
   o[2] = __halves2half2(__high2half(Cc[2]), __low2half(Cc[3])); // img1 g, b
   o[3] = A[0]; o[4] = A[1];                      // warped f0
   o[5] = Cc[0]; o[6] = Cc[1];                    // warped f1
-  if constexpr (NS == 1) {
-    o[7] = __halves2half2(__float2half_rn(t), __low2half(mfh[0]));      // timestep, mask
-    o[8] = __halves2half2(__high2half(mfh[0]), __low2half(mfh[1]));     // feat 0..7
-    o[9] = __halves2half2(__high2half(mfh[1]), __low2half(mfh[2]));
-    o[10] = __halves2half2(__high2half(mfh[2]), __low2half(mfh[3]));
-    o[11] = __halves2half2(__high2half(mfh[3]), __low2half(mfh[4]));
-  } else {
-    o[7] = __floats2half2_rn(t, mf[0]);            // timestep, mask
-    o[8] = __floats2half2_rn(mf[1], mf[2]);        // feat 0..7
-    o[9] = __floats2half2_rn(mf[3], mf[4]);
-    o[10] = __floats2half2_rn(mf[5], mf[6]);
-    o[11] = __floats2half2_rn(mf[7], mf[8]);
-  }
+  o[7] = __halves2half2(__float2half_rn(t), __low2half(mfh[0]));      // timestep, mask
+  o[8] = __halves2half2(__high2half(mfh[0]), __low2half(mfh[1]));     // feat 0..7
+  o[9] = __halves2half2(__high2half(mfh[1]), __low2half(mfh[2]));
+  o[10] = __halves2half2(__high2half(mfh[2]), __low2half(mfh[3]));
+  o[11] = __halves2half2(__high2half(mfh[3]), __low2half(mfh[4]));
   o[12] = __floats2half2_rn(fs[0] * fsc, fs[1] * fsc);
   o[13] = __floats2half2_rn(fs[2] * fsc, fs[3] * fsc);
   o[14] = __float2half2_rn(0.f);
