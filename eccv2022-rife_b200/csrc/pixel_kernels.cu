@@ -919,12 +919,26 @@ __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__
 #pragma unroll
   for (int c = 0; c < 4; ++c) flow[c] += t8[c];                                    // IFNet_HDv3.py:152
   const float gx = gridx[x], gy = gridy[y];
+  const int fr = geom.src_div == 1 ? b : b / geom.src_div;
   float a[4], c[4];
-  warp_img4(src0 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);   // IFNet_HDv3.py:155
-  warp_img4(src1 + (size_t)(b / geom.src_div) * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);   // IFNet_HDv3.py:156
+  warp_img4(src0 + (size_t)fr * H * W * SRC_C, H, W, geom, gx, gy, flow[0], flow[1], a);   // IFNet_HDv3.py:155
+  warp_img4(src1 + (size_t)fr * H * W * SRC_C, H, W, geom, gx, gy, flow[2], flow[3], c);   // IFNet_HDv3.py:156
   const float m = 1.f / (1.f + __expf(-t8[4]));                                    // IFNet_HDv3.py:158
-  for (int ch = 0; ch < C; ++ch)
-    omerged[(size_t)(b * lay.sb + ch * lay.sc + y * lay.sy + x * lay.sx)] = from_f<Tio>(a[ch] * m + c[ch] * (1.f - m));
+  float o[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) o[ch] = a[ch] * m + c[ch] * (1.f - m);            // IFNet_HDv3.py:159
+  // the two frame layouts of the API boundary, spelled out (generic 64-bit strides cost this issue-bound kernel ~25 %
+  // of its instructions): uint8 = HWC (B,h,w,C), float = NCHW (B,C,h,w), both cropped to the caller's (h, w)
+  if constexpr (sizeof(Tio) == 1) {
+    Tio* q = omerged + (((size_t)b * lay.h + y) * lay.w + x) * C;
+    q[0] = from_f<Tio>(o[0]); q[1] = from_f<Tio>(o[1]); q[2] = from_f<Tio>(o[2]);
+    if (C == 4) q[3] = from_f<Tio>(o[3]);
+  } else {
+    const size_t plane = (size_t)lay.h * lay.w;
+    Tio* q = omerged + ((size_t)b * C * lay.h + y) * lay.w + x;
+    q[0] = from_f<Tio>(o[0]); q[plane] = from_f<Tio>(o[1]); q[2 * plane] = from_f<Tio>(o[2]);
+    if (C == 4) q[3 * plane] = from_f<Tio>(o[3]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
