@@ -208,17 +208,39 @@ __device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t da, uint64_
     asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 0;" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
 }
 
+// Stride-2 3x3 convs run as 2x2 taps over the space-to-depth input, channel = parity * cs + c (api.cu: pack_conv3x3_s2d).
+// Only 9 of the 16 (tap, parity) pairs carry weights -- tap (dy, dx) reads parity (py, px) iff (dy == 0 || py == 1) and
+// (dx == 0 || px == 1); the other 7 are structural zeros.  With cs a multiple of 16 every K-step lies inside one parity, so
+// 14 of the 32 MMAs of a tile (KSTEPS = 8) multiply by zero and are not issued at all.
+template <int KIND, int KSTEPS, int E, int KK>
+__device__ __forceinline__ constexpr bool mma_nonzero() {
+  if constexpr (KIND == 1 && KSTEPS % 4 == 0) {
+    constexpr int par = KK / (KSTEPS / 4), py = par >> 1, px = par & 1;
+    return (Sched<1>::dy(E) == 0 || py == 1) && (Sched<1>::dx(E) == 0 || px == 1);
+  } else {
+    return true;
+  }
+}
+template <int KIND, int KSTEPS, int E, int KK = 0>
+__device__ __forceinline__ constexpr int first_nonzero_kk() {
+  if constexpr (mma_nonzero<KIND, KSTEPS, E, KK>()) return KK;
+  else return first_nonzero_kk<KIND, KSTEPS, E, KK + 1>();
+}
+
 // fully unrolled issue of one M-tile's MMAs: every operand offset is an immediate
 template <int KIND, int KSTEPS, int NE, int MT, int E = 0, int KK = 0>
 __device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
   using S = Sched<KIND>;
   if constexpr (E < S::NENT) {
-    constexpr int pitch = TW + S::R;
-    constexpr int plane16 = (TH * MT + S::R) * pitch;
-    constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
-    constexpr int b_off = E * (2 * KSTEPS) * NE + 2 * KK * NE;
-    constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;  // parity schedule: one NE-column group per output parity
-    umma_f16_c<!(S::first(E) && KK == 0)>(acc + d_col, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
+    if constexpr (mma_nonzero<KIND, KSTEPS, E, KK>()) {
+      constexpr int pitch = TW + S::R;
+      constexpr int plane16 = (TH * MT + S::R) * pitch;
+      constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
+      constexpr int b_off = E * (2 * KSTEPS) * NE + 2 * KK * NE;
+      constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;  // parity schedule: one NE-column group per output parity
+      constexpr bool first = S::first(E) && KK == first_nonzero_kk<KIND, KSTEPS, E>();   // overwrites the accumulator
+      umma_f16_c<!first>(acc + d_col, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
+    }
     if constexpr (KK + 1 < KSTEPS) issue_tile<KIND, KSTEPS, NE, MT, E, KK + 1>(acc, a_base, b_base, idesc);
     else issue_tile<KIND, KSTEPS, NE, MT, E + 1, 0>(acc, a_base, b_base, idesc);
   }
