@@ -33,6 +33,7 @@ struct UmmaParams {
   int npad, n_valid, tmem_cols, nw;  // nw = accumulator columns per CTA (N split over blockIdx.y)
   int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
   int epi, out_c, cpp, planar_out, res_pitch, out_f32;
+  unsigned long long kmask;  // bit ks = tap * nchunks + chunk set: that K block has non-zero weights (all ones if > 64 blocks)
   const float* bias;
   const float* beta;
   const __half* res;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.nw * p.kc * 2);
       for (int ks = 0; ks < ksteps; ++ks) {
+        if (ks < 64 && !((p.kmask >> ks) & 1ull)) continue;  // structurally zero K block (stride-2 convs on s2d input)
         const int tap = ks / p.nchunks, chunk = ks - tap * p.nchunks;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0, accum = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
+        if (ks < 64 && !((p.kmask >> ks) & 1ull)) continue;
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint64_t da = desc0 + (uint64_t)((tiles_base + stage * stage_bytes) >> 4);
@@ -475,6 +478,24 @@ int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
     if (!h.beta.empty()) (*beta)[n] = h.beta[colmap[n]];
   }
   L->kind = h.kind; L->taps = h.taps; L->cin = h.cin; L->kc = kc;
+  {
+    // K blocks (tap, kc-channel chunk) whose weights are all zero -- the structural zeros of a stride-2 conv written as 2x2
+    // taps over the space-to-depth input -- are neither loaded nor multiplied
+    const int nch = h.cin / kc;
+    unsigned long long m = ~0ull;
+    if (h.taps * nch <= 64) {
+      m = 0;
+      for (int t = 0; t < h.taps; ++t)
+        for (int k = 0; k < nch; ++k) {
+          bool nz = false;
+          for (int c = k * kc; c < (k + 1) * kc && !nz; ++c)
+            for (int n = 0; n < h.npad && !nz; ++n) nz = h.w[((size_t)t * h.cin + c) * h.npad + n] != 0.f;
+          if (nz) m |= 1ull << (t * nch + k);
+        }
+      if (!m) m = 1;  // an all-zero layer still has to write its accumulator
+    }
+    L->kmask = m;
+  }
   L->n = ps_layout ? 256 : h.n;
   L->npad = np;
   L->ps_cols = ps_layout ? 1 : 0;
@@ -518,6 +539,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   p.res_pitch = io.res_pitch ? io.res_pitch : io.out_c;
   p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
+  p.kmask = L.kmask;
   if (L.kind == CONV_3x3) {
     for (int t = 0; t < 9; ++t) { p.dy[t] = (signed char)(t / 3 - 1); p.dx[t] = (signed char)(t % 3 - 1); }
   } else {

@@ -25,6 +25,7 @@ struct UmmaLayer {
   int n = 0;       // valid GEMM columns
   int npad = 0;    // GEMM columns issued (multiple of 16, <= 256)
   int ps_cols = 0; // 1: columns permuted to the PixelShuffle-friendly order  ((par*4 + dy*2+dx)*16 + k), npad = 256
+  unsigned long long kmask = ~0ull;  // K blocks (tap * nchunks + chunk) with non-zero weights; zero blocks are skipped
 };
 
 // fp32 [tap][cin][npad] -> fp16 [tap][cin/kc][npad'][kc] (+ optional PixelShuffle column permutation);
