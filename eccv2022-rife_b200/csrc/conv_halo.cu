@@ -250,18 +250,20 @@ __device__ __forceinline__ void issue_tile(uint32_t acc, uint64_t a_base, uint64
 // weight-streaming variant: the MMAs of ONE schedule entry (one weight tile) for all MT stacked M-tiles
 template <int KIND, int KSTEPS, int NE, int MT, int E, int M = 0, int KK = 0>
 __device__ __forceinline__ void issue_entry(uint32_t acc0, uint32_t ncols, uint64_t a_base0, uint32_t mt_step,
-                                            uint64_t b_base, uint32_t idesc) {
+                                            uint64_t b_base, uint32_t idesc, int mt_eff) {
   using S = Sched<KIND>;
   if constexpr (M < MT) {
-    constexpr int pitch = TW + S::R;
-    constexpr int plane16 = (TH * MT + S::R) * pitch;
-    constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
-    constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;
-    umma_f16_c<!(S::first(E) && KK == 0)>(acc0 + (uint32_t)M * ncols + d_col,
-                                          a_base0 + (uint64_t)((uint32_t)M * mt_step + a_off), b_base + (uint64_t)(2 * KK * NE),
-                                          idesc);
-    if constexpr (KK + 1 < KSTEPS) issue_entry<KIND, KSTEPS, NE, MT, E, M, KK + 1>(acc0, ncols, a_base0, mt_step, b_base, idesc);
-    else issue_entry<KIND, KSTEPS, NE, MT, E, M + 1, 0>(acc0, ncols, a_base0, mt_step, b_base, idesc);
+    if (M == 0 || M < mt_eff) {  // stacked M-tiles below the image's last row are not computed
+      constexpr int pitch = TW + S::R;
+      constexpr int plane16 = (TH * MT + S::R) * pitch;
+      constexpr int a_off = 2 * KK * plane16 + (S::dy(E) + 1) * pitch + (S::dx(E) + 1);
+      constexpr int d_col = KIND == 2 ? (E >> 2) * NE : S::col16(E) * 16;
+      umma_f16_c<!(S::first(E) && KK == 0)>(acc0 + (uint32_t)M * ncols + d_col,
+                                            a_base0 + (uint64_t)((uint32_t)M * mt_step + a_off), b_base + (uint64_t)(2 * KK * NE),
+                                            idesc);
+    }
+    if constexpr (KK + 1 < KSTEPS) issue_entry<KIND, KSTEPS, NE, MT, E, M, KK + 1>(acc0, ncols, a_base0, mt_step, b_base, idesc, mt_eff);
+    else issue_entry<KIND, KSTEPS, NE, MT, E, M + 1, 0>(acc0, ncols, a_base0, mt_step, b_base, idesc, mt_eff);
   }
 }
 
@@ -552,6 +554,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait_t(smem_u32(&a_full[stage]), phase, t_af);
         tc_fence_after();
         const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
+        // stacked M-tiles that start below the last image row (H not a multiple of 16 * MT) are skipped altogether
+        const int ty_m = (tile / p.tiles_x) % p.tiles_y;
+        const int mt_eff = min(p.mt, (p.H - ty_m * p.mt * TH + TH - 1) / TH);
         if constexpr (KIND >= 0 && STREAM) {
           const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)NE * 16u, 128u);
           const uint32_t acc0 = tmem_base + (uint32_t)(buf * MT * p.ncols);
@@ -560,7 +565,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait_t(smem_u32(&b_full[bs]), bph, t_w);
             tc_fence_after();
             issue_entry<KIND, KSTEPS, NE, MT, E>(acc0, (uint32_t)p.ncols, a_desc0 + (uint64_t)sa16, mt_step,
-                                                 b_desc0 + (uint64_t)((w_smem + (uint32_t)(bs * p.wtile_al)) >> 4), idesc);
+                                                 b_desc0 + (uint64_t)((w_smem + (uint32_t)(bs * p.wtile_al)) >> 4), idesc, mt_eff);
             umma_commit(smem_u32(&b_empty[bs]));
             if (++bs == p.nb) { bs = 0; bph ^= 1; }
           };
@@ -569,10 +574,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t b_base = make_desc_noswz(w_smem, (uint32_t)NE * 16u, 128u);
 #pragma unroll
           for (int m = 0; m < MT; ++m)
-            issue_tile<KIND, KSTEPS, NE, MT>(tmem_base + (uint32_t)((buf * MT + m) * p.ncols),
-                                             a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step), b_base, idesc);
+            if (m < mt_eff)
+              issue_tile<KIND, KSTEPS, NE, MT>(tmem_base + (uint32_t)((buf * MT + m) * p.ncols),
+                                               a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step), b_base, idesc);
         } else {
-          for (int m = 0; m < p.mt; ++m) {
+          for (int m = 0; m < mt_eff; ++m) {
             const uint64_t a_base = a_desc0 + (uint64_t)(sa16 + (uint32_t)m * mt_step);
             const uint32_t acc = tmem_base + (uint32_t)((buf * p.mt + m) * p.ncols);
 #pragma unroll 4
@@ -727,6 +733,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         c.y0 = ty * MT * TH + ty_;
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
+          if (mi > 0 && (ty * MT + mi) * TH >= p.H) continue;   // M-tile below the image: not computed (see the MMA issuer)
 #pragma unroll
           for (int j = 0; j < NCOLS / 16; ++j) {
             if (ESPLIT == 2 && ((mi * (NCOLS / 16) + j) & 1) != ehalf) continue;
@@ -740,6 +747,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         c.y0 = ty * p.mt * TH + ty_;
         for (int jm = ehalf; jm < nchunk16 * p.mt; jm += ESPLIT) {
           const int mi = jm / nchunk16, j = jm - mi * nchunk16;
+          if (mi > 0 && (ty * p.mt + mi) * TH >= p.H) continue;
           float v[16];
           __syncwarp();
           tmem_ld16(trow + (uint32_t)((buf * p.mt + mi) * p.ncols + j * 16), v);
