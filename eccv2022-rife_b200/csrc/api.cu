@@ -277,8 +277,10 @@ int rife_weights_destroy(rife_weights* w) {
 
 // --------------------------------------------------------------------------------------------------
 // plan
+constexpr int kTileCtrs = 1024;
+
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, ctrs, stage_in0, stage_in1,
       stage_out, total;
   int s[5];   // block i works at H / s[i] * u[i]: scale_list[i] = s[i] / u[i] (one of the two is 1)
   int u[5];
@@ -336,6 +338,7 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   L->gridy = take((size_t)H * 4);
   L->tstep = take((size_t)B * 4);
   L->sync = take(256);   // grid-barrier counter of the ResConv chain kernel
+  L->ctrs = take(kTileCtrs * 4);   // one dynamic-tile-scheduling counter per halo-kernel launch of a call
   L->stage_in0 = take((size_t)(seq ? P + 1 : P) * H * W * C * 4);
   L->stage_in1 = take((size_t)(seq ? 0 : P) * H * W * C * 4);
   L->stage_out = take(N * C * 4);
@@ -352,6 +355,7 @@ struct rife_plan {
   int fh = 0, fw = 0;  // frame size seen by the caller (rife_plan_set_frame_size); 0 = H, W
   int chunk = 0;       // pairs per pass of the full-resolution stages (rife_plan_set_chunk); 0 = default
   unsigned int sync_host = 0;  // value of the ResConv chain's grid-barrier counter after everything enqueued so far
+  int next_ctr = 0;            // tile-scheduling counters handed out to the halo launches of the current call
   std::vector<float> ts_host;  // timesteps last written to the device buffer, and the stream they were written on
   cudaStream_t ts_stream = nullptr;
   bool ts_valid = false;
@@ -526,8 +530,19 @@ static int default_chunk_pairs() {
   return v;
 }
 
-static int run_conv(const rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
-  if (p->precision == RIFE_PRECISION_FP16) return hk ? launch_conv_halo(L.hk, io, st) : launch_conv_umma(L.h16, io, st);
+static bool dyn_tiles_on() {
+  static const bool on = !(getenv("RIFE_HK_DYN") && atoi(getenv("RIFE_HK_DYN")) == 0);  // A/B: static round robin
+  return on;
+}
+
+// halo-kernel launches take the call's next tile-scheduling counter (zeroed by the call's first kernel)
+static int run_conv(rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
+  if (p->precision == RIFE_PRECISION_FP16) {
+    if (!hk) return launch_conv_umma(L.h16, io, st);
+    ConvIO h = io;
+    if (dyn_tiles_on() && p->next_ctr < kTileCtrs) h.tile_ctr = (unsigned int*)p->at(p->L.ctrs) + p->next_ctr++;
+    return launch_conv_halo(L.hk, h, st);
+  }
   return launch_conv_f32(L.f32, io, st);
 }
 
@@ -570,6 +585,8 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.src1 = (char*)p->at(L.src) + (size_t)(p->seq ? 1 : p->P) * H * W * SRC_C * E;
   c.half_act = half_act;
   c.planar_head = half_act && w->head_hk;
+  c.tile_ctrs = (unsigned int*)p->at(L.ctrs); c.n_tile_ctrs = kTileCtrs;
+  p->next_ctr = 0;
   for (int i = 0; i < 5; ++i) c.any_up = c.any_up || L.u[i] > 1;
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
@@ -673,7 +690,9 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     if (narrow) {
       io.epi = EPI_PS8; io.out_c = 8;
       lev[i].pitch = 8;
+      if (dyn_tiles_on() && p->next_ctr < kTileCtrs) io.tile_ctr = (unsigned int*)p->at(L.ctrs) + p->next_ctr++;
       RIFE_STAGE(bn + ".lastconv", launch_conv_halo(w->blk[i].last8, io, st));
+      io.tile_ctr = nullptr;
     } else {
       RIFE_STAGE(bn + ".lastconv", run_conv(p, w->blk[i].last, io, hk_tail, st));
     }

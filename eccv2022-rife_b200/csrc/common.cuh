@@ -180,6 +180,7 @@ struct ConvIO {
   int res_pitch = 0;          // same for `res` (0 = out_c)
   int out_f32 = 0;            // NHWC tcgen05 kernel, EPI_LINEAR / EPI_CONVT only: the destination tensor is fp32
   int planar_out = 0;         // NHWC tcgen05 kernel, EPI_LRELU only: store planar-8 [B][C/8][H][W][8] (feeds conv_halo.cu)
+  unsigned int* tile_ctr = nullptr;  // halo kernel: device counter (zero when the kernel starts) for dynamic tile scheduling
 };
 
 int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);
@@ -221,6 +222,8 @@ struct PixelCtx {
   const void* src1;
   bool half_act;       // activation / src / tmp storage type: false = float, true = __half
   bool planar_head = false;  // Head input stored planar-8 (conv_halo.cu) instead of pixel-major
+  unsigned int* tile_ctrs = nullptr;  // the call's tile-scheduling counters, zeroed by the input-packing kernel
+  int n_tile_ctrs = 0;
 };
 
 // NCHW image (io dtype) -> SRC tensor channels 4..7 (+ zeros in 0..3) and the s2d Head input [2B][H/2][W/2][16]

@@ -55,6 +55,7 @@ struct HaloParams {
   __half* out_l[2];        // destination of even / odd layers
   unsigned int* sync;      // grid barrier counter: monotonic across launches (never reset)
   unsigned int sync_base;  // its value when this launch starts
+  unsigned int* tile_ctr;  // dynamic tile scheduling: zero-initialised counter of this launch (null: static round robin)
   int pdl_trig;    // launch_dependents: 0 implicit at CTA exit (default; measured best), 1 after the prologue, 2 after the last MMA
   long long* dbg;  // RIFE_HK_DEBUG=1: per-CTA role timers (8 x int64), else null
   signed char e_dy[MAX_ENTRIES], e_dx[MAX_ENTRIES];
@@ -164,6 +165,11 @@ __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int 
     __nanosleep(64);
   }
   asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy stores -> this CTA's TMA (async proxy) loads
+}
+
+__device__ __forceinline__ int ring_next_tile(const int* ring, const uint64_t* bars, int seq) {
+  mbar_wait(smem_u32(&bars[seq & 15]), ((uint32_t)seq >> 4) & 1u);
+  return *reinterpret_cast<const volatile int*>(&ring[seq & 15]);
 }
 
 template <int I> struct IntC { static constexpr int value = I; };
@@ -405,6 +411,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __shared__ __align__(8) uint64_t b_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t t_full[2];
   __shared__ __align__(8) uint64_t t_empty[2];
+  // tile ids travel from the TMA producer to the other roles through a 16-entry ring (entry seq & 15, barrier phase
+  // (seq >> 4) & 1; -1 = end of a layer): the producer takes its tiles either round robin or -- tile_ctr != null -- from a
+  // device-wide counter, so that a CTA that finishes early (cheap edge tiles, a faster SM) simply takes more tiles.  The
+  // producer is never more than stages + 2 < 16 tiles ahead of the slowest reader (a_empty / t_empty back-pressure).
+  __shared__ __align__(8) uint64_t tile_bar[16];
+  __shared__ int tile_ring[16];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_beta[128];
@@ -431,6 +443,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(smem_u32(&a_empty[s]), p.epi == EPI_RES ? 1 + NUM_EPI_WARPS : 1);
     }
     mbar_init(smem_u32(&w_full), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&tile_bar[i]), 1);
     if (STREAM) {
       for (int i = 0; i < p.nb; ++i) {
         mbar_init(smem_u32(&b_full[i]), 1);
@@ -486,7 +499,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // weights are constants; the activations are the previous kernel's output.  Everything else in this CTA
       // (MMAs, epilogue loads from the smem tile, output stores) is downstream of these loads.
       pdl_wait();
-      int stage = 0;
+      int stage = 0, seq = 0;
       uint32_t phase = 0;
       long long t_wait = 0;
       for (int l = 0; l < p.nlayers; ++l) {
@@ -503,27 +516,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
         const CUtensorMap* tm = (l & 1) ? &tm_b : &tm_a;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int tile = blockIdx.x;
+        while (tile < p.ntiles) {
           const int tx = tile % p.tiles_x;
           const int r = tile / p.tiles_x;
           const int ty = r % p.tiles_y, b = r / p.tiles_y;
+          // stacked M-tiles that start below the last image row (H not a multiple of 16 * MT) are skipped by the MMA
+          // issuer and the epilogue: their count rides in the ring entry's top bits
+          const int mt_eff = min(p.mt, (p.H - ty * p.mt * TH + TH - 1) / TH);
           mbar_wait_t(smem_u32(&a_empty[stage]), phase ^ 1, t_wait);
+          tile_ring[seq & 15] = tile | (mt_eff << 28);
+          mbar_arrive(smem_u32(&tile_bar[seq & 15]));
+          ++seq;
           const uint32_t fb = smem_u32(&a_full[stage]);
           mbar_expect_tx(fb, (uint32_t)p.a_tx_bytes);
           tma_load_4d(a_smem + stage * p.a_stage_bytes, tm, fb, (tx * TW - 1) * 8, ty * TH * p.mt - 1, 0, b);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tile = p.tile_ctr ? (int)(gridDim.x + atomicAdd(p.tile_ctr, 1u)) : tile + (int)gridDim.x;
         }
+        // end of this layer: an entry of -1 that takes a stage like a tile does (the MMA issuer learns about it through
+        // a_full, the other roles through tile_bar), completed by a plain arrive instead of a TMA transaction
+        mbar_wait_t(smem_u32(&a_empty[stage]), phase ^ 1, t_wait);
+        tile_ring[seq & 15] = -1;
+        mbar_arrive(smem_u32(&tile_bar[seq & 15]));
+        ++seq;
+        mbar_arrive(smem_u32(&a_full[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = t_wait;
     }
   } else if (STREAM && warp == 2 + NUM_EPI_WARPS) {
     if (lane == 0) {
       // ---------------- weight-tile producer: entry e of every tile -> ring slot (runs ahead across layers)
-      int bs = 0;
+      int bs = 0, seq = 0;
       uint32_t bph = 0;
       for (int l = 0; l < p.nlayers; ++l) {
         const uint8_t* wl = reinterpret_cast<const uint8_t*>(p.nlayers > 1 ? p.w_l[l] : p.w);
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        while (ring_next_tile(tile_ring, tile_bar, seq++) >= 0) {
           for (int e = 0; e < p.nentries; ++e) {
             mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
             const uint32_t fb = smem_u32(&b_full[bs]);
@@ -544,19 +573,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
       long long t_w = 0, t_te = 0, t_af = 0;
       const long long t_begin = clock64();
-      int stage = 0, it = 0, bs = 0;
+      int stage = 0, it = 0, bs = 0, seq = 0;
       uint32_t phase = 0, bph = 0;
       for (int l = 0; l < p.nlayers; ++l) {
       if (!STREAM) mbar_wait_t(smem_u32(&w_full), (uint32_t)(l & 1), t_w);
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      for (;; ++it) {
+        // the stage's a_full (acquire) also publishes the ring entry the producer wrote before arming it: no second wait
+        // on this thread, whose per-tile instruction count bounds the thin layers (18 MMAs per tile in block 4's conv0.0)
+        mbar_wait_t(smem_u32(&a_full[stage]), phase, t_af);
+        const int entry = *reinterpret_cast<const volatile int*>(&tile_ring[seq & 15]);
+        ++seq;
+        if (entry < 0) {  // end of the layer: hand the stage back like a tile would
+          umma_commit(smem_u32(&a_empty[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          break;
+        }
+        const int mt_eff = (KIND < 0 || MT > 1) ? (entry >> 28) : 1;
         const int buf = it & 1;
         mbar_wait_t(smem_u32(&t_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u, t_te);
-        mbar_wait_t(smem_u32(&a_full[stage]), phase, t_af);
         tc_fence_after();
         const uint32_t sa16 = (a_smem + stage * p.a_stage_bytes) >> 4;
-        // stacked M-tiles that start below the last image row (H not a multiple of 16 * MT) are skipped altogether
-        const int ty_m = (tile / p.tiles_x) % p.tiles_y;
-        const int mt_eff = min(p.mt, (p.H - ty_m * p.mt * TH + TH - 1) / TH);
         if constexpr (KIND >= 0 && STREAM) {
           const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)NE * 16u, 128u);
           const uint32_t acc0 = tmem_base + (uint32_t)(buf * MT * p.ncols);
@@ -612,13 +648,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nchunk16 = p.ncols >> 4;
     const size_t plane = (size_t)p.H * p.W * 8;  // elements per planar-8 channel group
-    int it = 0, stage = 0;
+    int it = 0, stage = 0, seq = 0;
     uint32_t phase = 0;
     long long t_tf = 0;
     const long long t_begin = clock64();
     for (int l = 0; l < p.nlayers; ++l) {
     __half* const out_l = p.nlayers > 1 ? p.out_l[l & 1] : p.out;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      const int entry = ring_next_tile(tile_ring, tile_bar, seq++);
+      if (entry < 0) {  // end of the layer: the entry took a stage
+        if ((EPI >= 0 ? EPI : p.epi) == EPI_RES) {
+          mbar_wait(smem_u32(&a_full[stage]), phase);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&a_empty[stage]));
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        break;
+      }
+      const int tile = entry & 0x0FFFFFFF;
       const int tx = tile % p.tiles_x;
       const int r = tile / p.tiles_x;
       const int ty = r % p.tiles_y, b = r / p.tiles_y;
@@ -1075,6 +1122,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par;
   p.w = L.w; p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
+  p.tile_ctr = chain ? nullptr : io.tile_ctr;   // (a chain would need one counter per layer)
   for (int e = 0; e < L.nentries; ++e) {
     p.e_dy[e] = L.e_dy[e]; p.e_dx[e] = L.e_dx[e]; p.e_col16[e] = L.e_col16[e]; p.e_first[e] = L.e_first[e];
   }

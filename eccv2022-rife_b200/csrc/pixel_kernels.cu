@@ -213,14 +213,23 @@ __device__ __forceinline__ void eval_state(const LevelsArg& L, int nlev, int j0,
   for (int c = 0; c < 4; ++c) flow[c] = (j == 0) ? last[c] * sc : flow[c] + last[c] * sc;
 }
 
+// The first kernel of a call also resets the call's tile-scheduling counters (conv_halo.cu): every conv of the previous call
+// on this plan has completed by then (stream order; pdl_wait() makes completion transitive).
+__device__ __forceinline__ void zero_tile_ctrs(unsigned int* __restrict__ ctrs, int n) {
+  if (ctrs && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ctrs[i] = 0u;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // prep: NCHW images -> SRC tensors (ch 4..7; ch 0..3 zero until Head writes them) + s2d Head input
 template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                    T* __restrict__ src_all, T* __restrict__ head_in, int F, int nf0,
-                                                   int C, int H, int W, int planar, int write_src, ImgLayout lay) {
+                                                   int C, int H, int W, int planar, int write_src, ImgLayout lay,
+                                                   unsigned int* __restrict__ ctrs, int nctrs) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
+  zero_tile_ctrs(ctrs, nctrs);
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)F * H2 * W2;
@@ -271,9 +280,11 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 // by Head.cnn3's epilogue).  One thread converts a 2 x 8 pixel strip: 16-byte loads per channel row, 16-byte stores.
 template <typename Tio>
 __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
-                                                          __half* __restrict__ head_in, int nf0, int C, int H, int W) {
+                                                          __half* __restrict__ head_in, int nf0, int C, int H, int W,
+                                                          unsigned int* __restrict__ ctrs, int nctrs) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
+  zero_tile_ctrs(ctrs, nctrs);
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;  // strip index along x (8 pixels)
   const int y2 = blockIdx.y, fb = blockIdx.z;            // frame index: img0's nf0 frames first, then img1's
@@ -322,9 +333,11 @@ __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_kernel(const 
 __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_u8_kernel(const uint8_t* __restrict__ img0,
                                                                              const uint8_t* __restrict__ img1,
                                                                              __half* __restrict__ head_in, int nf0, int h,
-                                                                             int H, int W) {
+                                                                             int H, int W, unsigned int* __restrict__ ctrs,
+                                                                             int nctrs) {
   pdl_wait();
   RIFE_PIX_TRIGGER();
+  zero_tile_ctrs(ctrs, nctrs);
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;
   const int y2 = blockIdx.y, fb = blockIdx.z;
@@ -1100,9 +1113,9 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   if (c.planar_head && c.half_act && c.W % 8 == 0 && fh == c.H && fw == c.W && io_dtype != RIFE_U8) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
     if (io_dtype == RIFE_F16)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
     else if (io_dtype == RIFE_F32)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
     else
       RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
     RIFE_LAUNCH_CHECK();
@@ -1112,7 +1125,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
       ((uintptr_t)img0 % 8) == 0 && ((uintptr_t)img1 % 8) == 0 && ((size_t)fh * fw * 3) % 8 == 0) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
     RIFE_CUDA_TRY(launch_pdl(prep_planar_u8_kernel, g, dim3(256), 0, st, (const uint8_t*)img0, (const uint8_t*)img1,
-                             (__half*)head_in, c.nf0, fh, c.H, c.W));
+                             (__half*)head_in, c.nf0, fh, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
     RIFE_LAUNCH_CHECK();
     return RIFE_OK;
   }
@@ -1121,7 +1134,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
 #define RIFE_PREP(TIO, T)                                                                                        \
   RIFE_CUDA_TRY(launch_pdl(prep_kernel<TIO, T>, grid, dim3(256), 0, st, (const TIO*)img0, (const TIO*)img1,            \
                            (T*)src_all, (T*)head_in, c.F, c.nf0, c.C, c.H, c.W, c.planar_head ? 1 : 0,                \
-                           c.planar_head ? 0 : 1, lay))
+                           c.planar_head ? 0 : 1, lay, c.tile_ctrs, c.n_tile_ctrs))
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
