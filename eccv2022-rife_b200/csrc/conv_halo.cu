@@ -1159,6 +1159,9 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   const bool coop = chain != nullptr;
   int grid = num_sms() * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
+  // with only a few tiles per CTA the counter's round trip costs more than the balance gains (block 2: 3.6 tiles per CTA)
+  static const int dyn_min = getenv("RIFE_HK_DYN_MIN") ? atoi(getenv("RIFE_HK_DYN_MIN")) : 4;
+  if (p.ntiles < dyn_min * grid) p.tile_ctr = nullptr;
   static const bool debug = getenv("RIFE_HK_DEBUG") != nullptr;
   p.dbg = nullptr;
   static const int pdl_trig = getenv("RIFE_PDL_HALO_TRIGGER") ? atoi(getenv("RIFE_PDL_HALO_TRIGGER")) : 0;
