@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RIFE_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
-    ap.add_argument("--pairs", type=int, default=12, help="frame pairs per step per GPU (batch of one Model.inference)")
+    ap.add_argument("--pairs", type=int, default=16, help="frame pairs per step per GPU (batch of one Model.inference)")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("RIFE_CHUNK_PAIRS", "0")),
                     help="pairs per pass of the 1/2- and full-resolution stages (rife_plan_set_chunk); 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
