@@ -40,6 +40,7 @@ def test_error_paths_without_gpu(pkg):
     # null arguments are rejected before any CUDA call
     assert lib.rife_weights_create(None, 0, None, None, None, 0) == -1
     assert lib.rife_plan_set_profiling(None, 1) == -1
+    assert lib.rife_plan_set_chunk(None, 4) == -1
     assert lib.rife_plan_workspace_bytes_ex(3, 3, 1, 3, 64, 64, 1.0, 1) > lib.rife_plan_workspace_bytes(3, 3, 64, 64, 1.0, 1)
     assert lib.rife_scene_ssim(None, None, 0, 1, 3, 8, 8, 32, None, None) == -1
     assert lib.rife_launch_count() == launches                                   # none of the above launched anything

@@ -98,3 +98,44 @@ def test_shard_range(pkg):
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         pkg.shard_range(4, 2, 2)
+
+
+def test_interpolation_helpers_match_reference_semantics(pkg):
+    """eccv2022-rife_b200/interpolation.py against the reference's own rife_app/utils/interpolation.py (loaded by path in the
+    build container; skipped where /root/reference does not exist) with a stand-in model whose inference is a cheap
+    non-linear function of the two frames: same number of frames, same order, same values -- while issuing one
+    model.inference call per refinement stage instead of one per adjacent pair."""
+    import importlib.util
+    import os
+    import pytest
+    import torch
+    ref_path = "/root/reference/rife_app/utils/interpolation.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference checkout not present")
+    spec = importlib.util.spec_from_file_location("ref_interpolation", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ours = importlib.import_module("eccv2022-rife_b200.interpolation")
+
+    class Fake:
+        def __init__(self):
+            self.calls = 0
+
+        def inference(self, a, b, timestep=0.5, scale=1.0):
+            self.calls += 1
+            return 0.5 * (a + b) + 0.1 * torch.sin(3.0 * a) * torch.cos(2.0 * b) * scale
+
+    g = torch.Generator().manual_seed(3)
+    i0, i1 = torch.rand(2, 3, 8, 8, generator=g), torch.rand(2, 3, 8, 8, generator=g)
+    for n in (0, 1, 2, 4):
+        m_ref, m_ours = Fake(), Fake()
+        want = ref.progressive_interpolate_frames(i0, i1, n, m_ref, 0.5)
+        got = ours.progressive_interpolate_frames(i0, i1, n, m_ours, 0.5)
+        assert len(got) == len(want) == (2 ** n - 1 if n else 0)
+        assert all(torch.allclose(x, y, atol=1e-6) for x, y in zip(got, want))
+        assert m_ours.calls == n and m_ref.calls == (2 ** n - 1 if n else 0)
+        assert all(torch.allclose(x, y, atol=1e-6)
+                   for x, y in zip(ours.recursive_interpolate_video_frames(i0, i1, n, Fake(), 0.5), want))
+    want = ref.generate_interpolated_frames(i0, i1, 3, Fake())
+    got = ours.generate_interpolated_frames(i0, i1, 3, Fake())
+    assert len(got) == len(want) == 9 and all(torch.allclose(x, y, atol=1e-6) for x, y in zip(got, want))
