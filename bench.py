@@ -208,7 +208,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     if args.chunk:
         os.environ["RIFE_CHUNK_PAIRS"] = str(args.chunk)    # read once by the library

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RIFE_B200_LIB") or os.path.join(_HERE, "csrc", "librife_b200.so")   # override: A/B builds
 
 RIFE_F32, RIFE_F16, RIFE_U8 = 0, 1, 2
-PRECISION_FP32, PRECISION_FP16 = 0, 1
+PRECISION_FP32, PRECISION_FP16, PRECISION_BF16 = 0, 1, 2
 
 # every symbol declared in include/rife_b200.h
 SYMBOLS = [

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "conv_halo.cuh"
+#include "conv_strip.cuh"
 #include "conv_umma.cuh"
 
 namespace rife {
@@ -110,7 +111,11 @@ struct DevLayer {
   UmmaLayer h16;      // present when precision == FP16: NHWC tcgen05 kernel (conv_umma.cu)
   HaloLayer hk;       // present when precision == FP16 and the layer fits the halo kernel (conv_halo.cu)
   bool use_hk = false;
+  // RIFE_PRECISION_BF16: operand type of this layer's input + weights, and storage type of its activation output
+  bool in_bf16 = false, out_bf16 = false;
 };
+
+static inline bool is_half_mode(int precision) { return precision == RIFE_PRECISION_FP16 || precision == RIFE_PRECISION_BF16; }
 
 }  // namespace rife
 
@@ -125,6 +130,11 @@ struct rife_weights {
   // 2 = conv0.* on the NHWC kernel (conv0.1 stores planar-8), ResConv x8 + lastconv on the halo kernel (streamed weights)
   int blk_hk[5] = {0, 0, 0, 0, 0};
   std::vector<void*> allocs;
+  // conv_strip.cu: Head.cnn1 + cnn2 as one launch, and the ResConv layers (2j, 2j + 1) of IFBlock 4 as one launch each
+  StripPair strip_head;
+  bool has_strip_head = false;
+  StripPair strip_res4[4];
+  bool has_strip_res4 = false;
   DevLayer head[4];
   struct Block {
     DevLayer conv00, conv01, res[8], last;
@@ -141,7 +151,9 @@ static int upload(rife_weights* w, const void* host, size_t bytes, void** dev) {
   return RIFE_OK;
 }
 
-static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool ps_layout = false) {
+// in_bf / out_bf (RIFE_PRECISION_BF16 only): see DevLayer
+static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool ps_layout = false, bool in_bf = false,
+                        bool out_bf = false) {
   void *pw, *pb, *pbeta = nullptr;
   RIFE_TRY(upload(w, h.w.data(), h.w.size() * 4, &pw));
   RIFE_TRY(upload(w, h.bias.data(), h.bias.size() * 4, &pb));
@@ -150,11 +162,12 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool p
   d->f32.bias = (const float*)pb;
   d->f32.beta = (const float*)pbeta;
   d->f32.kind = h.kind; d->f32.cin = h.cin; d->f32.n = h.n; d->f32.npad = h.npad;
-  if (w->precision == RIFE_PRECISION_FP16) {
+  d->in_bf16 = in_bf; d->out_bf16 = out_bf;
+  if (is_half_mode(w->precision)) {
     void *ph = nullptr, *phb = nullptr, *phbeta = nullptr;
     std::vector<__half> packed;
     std::vector<float> hb, hbeta;
-    RIFE_TRY(umma_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->h16));
+    RIFE_TRY(umma_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->h16, in_bf));
     RIFE_TRY(upload(w, packed.data(), packed.size() * sizeof(__half), &ph));
     RIFE_TRY(upload(w, hb.data(), hb.size() * 4, &phb));
     if (!hbeta.empty()) RIFE_TRY(upload(w, hbeta.data(), hbeta.size() * 4, &phbeta));
@@ -163,7 +176,7 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool p
     d->h16.beta = (const float*)phbeta;
     if (!w->force_nhwc && halo_fits(h, ps_layout)) {
       void *pk = nullptr, *pkb = nullptr, *pkbeta = nullptr;
-      RIFE_TRY(halo_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->hk));
+      RIFE_TRY(halo_pack_weights(h, ps_layout, &packed, &hb, &hbeta, &d->hk, in_bf));
       RIFE_TRY(upload(w, packed.data(), packed.size() * sizeof(__half), &pk));
       RIFE_TRY(upload(w, hb.data(), hb.size() * 4, &pkb));
       if (!hbeta.empty()) RIFE_TRY(upload(w, hbeta.data(), hbeta.size() * 4, &pkbeta));
@@ -176,6 +189,29 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool p
   return RIFE_OK;
 }
 
+static bool strip_enabled() {
+  static const bool on = !(getenv("RIFE_STRIP") && atoi(getenv("RIFE_STRIP")) == 0);   // A/B switch: per-layer halo kernel
+  return on;
+}
+
+// two consecutive 3x3 c -> c layers (c = 16 / 32) packed for the fused strip kernel; biases / betas are those already
+// uploaded for the per-layer kernels
+static int upload_strip_pair(rife_weights* w, const HostLayer& a, const HostLayer& b, const DevLayer& da, const DevLayer& db,
+                             bool res, bool bf, StripPair* out) {
+  std::vector<__half> pa, pb;
+  RIFE_TRY(strip_pack_weights(a, &pa, bf));
+  RIFE_TRY(strip_pack_weights(b, &pb, bf));
+  pa.insert(pa.end(), pb.begin(), pb.end());
+  void* pw = nullptr;
+  RIFE_TRY(upload(w, pa.data(), pa.size() * sizeof(__half), &pw));
+  out->w = (const __half*)pw;
+  out->bias[0] = da.f32.bias; out->bias[1] = db.f32.bias;
+  out->beta[0] = res ? da.f32.beta : nullptr; out->beta[1] = res ? db.f32.beta : nullptr;
+  out->res[0] = out->res[1] = res ? 1 : 0;
+  out->c = a.cin;
+  return RIFE_OK;
+}
+
 extern "C" {
 
 int rife_abi_version(void) { return RIFE_B200_ABI_VERSION; }
@@ -185,8 +221,12 @@ uint64_t rife_launch_count(void) { return g_launch_count.load(); }
 int rife_weights_create(rife_weights** out, int n, const char* const* names, const float* const* data,
                         const int64_t* numel, int precision) {
   if (!out || !names || !data || !numel) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_weights_create: null argument");
-  if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16)
-    RIFE_FAIL(RIFE_ERR_DTYPE, "rife_weights_create: precision must be RIFE_PRECISION_FP32 or RIFE_PRECISION_FP16");
+  if (precision != RIFE_PRECISION_FP32 && !is_half_mode(precision))
+    RIFE_FAIL(RIFE_ERR_DTYPE, "rife_weights_create: precision must be RIFE_PRECISION_FP32, RIFE_PRECISION_FP16 or RIFE_PRECISION_BF16");
+  // bf16 mode: every conv whose input is itself a conv activation runs bf16 x bf16 and every conv activation is stored
+  // as bf16; the layers that read a pixel-kernel product (Head.cnn0: the s2d frame, conv0.0: the block input) keep fp16
+  // operands, and the tensors the pixel kernels read (SRC, tmp) stay fp16 -- see DESIGN.md section 2
+  const bool bf = precision == RIFE_PRECISION_BF16;
   std::map<std::string, std::pair<const float*, int64_t>> sd;
   for (int i = 0; i < n; ++i) sd[names[i]] = {data[i], numel[i]};
   std::string missing;
@@ -215,10 +255,17 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
     const float *w2 = get("encode.cnn2.weight", 16 * 16 * 9), *b2 = get("encode.cnn2.bias", 16);
     const float *w3 = get("encode.cnn3.weight", 16 * 4 * 16), *b3 = get("encode.cnn3.bias", 4);
     if (!missing.empty()) { set_error("rife_weights_create: bad tensor " + missing); return fail(RIFE_ERR_WEIGHTS); }
-    if ((st = upload_layer(w, pack_conv3x3_s2d(w0, b0, 16, 3, 3, 16), &w->head[0]))) return fail(st);
-    if ((st = upload_layer(w, pack_conv3x3(w1, b1, 16, 16, 16), &w->head[1]))) return fail(st);
-    if ((st = upload_layer(w, pack_conv3x3(w2, b2, 16, 16, 16), &w->head[2]))) return fail(st);
-    if ((st = upload_layer(w, pack_convT(w3, b3, 16, 4, 16), &w->head[3]))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w0, b0, 16, 3, 3, 16), &w->head[0], false, false, bf))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3(w1, b1, 16, 16, 16), &w->head[1], false, bf, bf))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3(w2, b2, 16, 16, 16), &w->head[2], false, bf, bf))) return fail(st);
+    if ((st = upload_layer(w, pack_convT(w3, b3, 16, 4, 16), &w->head[3], false, bf, false))) return fail(st);
+    if (is_half_mode(precision) && strip_enabled() && w->head[1].use_hk && w->head[2].use_hk) {
+      const HostLayer h1 = pack_conv3x3(w1, b1, 16, 16, 16), h2 = pack_conv3x3(w2, b2, 16, 16, 16);
+      if (strip_fits(h1) && strip_fits(h2)) {
+        if ((st = upload_strip_pair(w, h1, h2, w->head[1], w->head[2], false, bf, &w->strip_head))) return fail(st);
+        w->has_strip_head = true;
+      }
+    }
   }
   // ---- IFBlocks (train_log/IFNet_HDv3.py:57-76, 95-99)
   for (int i = 0; i < 5; ++i) {
@@ -230,8 +277,8 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
     const float *w01 = get(pre + "conv0.1.0.weight", (int64_t)c * (c / 2) * 9), *b01 = get(pre + "conv0.1.0.bias", c);
     const float *wl = get(pre + "lastconv.0.weight", (int64_t)c * kLastCo * 16), *bl = get(pre + "lastconv.0.bias", kLastCo);
     if (!missing.empty()) { set_error("rife_weights_create: bad tensor " + missing); return fail(RIFE_ERR_WEIGHTS); }
-    if ((st = upload_layer(w, pack_conv3x3_s2d(w00, b00, c / 2, p, XIN_C, 4 * XIN_C), &B.conv00))) return fail(st);
-    if ((st = upload_layer(w, pack_conv3x3_s2d(w01, b01, c, c / 2, c / 2, 2 * c), &B.conv01))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w00, b00, c / 2, p, XIN_C, 4 * XIN_C), &B.conv00, false, false, bf))) return fail(st);
+    if ((st = upload_layer(w, pack_conv3x3_s2d(w01, b01, c, c / 2, c / 2, 2 * c), &B.conv01, false, bf, bf))) return fail(st);
     for (int j = 0; j < 8; ++j) {
       const std::string rp = pre + "convblock." + std::to_string(j) + ".";
       const float *wr = get(rp + "conv.weight", (int64_t)c * c * 9), *br = get(rp + "conv.bias", c);
@@ -240,17 +287,30 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
       HostLayer L = pack_conv3x3(wr, br, c, c, c);
       L.beta.assign(L.npad, 0.f);
       for (int k = 0; k < c; ++k) L.beta[k] = be[k];
-      if ((st = upload_layer(w, L, &B.res[j]))) return fail(st);
+      if ((st = upload_layer(w, L, &B.res[j], false, bf, bf))) return fail(st);
+    }
+    if (i == 4 && is_half_mode(precision) && strip_enabled() && B.res[0].use_hk) {
+      bool ok = true;
+      for (int j = 0; j < 8 && ok; j += 2) {
+        HostLayer hp[2];
+        for (int k = 0; k < 2; ++k) {
+          const std::string rp = pre + "convblock." + std::to_string(j + k) + ".";
+          hp[k] = pack_conv3x3(get(rp + "conv.weight", (int64_t)c * c * 9), get(rp + "conv.bias", c), c, c, c);
+        }
+        ok = strip_fits(hp[0]) && strip_fits(hp[1]);
+        if (ok && (st = upload_strip_pair(w, hp[0], hp[1], B.res[j], B.res[j + 1], true, bf, &w->strip_res4[j / 2]))) return fail(st);
+      }
+      w->has_strip_res4 = ok;
     }
     const HostLayer hl = pack_convT(wl, bl, c, kLastCo, c);
-    if ((st = upload_layer(w, hl, &B.last, /*ps_layout=*/true))) return fail(st);
+    if ((st = upload_layer(w, hl, &B.last, /*ps_layout=*/true, bf, false))) return fail(st);
     if (i == 4 && B.last.use_hk && halo_fits(hl, 2)) {
       // nothing downstream reads the last block's feat channels (IFNet_HDv3.py:148-159): Model.inference runs a lastconv
       // with 5 of the 13 output channels
       std::vector<__half> packed;
       std::vector<float> hb, hbeta;
       void *pk = nullptr, *pkb = nullptr;
-      if ((st = halo_pack_weights(hl, 2, &packed, &hb, &hbeta, &B.last8))) return fail(st);
+      if ((st = halo_pack_weights(hl, 2, &packed, &hb, &hbeta, &B.last8, bf))) return fail(st);
       if ((st = upload(w, packed.data(), packed.size() * sizeof(__half), &pk))) return fail(st);
       if ((st = upload(w, hb.data(), hb.size() * 4, &pkb))) return fail(st);
       B.last8.w = (const __half*)pk;
@@ -294,7 +354,7 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   if (C != 3 && C != 4) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: C must be 3 or 4 (IFNet_HDv3.py:121-123 splits an RGB/RGBA pair)");
   if (!(scale == 1.f || scale == 0.5f || scale == 0.25f || scale == 2.f || scale == 4.f))
     RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be one of 0.25, 0.5, 1, 2, 4 (inference_video.py:92)");
-  if (precision != RIFE_PRECISION_FP32 && precision != RIFE_PRECISION_FP16) RIFE_FAIL(RIFE_ERR_DTYPE, "plan: bad precision");
+  if (precision != RIFE_PRECISION_FP32 && !is_half_mode(precision)) RIFE_FAIL(RIFE_ERR_DTYPE, "plan: bad precision");
   const int base[5] = {16, 8, 4, 2, 1};
   bool any_up = false;
   for (int i = 0; i < 5; ++i) {  // scale_list = [16, 8, 4, 2, 1] / scale, RIFE_HDv3.py:58
@@ -307,7 +367,7 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   if (H % mult || W % mult)
     RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale = " + std::to_string(mult) + " (got " +
                                   std::to_string(H) + "x" + std::to_string(W) + ")");
-  const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
+  const size_t E = is_half_mode(precision) ? 2 : 4;
   const size_t N = (size_t)B * H * W, NF = (size_t)F * H * W;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -536,14 +596,16 @@ static bool dyn_tiles_on() {
 }
 
 // halo-kernel launches take the call's next tile-scheduling counter (zeroed by the call's first kernel)
-static int run_conv(rife_plan* p, const DevLayer& L, const ConvIO& io, bool hk, cudaStream_t st) {
-  if (p->precision == RIFE_PRECISION_FP16) {
+static int run_conv(rife_plan* p, const DevLayer& L, const ConvIO& io_, bool hk, cudaStream_t st) {
+  if (is_half_mode(p->precision)) {
+    ConvIO io = io_;
+    io.in_bf16 = L.in_bf16 ? 1 : 0; io.out_bf16 = L.out_bf16 ? 1 : 0;
     if (!hk) return launch_conv_umma(L.h16, io, st);
     ConvIO h = io;
     if (dyn_tiles_on() && p->next_ctr < kTileCtrs) h.tile_ctr = (unsigned int*)p->at(p->L.ctrs) + p->next_ctr++;
     return launch_conv_halo(L.hk, h, st);
   }
-  return launch_conv_f32(L.f32, io, st);
+  return launch_conv_f32(L.f32, io_, st);
 }
 
 static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
@@ -557,7 +619,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   const rife_weights* w = p->w;
   const PlanLayout& L = p->L;
   const int B = p->B, H = p->H, W = p->W;
-  const bool half_act = p->precision == RIFE_PRECISION_FP16;
+  const bool half_act = is_half_mode(p->precision);
   const size_t E = half_act ? 2 : 4;
   const size_t N = (size_t)B * H * W;
 
@@ -597,11 +659,21 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     io.B = c.F; io.H = H / 2; io.W = W / 2;
     io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;
     RIFE_STAGE("head.cnn0", run_conv(p, w->head[0], io, c.planar_head, st));
-    io.in = p->at(L.head_a); io.out = p->at(L.head_b);
-    RIFE_STAGE("head.cnn1", run_conv(p, w->head[1], io, c.planar_head, st));
-    io.in = p->at(L.head_b); io.out = p->at(L.head_a);
-    RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, c.planar_head, st));
-    io.in = p->at(L.head_a); io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
+    const void* head_feat = p->at(L.head_a);
+    if (c.planar_head && w->has_strip_head) {
+      // cnn1 + cnn2 in one launch: the activation between them never leaves shared memory (conv_strip.cu)
+      io.in = p->at(L.head_a); io.out = p->at(L.head_b);
+      io.in_bf16 = io.out_bf16 = w->head[1].in_bf16 ? 1 : 0;
+      RIFE_STAGE("head.cnn1+2", launch_conv_strip2(w->strip_head, io, st));
+      io.in_bf16 = io.out_bf16 = 0;
+      head_feat = p->at(L.head_b);
+    } else {
+      io.in = p->at(L.head_a); io.out = p->at(L.head_b);
+      RIFE_STAGE("head.cnn1", run_conv(p, w->head[1], io, c.planar_head, st));
+      io.in = p->at(L.head_b); io.out = p->at(L.head_a);
+      RIFE_STAGE("head.cnn2", run_conv(p, w->head[2], io, c.planar_head, st));
+    }
+    io.in = head_feat; io.out = p->at(L.src); io.epi = EPI_HEADT; io.out_c = SRC_C; io.co_per_par = 4;
     io.res = c.planar_head ? p->at(L.head_in) : nullptr;  // halo kernel: assembles the full SRC pixel (see conv_halo.cu)
     RIFE_STAGE("head.cnn3", run_conv(p, w->head[3], io, c.planar_head, st));
   }
@@ -670,6 +742,17 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
       if (rc < 0) return rc;
       chained = rc == 0;   // 1: this shape cannot be chained (no instantiation / not co-resident)
     }
+    if (!chained && i == 4 && hk_tail && w->has_strip_res4) {
+      // ResConv layers (2j, 2j + 1) as one launch each (conv_strip.cu)
+      for (int j = 0; j < 4; ++j) {
+        io.in = cur; io.res = nullptr; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
+        io.in_bf16 = io.out_bf16 = w->blk[i].res[0].in_bf16 ? 1 : 0;
+        RIFE_STAGE(bn + ".res", launch_conv_strip2(w->strip_res4[j], io, st));
+        io.in_bf16 = io.out_bf16 = 0;
+        void* t = cur; cur = nxt; nxt = t;
+      }
+      chained = true;
+    }
     if (!chained) {
       for (int j = 0; j < 8; ++j) {  // ResConv x8 (IFNet_HDv3.py:63-72)
         io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
@@ -689,6 +772,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
                         !c.any_up && outs->merged && !per_level_outputs;
     if (narrow) {
       io.epi = EPI_PS8; io.out_c = 8;
+      io.in_bf16 = w->blk[i].last.in_bf16 ? 1 : 0; io.out_bf16 = 0;
       lev[i].pitch = 8;
       if (dyn_tiles_on() && p->next_ctr < kTileCtrs) io.tile_ctr = (unsigned int*)p->at(L.ctrs) + p->next_ctr++;
       RIFE_STAGE(bn + ".lastconv", launch_conv_halo(w->blk[i].last8, io, st));
@@ -834,14 +918,17 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
                            const float* residual_nchw, float* y_nchw, int epi, int out_c_store, int cpp, int out_C,
                            int out_H, int out_W, int out_Cpad, cudaStream_t st) {
   rife_weights tmpw;
-  tmpw.force_nhwc = precision == 3;  // test hook: RIFE_PRECISION_FP16 through the NHWC tcgen05 kernel only
+  // test hooks: 3 = RIFE_PRECISION_FP16 through the NHWC tcgen05 kernel only, 4 = the same for RIFE_PRECISION_BF16
+  tmpw.force_nhwc = precision == 3 || precision == 4;
   if (precision == 3) precision = RIFE_PRECISION_FP16;
+  if (precision == 4) precision = RIFE_PRECISION_BF16;
   tmpw.precision = precision;
   cudaGetDevice(&tmpw.device);
   DevLayer d;
-  int rc = upload_layer(&tmpw, h, &d, epi == EPI_PS);
-  const size_t E = precision == RIFE_PRECISION_FP16 ? 2 : 4;
-  (void)E;
+  const bool bf = precision == RIFE_PRECISION_BF16;
+  // bf16 mode: bf16 operands; the activation epilogues store bf16, the scatter epilogues (PixelShuffle / ConvT) fp16
+  const bool obf = bf && (epi == EPI_LRELU || epi == EPI_LINEAR || epi == EPI_RES);
+  int rc = upload_layer(&tmpw, h, &d, epi == EPI_PS, bf, obf);
   float *xin = nullptr, *res = nullptr, *yout = nullptr;
   const int gh = s2d ? H / 2 : H, gw = s2d ? W / 2 : W;  // GEMM row grid
   const int cin_act = s2d ? h.cin / 4 : h.cin;
@@ -869,7 +956,8 @@ static int run_single_conv(HostLayer& h, int precision, const float* x_nchw, int
   ConvIO io;
   io.B = B; io.H = gh; io.W = gw; io.in = xin; io.res = res; io.out = yout; io.epi = epi; io.out_c = out_c_store;
   io.co_per_par = cpp;
-  if (precision == RIFE_PRECISION_FP16) {
+  io.in_bf16 = bf ? 1 : 0; io.out_bf16 = obf ? 1 : 0;
+  if (is_half_mode(precision)) {
     // streamed-weight halo instantiations exist for the ResConv / lastconv epilogues only
     if (d.use_hk && !(d.hk.stream && epi != EPI_RES && epi != EPI_PS)) RIFE_SC(launch_conv_halo_f32io(d.hk, io, st));
     else RIFE_SC(launch_conv_umma_f32io(d.h16, io, st));

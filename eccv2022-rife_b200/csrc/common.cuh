@@ -1,8 +1,10 @@
 // Shared declarations for the RIFE B200 kernels (device helpers, layer descriptors, launch API).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <atomic>
 #include <string>
@@ -103,6 +105,43 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// 16-bit activation storage that is fp16 or bf16 by a (warp-uniform) run-time flag: RIFE_PRECISION_BF16 keeps the conv
+// activations inside the Head / IFBlocks in bf16 (same range as fp32), everything else of the fp16 pipeline in fp16
+__device__ __forceinline__ uint32_t pack2x(float a, float b, bool bf) {
+  if (bf) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2x(uint32_t u, bool bf) {
+  if (bf) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ uint4 pack8x(const float (&v)[8], bool bf) {
+  uint4 u;
+  u.x = pack2x(v[0], v[1], bf); u.y = pack2x(v[2], v[3], bf); u.z = pack2x(v[4], v[5], bf); u.w = pack2x(v[6], v[7], bf);
+  return u;
+}
+__device__ __forceinline__ void unpack8x(const uint4& u, bool bf, float (&v)[8]) {
+  float2 f;
+  f = unpack2x(u.x, bf); v[0] = f.x; v[1] = f.y;
+  f = unpack2x(u.y, bf); v[2] = f.x; v[3] = f.y;
+  f = unpack2x(u.z, bf); v[4] = f.x; v[5] = f.y;
+  f = unpack2x(u.w, bf); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ void st8x(__half* p, const float (&v)[8], bool bf) { *reinterpret_cast<uint4*>(p) = pack8x(v, bf); }
+// host: fp32 -> the 16-bit pattern of the layer's operand type (round to nearest even), carried in a __half slot
+inline __half host_cvt16(float x, bool bf) {
+  if (!bf) return __float2half_rn(x);
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);   // RNE (NaN / Inf pass through)
+  __half_raw r;
+  r.x = (unsigned short)(u >> 16);
+  return __half(r);
+}
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
   float4 a = *reinterpret_cast<const float4*>(p);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -181,6 +220,8 @@ struct ConvIO {
   int out_f32 = 0;            // NHWC tcgen05 kernel, EPI_LINEAR / EPI_CONVT only: the destination tensor is fp32
   int planar_out = 0;         // NHWC tcgen05 kernel, EPI_LRELU only: store planar-8 [B][C/8][H][W][8] (feeds conv_halo.cu)
   unsigned int* tile_ctr = nullptr;  // halo kernel: device counter (zero when the kernel starts) for dynamic tile scheduling
+  int in_bf16 = 0;            // tcgen05 kernels: `in` (and `res` of EPI_RES) and the packed weights are bf16 instead of fp16
+  int out_bf16 = 0;           // tcgen05 kernels: planar-8 / NHWC activation outputs are stored as bf16 (tmp / SRC stay fp16)
 };
 
 int launch_conv_f32(const ConvLayerF32& L, const ConvIO& io, cudaStream_t st);

@@ -41,6 +41,7 @@ struct HaloParams {
   int nentries, ne, ncols, tmem_cols, n_valid, w_bytes, wtile_bytes;
   int nb, wtile_al;  // weight streaming: ring of nb tiles of wtile_al bytes (0 = weights resident)
   int epi, out_c, cpp;
+  int in_bf, out_bf;  // operand / activation-output storage type: 0 = fp16, 1 = bf16 (RIFE_PRECISION_BF16)
   const __half* w;
   const float* bias;
   const float* beta;
@@ -314,10 +315,10 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
     float a[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = v[i];
-    st8(dst, a);
+    st8x(dst, a, p.out_bf);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
-    st8(dst + pl, a);
+    st8x(dst + pl, a, p.out_bf);
   } else if constexpr (EPI == EPI_RES) {
     const size_t o = ((size_t)c.b * (p.out_c >> 3) + (n0 >> 3)) * c.plane + ((size_t)y * p.W + c.x) * 8;
 #pragma unroll
@@ -326,19 +327,14 @@ __device__ __forceinline__ void epi_chunk(const HaloParams& p, const EpiCtx& c, 
       uint4 u;
       const uint32_t ra = c.res_smem + (uint32_t)(((n0 >> 3) + h) * p.plane_bytes + mi * TH * pitch * 16);
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ra));
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
       float rr[8], a[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(hh[i]);
-        rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
-      }
+      unpack8x(u, p.in_bf, rr);
       const float4 b0 = *reinterpret_cast<const float4*>(s_beta + n0 + 8 * h);
       const float4 b1 = *reinterpret_cast<const float4*>(s_beta + n0 + 8 * h + 4);
       const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
-      st8(c.out + o + h * c.plane, a);
+      st8x(c.out + o + h * c.plane, a, p.out_bf);
     }
   } else if constexpr (EPI == EPI_PS) {
     const int par = j >> 2, sub = j & 3;
@@ -568,7 +564,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ne >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // instruction descriptor: D = f32, A / B format 0 = f16 or 1 = bf16 (bits 7-9 / 10-12), N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (p.in_bf ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(p.ne >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_desc0 = make_desc_noswz(0, (uint32_t)p.plane_bytes, (uint32_t)pitch * 16u);
       const uint32_t mt_step = (uint32_t)(TH * pitch);  // 16 halo rows, in 16-byte units (one pixel = 16 B per plane)
       long long t_w = 0, t_te = 0, t_af = 0;
@@ -839,23 +837,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------- layout converters (tests)
-__global__ void nhwc_f32_to_planar8_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * H * W * C) return;
-  const int c = (int)(i % C);
-  const size_t pix = i / C;
-  const size_t hw = (size_t)H * W;
-  const size_t b = pix / hw, p = pix % hw;
-  y[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)] = __float2half_rn(x[i]);
+__device__ __forceinline__ __half cvt16_dev(float x, bool bf) {
+  if (!bf) return __float2half_rn(x);
+  const __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<const __half*>(&b);
 }
-__global__ void planar8_to_nhwc_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+__device__ __forceinline__ float cvt16_to_f(__half h, bool bf) {
+  if (!bf) return __half2float(h);
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h));
+}
+__global__ void nhwc_f32_to_planar8_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C,
+                                           bool bf) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * H * W * C) return;
   const int c = (int)(i % C);
   const size_t pix = i / C;
   const size_t hw = (size_t)H * W;
   const size_t b = pix / hw, p = pix % hw;
-  y[i] = __half2float(x[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)]);
+  y[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)] = cvt16_dev(x[i], bf);
+}
+__global__ void planar8_to_nhwc_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C,
+                                           bool bf) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * H * W * C) return;
+  const int c = (int)(i % C);
+  const size_t pix = i / C;
+  const size_t hw = (size_t)H * W;
+  const size_t b = pix / hw, p = pix % hw;
+  y[i] = cvt16_to_f(x[((b * (C / 8) + c / 8) * hw + p) * 8 + (c & 7)], bf);
 }
 __global__ void f16_to_f32_k(const __half* __restrict__ x, float* __restrict__ y, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -909,7 +918,7 @@ int halo_mode(const HostLayer& h, int ps_layout) {
 bool halo_fits(const HostLayer& h, int ps_layout) { return halo_mode(h, ps_layout) != 0; }
 
 int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
-                      std::vector<float>* beta, HaloLayer* L) {
+                      std::vector<float>* beta, HaloLayer* L, bool bf16) {
   if (!halo_fits(h, ps_layout)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "halo_pack_weights: layer does not fit the halo kernel");
   const int kg = h.cin / 8;
   *L = HaloLayer();
@@ -940,7 +949,7 @@ int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* pa
                 const int n = sub * pc + k, on = par * 52 + 4 * k + sub;
                 for (int c = 0; c < 8; ++c)
                   (*packed)[(((size_t)e * kg + g) * ne + n) * 8 + c] =
-                      __float2half_rn(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + on]);
+                      host_cvt16(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + on], bf16);
               }
         }
     }
@@ -957,7 +966,7 @@ int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* pa
         for (int n = 0; n < h.npad; ++n)
           for (int c = 0; c < 8; ++c)
             (*packed)[(((size_t)t * kg + g) * h.npad + n) * 8 + c] =
-                __float2half_rn(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + n]);
+                host_cvt16(h.w[((size_t)t * h.cin + g * 8 + c) * h.npad + n], bf16);
     }
   }
   L->w_bytes = (int)(packed->size() * sizeof(__half));
@@ -1120,6 +1129,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   }
   p.stages = stages;
   p.epi = io.epi; p.out_c = io.out_c; p.cpp = io.co_per_par;
+  p.in_bf = io.in_bf16 ? 1 : 0; p.out_bf = io.out_bf16 ? 1 : 0;
   p.w = L.w; p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
   p.tile_ctr = chain ? nullptr : io.tile_ctr;   // (a chain would need one counter per layer)
@@ -1257,15 +1267,18 @@ int launch_conv_halo_f32io(const HaloLayer& L, const ConvIO& io, cudaStream_t st
     cleanup();
     RIFE_FAIL(RIFE_ERR_CUDA, std::string("conv_halo_f32io: ") + cudaGetErrorString(e));
   }
-  nhwc_f32_to_planar8_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, io.B, io.H, io.W, L.cin);
+  nhwc_f32_to_planar8_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, io.B, io.H, io.W, L.cin,
+                                                                           io.in_bf16 != 0);
   if (nres)
-    nhwc_f32_to_planar8_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, io.B, io.H, io.W, io.out_c);
+    nhwc_f32_to_planar8_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, io.B, io.H, io.W,
+                                                                             io.out_c, io.in_bf16 != 0);
   ConvIO h = io;
   h.in = hin; h.res = hres; h.out = hout;
   int rc = launch_conv_halo(L, h, st);
   if (rc == RIFE_OK) {
     if (planar_out)
-      planar8_to_nhwc_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, io.B, oh, ow, oc);
+      planar8_to_nhwc_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, io.B, oh, ow, oc,
+                                                                                 io.out_bf16 != 0);
     else
       f16_to_f32_k<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, nout);
     if (cudaGetLastError() != cudaSuccess) rc = RIFE_ERR_CUDA;

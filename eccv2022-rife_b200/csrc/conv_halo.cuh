@@ -25,8 +25,9 @@ struct HaloLayer {
 
 bool halo_fits(const HostLayer& h, int ps_layout);  // ps_layout: 0 plain, 1 ConvT+PixelShuffle (16-ch tmp), 2 narrow (8-ch tmp: flow + mask)
 int halo_mode(const HostLayer& h, int ps_layout);  // 0 no, 1 resident weights, 2 streamed weights
+// bf16: the packed weights carry bf16 bit patterns (the layer then runs with ConvIO::in_bf16)
 int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
-                      std::vector<float>* beta, HaloLayer* L);
+                      std::vector<float>* beta, HaloLayer* L, bool bf16 = false);
 // planar-8 fp16 activations [B][C/8][H][W][8] in; planar-8 (LRELU / LINEAR / RES / LRELU_S2D) or pixel-major
 // (PS / HEADT / CONVT) fp16 out
 int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st);

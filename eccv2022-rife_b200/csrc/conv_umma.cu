@@ -33,6 +33,7 @@ struct UmmaParams {
   int npad, n_valid, tmem_cols, nw;  // nw = accumulator columns per CTA (N split over blockIdx.y)
   int a_bytes, b_bytes;  // per stage (b rounded up to 1024)
   int epi, out_c, cpp, planar_out, res_pitch, out_f32;
+  int in_bf, out_bf;  // operand / activation-output storage type: 0 = fp16, 1 = bf16 (RIFE_PRECISION_BF16)
   unsigned long long kmask;  // bit ks = tap * nchunks + chunk set: that K block has non-zero weights (all ones if > 64 blocks)
   const float* bias;
   const float* beta;
@@ -115,14 +116,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
+__device__ __forceinline__ void store16h(__half* dst, const float (&v)[16], bool bf = false) {
   float a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = v[i];
-  st8(dst, a);
+  st8x(dst, a, bf);
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = v[8 + i];
-  st8(dst + 8, a);
+  st8x(dst + 8, a, bf);
 }
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -206,7 +207,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- MMA issuer
       // instruction descriptor: D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.nw >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      // (A / B format bits 7-9 / 10-12: 1 = bf16)
+      const uint32_t idesc = (1u << 4) | (p.in_bf ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(p.nw >> 3) << 17) |
+                             ((uint32_t)(TILE_M >> 4) << 24);
       const uint32_t sbo = 8u * (uint32_t)p.kc * 2u;
       const uint32_t layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
       const uint64_t desc0 = make_smem_desc(0, sbo, layout);
@@ -296,19 +299,19 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
               float a8[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) a8[i] = v[i];
-              st8(d, a8);
+              st8x(d, a8, p.out_bf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) a8[i] = v[8 + i];
-              st8(d + hw * 8, a8);
+              st8x(d + hw * 8, a8, p.out_bf);
             } else {
-              store16h(p.out + pix * p.out_c + n0, v);
+              store16h(p.out + pix * p.out_c + n0, v, p.out_bf);
             }
           }
         } else if constexpr (EPI == EPI_LRELU_S2D) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
           const size_t o = ((((size_t)b * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1)));
-          if (n0 < p.n_valid) store16h(p.out + o * p.out_c + n0, v);
+          if (n0 < p.n_valid) store16h(p.out + o * p.out_c + n0, v, p.out_bf);
         } else if constexpr (EPI == EPI_RES) {
           uint4 r2[2];
           if (jb == 0) { r2[0] = resv[2 * jj]; r2[1] = resv[2 * jj + 1]; }
@@ -318,18 +321,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const __half2* hh = reinterpret_cast<const __half2*>(&r2[h]);
+            float rr[8];
+            unpack8x(r2[h], p.in_bf, rr);
             const float4 b0 = *reinterpret_cast<const float4*>(s_beta + nl + 8 * h);
             const float4 b1 = *reinterpret_cast<const float4*>(s_beta + nl + 8 * h + 4);
             const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(hh[i]);
-              v[8 * h + 2 * i] = lrelu02(v[8 * h + 2 * i] * be[2 * i] + f.x);
-              v[8 * h + 2 * i + 1] = lrelu02(v[8 * h + 2 * i + 1] * be[2 * i + 1] + f.y);
-            }
+            for (int i = 0; i < 8; ++i) v[8 * h + i] = lrelu02(v[8 * h + i] * be[i] + rr[i]);
           }
-          store16h(p.out + pix * p.out_c + n0, v);
+          store16h(p.out + pix * p.out_c + n0, v, p.out_bf);
         } else if constexpr (EPI == EPI_PRELU || EPI == EPI_PRELU_ADD) {
           // ECCV-paper net: per-channel PReLU (slopes in s_beta), optionally "+ res" afterwards (model/IFNet.py:46)
 #pragma unroll
@@ -409,13 +409,19 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_umma_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ casts for the f32io wrapper
-__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n) {
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n, bool bf) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __float2half_rn(x[i]);
+  if (i >= n) return;
+  if (bf) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(x[i]);
+    y[i] = *reinterpret_cast<const __half*>(&b);
+  } else {
+    y[i] = __float2half_rn(x[i]);
+  }
 }
-__global__ void f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, size_t n) {
+__global__ void f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, size_t n, bool bf) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __half2float(x[i]);
+  if (i < n) y[i] = bf ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&x[i])) : __half2float(x[i]);
 }
 
 // ------------------------------------------------------------------------------------------ tensor maps
@@ -442,7 +448,7 @@ CUtensorMapSwizzle swizzle_for(int kc) {
 }  // namespace
 
 int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
-                      std::vector<float>* beta, UmmaLayer* L) {
+                      std::vector<float>* beta, UmmaLayer* L, bool bf16) {
   if (h.cin % 16) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "umma_pack_weights: cin must be a multiple of 16");
   const int kc = (h.cin % 64 == 0) ? 64 : ((h.cin % 32 == 0) ? 32 : 16);
   const int nchunks = h.cin / kc;
@@ -467,7 +473,7 @@ int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* p
         if (on < 0) continue;
         for (int k = 0; k < kc; ++k)
           (*packed)[(((size_t)t * nchunks + ch) * np + n) * kc + k] =
-              __float2half_rn(h.w[((size_t)t * h.cin + ch * kc + k) * h.npad + on]);
+              host_cvt16(h.w[((size_t)t * h.cin + ch * kc + k) * h.npad + on], bf16);
       }
   bias->assign(np, 0.f);
   beta->clear();
@@ -539,6 +545,7 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   p.res_pitch = io.res_pitch ? io.res_pitch : io.out_c;
   p.bias = L.bias; p.beta = L.beta;
   p.res = (const __half*)io.res; p.out = (__half*)io.out;
+  p.in_bf = io.in_bf16 ? 1 : 0; p.out_bf = io.out_bf16 ? 1 : 0;
   p.kmask = L.kmask;
   if (L.kind == CONV_3x3) {
     for (int t = 0; t < 9; ++t) { p.dy[t] = (signed char)(t / 3 - 1); p.dx[t] = (signed char)(t % 3 - 1); }
@@ -621,13 +628,15 @@ int launch_conv_umma_f32io(const UmmaLayer& L, const ConvIO& io, cudaStream_t st
     cleanup();
     RIFE_FAIL(RIFE_ERR_CUDA, std::string("conv_umma_f32io: ") + cudaGetErrorString(e));
   }
-  f32_to_f16_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, nin);
-  if (nres) f32_to_f16_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, nres);
+  f32_to_f16_kernel<<<(unsigned)((nin + 255) / 256), 256, 0, st>>>((const float*)io.in, hin, nin, io.in_bf16 != 0);
+  if (nres) f32_to_f16_kernel<<<(unsigned)((nres + 255) / 256), 256, 0, st>>>((const float*)io.res, hres, nres, io.in_bf16 != 0);
   ConvIO h = io;
   h.in = hin; h.res = hres; h.out = hout;
   int rc = launch_conv_umma(L, h, st);
   if (rc == RIFE_OK) {
-    f16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, nout);
+    // PixelShuffle / ConvTranspose scatter epilogues always store fp16
+    const bool obf = io.out_bf16 && (io.epi == EPI_LRELU || io.epi == EPI_LINEAR || io.epi == EPI_RES || io.epi == EPI_LRELU_S2D);
+    f16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(hout, (float*)io.out, nout, obf);
     if (cudaGetLastError() != cudaSuccess) rc = RIFE_ERR_CUDA;
   }
   cleanup();

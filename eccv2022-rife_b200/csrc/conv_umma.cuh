@@ -30,8 +30,9 @@ struct UmmaLayer {
 
 // fp32 [tap][cin][npad] -> fp16 [tap][cin/kc][npad'][kc] (+ optional PixelShuffle column permutation);
 // fills the geometry of *L and the (possibly permuted) bias / beta vectors.
+// bf16: the packed weights carry bf16 bit patterns (the layer then runs with ConvIO::in_bf16)
 int umma_pack_weights(const HostLayer& h, bool ps_layout, std::vector<__half>* packed, std::vector<float>* bias,
-                      std::vector<float>* beta, UmmaLayer* L);
+                      std::vector<float>* beta, UmmaLayer* L, bool bf16 = false);
 // fp16 NHWC activations in / out (pipeline path)
 int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st);
 // fp32 NHWC in / out wrapper used by the op-level test entry points (casts to fp16 and back, synchronous)

@@ -58,8 +58,8 @@ class IFBlock(nn.Module):
 
 def _precision_from_env(default):
     v = os.environ.get("RIFE_B200_PRECISION", default).lower()
-    if v not in ("fp32", "fp16", "auto"):
-        raise ValueError("RIFE_B200_PRECISION must be fp32, fp16 or auto")
+    if v not in ("fp32", "fp16", "bf16", "auto"):
+        raise ValueError("RIFE_B200_PRECISION must be fp32, fp16, bf16 or auto")
     return v
 
 
@@ -71,8 +71,11 @@ class IFNet(nn.Module):
     """Drop-in for `train_log.IFNet_HDv3.IFNet`.
 
     precision: "fp32" (fp32 storage + FMA convs, <=1e-4 vs the reference), "fp16" (fp16 NHWC
-    activations, tcgen05 tensor-core convs, fp32 accumulate/coordinates) or "auto" (follows the input
-    dtype: float16 inputs -> fp16 mode, float32 inputs -> fp32 mode).  Env override: RIFE_B200_PRECISION.
+    activations, tcgen05 tensor-core convs, fp32 accumulate/coordinates), "bf16" (as fp16 with the conv
+    activations inside the Head / IFBlocks in bf16: fp32 range, cannot overflow) or "auto" (follows the input
+    dtype: float16 -> fp16 mode, bfloat16 -> bf16 mode, float32 -> fp32 mode).  Env override: RIFE_B200_PRECISION.
+    bfloat16 frame tensors are accepted in every 16-bit mode: they cross the boundary as float16 (exact for
+    values in [0, 1]) and the result is cast back.
     """
 
     def __init__(self, precision="auto"):
@@ -124,8 +127,8 @@ class IFNet(nn.Module):
     def _resolve_precision(self, dtype):
         p = self.precision
         if p == "auto":
-            p = "fp16" if dtype == torch.float16 else "fp32"
-        return _lib.PRECISION_FP16 if p == "fp16" else _lib.PRECISION_FP32
+            p = "fp16" if dtype == torch.float16 else ("bf16" if dtype == torch.bfloat16 else "fp32")
+        return {"fp16": _lib.PRECISION_FP16, "bf16": _lib.PRECISION_BF16}.get(p, _lib.PRECISION_FP32)
 
     def _get_weights(self, device, prec):
         lib = _lib.load()
@@ -199,8 +202,8 @@ class IFNet(nn.Module):
     def _check_input(self, x):
         if not x.is_cuda:
             raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
-        if x.dtype not in (torch.float32, torch.float16, torch.uint8):
-            raise TypeError("eccv2022-rife_b200: float32 / float16 NCHW frames or uint8 HWC frames required")
+        if x.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.uint8):
+            raise TypeError("eccv2022-rife_b200: float32 / float16 / bfloat16 NCHW frames or uint8 HWC frames required")
 
     @staticmethod
     def _io(dtype):
@@ -227,15 +230,37 @@ class IFNet(nn.Module):
         `(x*255).byte()` on the way out).  pad=True accepts any H, W (zero-pad + crop inside the kernels)."""
         self._check_input(img0)
         lib = _lib.load()
+        if img0.dtype == torch.bfloat16 and torch.is_tensor(img1) and img1.dtype == torch.bfloat16:
+            prec0 = self._resolve_precision(torch.bfloat16)
+            if prec0 == _lib.PRECISION_FP32:
+                a, b_ = img0.float(), img1.float()
+            else:
+                a, b_ = img0.half(), img1.half()
+            r = self._run_prec(a, b_, timestep, scale, want_all, pad, prec0)
+            if not want_all:
+                return r.to(torch.bfloat16)
+            flows, mask, merged = r
+            bf = torch.bfloat16
+            return ([f.to(bf) for f in flows], mask.to(bf),
+                    [(m[0].to(bf), m[1].to(bf)) for m in merged[:4]] + [merged[4].to(bf)])
+        return self._run_prec(img0, img1, timestep, scale, want_all, pad, None)
+
+    def _run_prec(self, img0, img1, timestep, scale, want_all, pad, prec):
+        lib = _lib.load()
         u8 = img0.dtype == torch.uint8
         if u8:
             b, h, w, c = img0.shape
         else:
             b, c, h, w = img0.shape
+        if not torch.is_tensor(img1) or img1.shape != img0.shape or img1.dtype != img0.dtype or img1.device != img0.device:
+            raise ValueError("eccv2022-rife_b200: img0 and img1 must have the same shape, dtype and CUDA device "
+                             f"(got {tuple(img0.shape)} {img0.dtype} {img0.device} vs "
+                             f"{tuple(getattr(img1, 'shape', ()))} {getattr(img1, 'dtype', None)} {getattr(img1, 'device', None)})")
         img0 = img0.contiguous()
         img1 = img1.contiguous()
         dev = img0.device
-        prec = self._resolve_precision(torch.float16 if u8 else img0.dtype)
+        if prec is None:
+            prec = self._resolve_precision(torch.float16 if u8 else img0.dtype)
         pl = self.plan_for(dev, prec, b, c, h, w, scale, 0, pad or u8)
         io = self._io(img0.dtype)
         ts = self._timesteps(timestep, b)
@@ -271,6 +296,15 @@ class IFNet(nn.Module):
         self._check_input(img0)
         lib = _lib.load()
         seq = img1 is None
+        if img0.dtype == torch.bfloat16:
+            p0 = self._resolve_precision(torch.bfloat16)
+            cast = torch.float32 if p0 == _lib.PRECISION_FP32 else torch.float16
+            saved, self.precision = self.precision, {_lib.PRECISION_FP32: "fp32", _lib.PRECISION_FP16: "fp16",
+                                                     _lib.PRECISION_BF16: "bf16"}[p0]
+            try:
+                return self.run_multi(img0.to(cast), None if seq else img1.to(cast), timesteps, scale, pad).to(torch.bfloat16)
+            finally:
+                self.precision = saved
         u8 = img0.dtype == torch.uint8
         if u8:
             n, h, w, c = img0.shape
@@ -279,8 +313,8 @@ class IFNet(nn.Module):
         pairs = n - 1 if seq else n
         if pairs < 1:
             raise ValueError("sequence mode needs at least two frames")
-        if not seq and (img1.shape != img0.shape or img1.dtype != img0.dtype):
-            raise ValueError("img0 and img1 must have the same shape and dtype")
+        if not seq and (img1.shape != img0.shape or img1.dtype != img0.dtype or img1.device != img0.device):
+            raise ValueError("img0 and img1 must have the same shape, dtype and device")
         tl = [float(t) for t in timesteps]
         nt = len(tl)
         if nt < 1:

@@ -82,34 +82,61 @@ class Model:
             frames = nxt
         return frames
 
-    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0, streams=None):
+    def inference_host(self, img0_host, img1_host, out_host, timestep=0.5, scale=1.0, stream=None, slot=0, streams=None,
+                       device=None):
         """End-to-end call on HOST (ideally pinned) tensors -- NCHW float16/float32, or HWC uint8 frames exactly as a
         video decoder delivers them (any H, W): H2D copies, inference and the D2H copy of the result are enqueued on
         `stream` (default: current) by rife_inference_host; returns without syncing.
+        `img1_host=None` selects video order (inference_video.py:215-260): `img0_host` holds N + 1 consecutive frames,
+        `out_host` receives the N in-between frames, and every frame crosses the host link (and the Head) once.
         `slot` selects an independent plan (workspace + staging buffers).  With `streams=(h2d, compute, d2h)` the call
         becomes one stage set of a software pipeline (rife_inference_host_pipelined): rotate two or three slots over the
         same three streams and the PCIe copies of one call overlap the kernels of its neighbours, while the kernels
-        of consecutive calls run back to back on the single compute stream."""
+        of consecutive calls run back to back on the single compute stream.
+        `device`: the CUDA device to run on (default: the current device) -- one handle set per device, no module global."""
         net = self.flownet
-        if img0_host.is_cuda or out_host.is_cuda:
-            raise ValueError("inference_host takes host tensors")
+        seq = img1_host is None
+        for name, t in (("img0_host", img0_host), ("img1_host", img1_host), ("out_host", out_host)):
+            if t is None and name == "img1_host":
+                continue
+            if not torch.is_tensor(t) or t.is_cuda:
+                raise ValueError(f"inference_host: {name} must be a host (CPU) tensor")
+            if not t.is_contiguous():
+                raise ValueError(f"inference_host: {name} must be contiguous (got strides {t.stride()})")
+        if img0_host.dtype not in (torch.float32, torch.float16, torch.uint8):
+            raise TypeError("inference_host: float32 / float16 NCHW frames or uint8 HWC frames required")
+        if img0_host.dim() != 4:
+            raise ValueError("inference_host: frames must be 4-D (B,C,H,W) float or (B,H,W,C) uint8")
+        if not seq and (img1_host.shape != img0_host.shape or img1_host.dtype != img0_host.dtype):
+            raise ValueError("inference_host: img0_host and img1_host must have the same shape and dtype")
         lib = _lib.load()
         u8 = img0_host.dtype == torch.uint8
         if u8:
-            b, h, w, c = img0_host.shape
+            n, h, w, c = img0_host.shape
         else:
-            b, c, h, w = img0_host.shape
+            n, c, h, w = img0_host.shape
+        b = n - 1 if seq else n
+        if b < 1:
+            raise ValueError("inference_host: video order needs at least two frames")
+        if out_host.dtype != img0_host.dtype or out_host.numel() != b * c * h * w:
+            raise ValueError(f"inference_host: out_host must hold {b} frames shaped like the inputs in {img0_host.dtype} "
+                             f"(got {tuple(out_host.shape)} {out_host.dtype})")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("eccv2022-rife_b200: a CUDA device is required -- the B200 hot path has no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         prec = net._resolve_precision(torch.float16 if u8 else img0_host.dtype)
-        pl = net.plan_for(device, prec, b, c, h, w, scale, slot, True)
+        pl = net.plan_for(dev, prec, b, c, h, w, scale, slot, True, 1, seq)
         io = net._io(img0_host.dtype)
         ts = net._timesteps(timestep, b)
-        with torch.cuda.device(device):
+        p1 = None if seq else img1_host.data_ptr()
+        with torch.cuda.device(dev):
             if streams is not None:
                 s_in, s_c, s_out = (x.cuda_stream for x in streams)
-                _lib.check(lib.rife_inference_host_pipelined(pl.handle, img0_host.data_ptr(), img1_host.data_ptr(), ts,
+                _lib.check(lib.rife_inference_host_pipelined(pl.handle, img0_host.data_ptr(), p1, ts,
                                                              out_host.data_ptr(), io, s_in, s_c, s_out))
                 return out_host
             st = (stream or torch.cuda.current_stream()).cuda_stream
-            _lib.check(lib.rife_inference_host(pl.handle, img0_host.data_ptr(), img1_host.data_ptr(), ts,
-                                               out_host.data_ptr(), io, st))
+            _lib.check(lib.rife_inference_host(pl.handle, img0_host.data_ptr(), p1, ts, out_host.data_ptr(), io, st))
         return out_host

@@ -45,8 +45,14 @@ typedef enum rife_dtype { RIFE_F32 = 0, RIFE_F16 = 1, RIFE_U8 = 2 } rife_dtype;
 /* Arithmetic mode of the whole pipeline.
  *  RIFE_PRECISION_FP32: fp32 storage, fp32 FMA convs        (<= 1e-4 max-abs vs reference fp32)
  *  RIFE_PRECISION_FP16: fp16 NHWC activations, tcgen05 tensor-core convs with fp32
- *                       accumulation in TMEM, fp32 coordinates (<= 2e-2 max-abs, >= 45 dB PSNR) */
-typedef enum rife_precision { RIFE_PRECISION_FP32 = 0, RIFE_PRECISION_FP16 = 1 } rife_precision;
+ *                       accumulation in TMEM, fp32 coordinates (<= 2e-2 max-abs, >= 45 dB PSNR)
+ *  RIFE_PRECISION_BF16: as FP16, but the conv activations inside the Head and the IFBlocks (the only tensors without
+ *                       an a-priori bound: 8 ResConv residual accumulations per block) are bf16 operands of bf16 x bf16
+ *                       tcgen05 MMAs -- fp32 range, no overflow whatever the weights; frames, features, flow / mask
+ *                       levels and warp coordinates keep their fp16 / fp32 storage.  Same stated bar as FP16.  (The
+ *                       reference has only the --fp16 switch, inference_video.py:85-86, and that mode overflows to NaN on
+ *                       the 256x448 ECCV fixture, tests/golden/eccv_ref_fp16.json.) */
+typedef enum rife_precision { RIFE_PRECISION_FP32 = 0, RIFE_PRECISION_FP16 = 1, RIFE_PRECISION_BF16 = 2 } rife_precision;
 
 typedef struct rife_weights rife_weights; /* immutable packed weights on one device          */
 typedef struct rife_plan rife_plan;       /* shape-specialised launch plan bound to a workspace */

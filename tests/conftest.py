@@ -56,6 +56,38 @@ def seeded_model(pkg, amp=1.0, precision="auto"):
     return _models[key]
 
 
+RANGE_K, BIGFLOW_AMP = 2.0e5, 20.0   # tests/golden/make_golden.py: case_stress
+
+
+def stress_model(pkg, kind, precision="auto"):
+    """The mirror with the weight transformations of tests/golden/make_golden.py:case_stress.
+    "range": conv activations of the Head and of every IFBlock * 2e5 (>= 3e4 everywhere, > the fp16 maximum in blocks
+    0-4), the activation-free last conv of each chain / 2e5; "bigflow": every lastconv * 20 (|flow| up to 240 px)."""
+    import torch
+    key = ("stress", kind, precision)
+    if key not in _models:
+        torch.manual_seed(1234)
+        m = pkg.Model(precision=precision)
+        m.eval()
+        net = m.flownet
+        with torch.no_grad():
+            if kind == "range":
+                net.encode.cnn1.weight.mul_(RANGE_K); net.encode.cnn1.bias.mul_(RANGE_K)
+                net.encode.cnn3.weight.div_(RANGE_K)
+                for i in range(5):
+                    blk = getattr(net, f"block{i}")
+                    blk.conv0[1][0].weight.mul_(RANGE_K); blk.conv0[1][0].bias.mul_(RANGE_K)
+                    blk.lastconv[0].weight.mul_(AMP / RANGE_K)
+            elif kind == "bigflow":
+                for i in range(5):
+                    getattr(net, f"block{i}").lastconv[0].weight.mul_(BIGFLOW_AMP)
+            else:
+                raise ValueError(kind)
+        net.invalidate()
+        _models[key] = m
+    return _models[key]
+
+
 def numpy_state_dict(model):
     return {k: v.detach().cpu().numpy().astype(np.float32) for k, v in model.flownet.state_dict().items()}
 

@@ -311,6 +311,59 @@ def case_scene_ssim():
          ssim=np.asarray(vals, np.float64))
 
 
+RANGE_K = 2.0e5    # "range" stress: activations of every conv chain scaled by K (fp16 overflows, the result barely moves)
+BIGFLOW_AMP = 20.0  # "bigflow" stress: |flow| of 50-200 px through the whole net
+
+
+def apply_range_stress(net, k=RANGE_K, amp=AMP):
+    """LeakyReLU is positively homogeneous: multiplying the SECOND conv of a chain (weight and bias) by k multiplies every
+    activation behind it by ~k (the later biases become negligible), dividing the chain's LAST (activation-free) conv weight
+    by k brings the output back.  Head: cnn1 * k, cnn3 / k.  IFBlock i: conv0.1 * k, lastconv * amp / k.  (The first conv of
+    each chain reads bounded data -- frames, warped frames, flow -- and keeps ordinary weights.)"""
+    net.encode.cnn1.weight.mul_(k); net.encode.cnn1.bias.mul_(k)
+    net.encode.cnn3.weight.div_(k)
+    for i in range(5):
+        blk = getattr(net, f"block{i}")
+        blk.conv0[1][0].weight.mul_(k); blk.conv0[1][0].bias.mul_(k)
+        blk.lastconv[0].weight.mul_(amp / k)
+
+
+def case_stress():
+    """Trained-weight-like stress fixtures recorded from the unmodified reference (fp32, CPU):
+    (i) "range": conv activations of the Head and of every IFBlock reach >= 3e4 (beyond what fp16 storage can follow);
+    (ii) "bigflow": lastconv * 20 drives |flow| to 50-200 px through the full net (warp border clamps everywhere)."""
+    arrs = {}
+    torch.manual_seed(1234)
+    m = Model()
+    m.eval()
+    apply_range_stress(m.flownet)
+    peak = {}
+    hooks = []
+    for name, mod in m.flownet.named_modules():
+        if name.endswith("convblock.7") or name == "encode.cnn2":
+            hooks.append(mod.register_forward_hook(lambda _m, _i, o, name=name: peak.__setitem__(name, max(peak.get(name, 0.), float(o.abs().max())))))
+    img0, img1 = rand_frames(71, 1, 3, 128, 192, smooth=True)
+    out = m.inference(img0, img1, 0.5)
+    fl, _, _ = m.flownet(torch.cat((img0, img1), 1), 0.5, [16, 8, 4, 2, 1])
+    for h in hooks:
+        h.remove()
+    print("range stress: peak |activation|", {k: f"{v:.3g}" for k, v in peak.items()}, "|flow|max", float(fl[-1].abs().max()))
+    assert min(peak.values()) >= 3e4, peak
+    arrs["r_img0"], arrs["r_img1"], arrs["r_out"] = f32(img0), f32(img1), f32(out)
+    arrs["r_peak_act"] = np.asarray([peak[k] for k in sorted(peak)], np.float32)
+    arrs["r_flow_absmax"] = np.float32(fl[-1].abs().max())
+    mb = build_model(1234, BIGFLOW_AMP)
+    img0, img1 = rand_frames(72, 1, 3, 192, 320, smooth=True)
+    out = mb.inference(img0, img1, 0.5)
+    fl, _, _ = mb.flownet(torch.cat((img0, img1), 1), 0.5, [16, 8, 4, 2, 1])
+    q = torch.quantile(fl[-1].abs().flatten()[::7], torch.tensor([0.5, 0.9]))
+    print("bigflow stress: |flow| median / p90 / max", q.tolist(), float(fl[-1].abs().max()))
+    arrs["f_img0"], arrs["f_img1"], arrs["f_out"] = f32(img0), f32(img1), f32(out)
+    arrs["f_flow"] = f32(fl[-1]).astype(np.float16)
+    arrs["f_flow_absmax"] = np.float32(fl[-1].abs().max())
+    save("stress_cases", **arrs)
+
+
 def case_eccv_ref_fp16():
     """How far the reference's OWN half-precision mode (inference_video.py --fp16: default tensor type Half, so weights,
     frames and the warp grid of model/warplayer.py are all fp16) lands from its fp32 result on the eccv_cases inputs.
@@ -349,6 +402,10 @@ def case_eccv_ref_fp16():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "stress":
+        with torch.no_grad():
+            case_stress()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "scale_up":
         case_scale_up()

@@ -162,3 +162,65 @@ def test_conv_transpose_fp16_tcgen05(pkg, ci, co, ps, prec):
     if ps:
         ref = O.pixel_shuffle2(ref)
     assert np.abs(y.cpu().numpy() - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+# ---------------------------------------------------------------------------------------------- bf16 operands (RIFE_PRECISION_BF16)
+def _b(a):
+    """round to bf16 (nearest even) and back"""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return t.to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("ci,co,h,w,stride", [(16, 16, 24, 40, 1), (32, 32, 17, 30, 1), (64, 64, 16, 32, 1), (96, 96, 20, 36, 1),
+                                              (192, 192, 9, 15, 1), (64, 128, 16, 32, 2), (16, 32, 64, 96, 2)])
+@pytest.mark.parametrize("prec", [2, 4])   # 2 = bf16, pipeline policy (halo kernel when the layer fits); 4 = bf16, NHWC kernel only
+def test_conv3x3_bf16_tcgen05(pkg, ci, co, h, w, stride, prec):
+    """bf16 x bf16 tcgen05 MMAs with fp32 accumulation; the activation output is stored as bf16 (2^-9 relative rounding)."""
+    rng = np.random.default_rng(ci * 7 + co)
+    x = _b(rng.standard_normal((2, ci, h, w)).astype(np.float32))
+    wt = _b((rng.standard_normal((co, ci, 3, 3)) / np.sqrt(9 * ci)).astype(np.float32))
+    b = rng.standard_normal(co).astype(np.float32)
+    y = _conv(pkg, x, wt, b, stride, 1, precision=prec)
+    ref = O.leaky_relu(O.conv2d(x, wt, b, stride, 1))
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < 8e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("prec,c,hh", [(2, 64, 20), (4, 64, 20), (2, 32, 20), (2, 96, 40), (2, 128, 20), (2, 192, 20)])
+def test_resconv_bf16_tcgen05(pkg, prec, c, hh):
+    rng = np.random.default_rng(5)
+    x = _b(rng.standard_normal((2, c, hh, 28)).astype(np.float32))
+    wt = _b((rng.standard_normal((c, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
+    b = rng.standard_normal(c).astype(np.float32)
+    beta = rng.standard_normal(c).astype(np.float32)
+    y = _conv(pkg, x, wt, b, 1, 1, beta=beta, res=x, precision=prec)
+    ref = O.leaky_relu(O.conv2d(x, wt, b, 1, 1) * beta[None, :, None, None] + x)
+    assert np.abs(y - ref).max() < 8e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_conv_bf16_range_beyond_fp16(pkg):
+    """What the mode is for: activations far above the fp16 maximum (65504) come through finite and accurate."""
+    rng = np.random.default_rng(8)
+    x = _b((rng.standard_normal((1, 32, 16, 24)) * 3e4).astype(np.float32))
+    wt = _b((rng.standard_normal((32, 32, 3, 3)) / np.sqrt(9 * 32) * 8).astype(np.float32))
+    b = rng.standard_normal(32).astype(np.float32)
+    y = _conv(pkg, x, wt, b, 1, 1, precision=2)
+    ref = O.leaky_relu(O.conv2d(x, wt, b, 1, 1))
+    assert float(np.abs(ref).max()) > 2e5 and np.isfinite(y).all()
+    assert np.abs(y - ref).max() < 8e-3 * float(np.abs(ref).max())
+
+
+@pytest.mark.parametrize("ci", [32, 64, 128])
+def test_conv_transpose_bf16_tcgen05(pkg, ci):
+    """lastconv in bf16 mode: bf16 operands, fp16 tmp pixels out."""
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(ci)
+    x = _b(rng.standard_normal((2, ci, 10, 14)).astype(np.float32))
+    wt = _b((rng.standard_normal((ci, 52, 4, 4)) / np.sqrt(4 * ci)).astype(np.float32))
+    b = rng.standard_normal(52).astype(np.float32)
+    xd, wd, bd = (torch.from_numpy(a).to(DEV) for a in (x, wt, b))
+    y = torch.empty((2, 13, 40, 56), device=DEV)
+    pkg._lib.check(lib.rife_conv_transpose4x4s2(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 2, ci, 10, 14,
+                                                52, 1, 2, _stream()))
+    ref = O.pixel_shuffle2(O.conv_transpose2d_k4s2p1(x, wt, b))
+    assert np.abs(y.cpu().numpy() - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import AMP, GOLDEN, load_golden, numpy_state_dict, seeded_model, torch_state_dict
+from conftest import AMP, GOLDEN, load_golden, numpy_state_dict, seeded_model, stress_model, torch_state_dict
 from oracle import rife_oracle as O
 from oracle import torch_ref as T
 
@@ -135,3 +135,18 @@ def test_demo_config1(pkg):
     assert np.abs(out - g["out"]).max() < 1e-4
     out_amp = T.model_inference(torch_state_dict(seeded_model(pkg, AMP)), torch.from_numpy(img0), torch.from_numpy(img1)).numpy()
     assert np.abs(out_amp - g["out_amp"]).max() < 1e-4
+
+
+def test_stress_cases_torch_oracle(pkg):
+    """The trained-weight-like stress fixtures (tests/golden/make_golden.py:case_stress, recorded from the unmodified
+    reference): conv activations up to 5.8e5 ("range") and |flow| up to 240 px ("bigflow").  The torch-CPU restatement
+    reproduces both; the mirror's weight transformation is therefore the fixture's."""
+    g = load_golden("stress_cases")
+    assert float(g["r_peak_act"].min()) >= 3e4 and float(g["r_peak_act"].max()) > 65504.0
+    assert float(g["f_flow_absmax"]) > 200.0
+    m = stress_model(pkg, "range", "fp32")
+    out = T.model_inference(torch_state_dict(m), torch.from_numpy(g["r_img0"]), torch.from_numpy(g["r_img1"]), 0.5).numpy()
+    assert np.abs(out - g["r_out"]).max() < 1e-4
+    m = stress_model(pkg, "bigflow", "fp32")
+    out = T.model_inference(torch_state_dict(m), torch.from_numpy(g["f_img0"]), torch.from_numpy(g["f_img1"]), 0.5).numpy()
+    assert np.abs(out - g["f_out"]).max() < 1e-4

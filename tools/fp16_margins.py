@@ -1,4 +1,5 @@
-"""Prints fp16-mode error margins (max-abs / PSNR vs the fp32 goldens and the torch-CPU restatement)."""
+"""Prints fp16- / bf16-mode error margins (max-abs / PSNR vs the fp32 goldens and the torch-CPU restatement).
+    python tools/fp16_margins.py [fp16|bf16]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +9,9 @@ from oracle import torch_ref as T
 pkg = importlib.import_module("eccv2022-rife_b200")
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 g = load_golden("inference_variants")
-m, ma = seeded_model(pkg, 1.0, "fp16"), seeded_model(pkg, AMP, "fp16")
+PREC = sys.argv[1] if len(sys.argv) > 1 else "fp16"
+print("precision mode:", PREC)
+m, ma = seeded_model(pkg, 1.0, PREC), seeded_model(pkg, AMP, PREC)
 def rep(name, out, ref): print(f"{name:28s} max-abs {np.abs(out-ref).max():.5f}  PSNR {psnr(out, ref):.1f} dB")
 rep("a noise amp t=.3", ma.inference(cu(g["a_img0"]), cu(g["a_img1"]), 0.3).cpu().numpy(), g["a_out"])
 rep("b smooth amp scale .5", ma.inference(cu(g["b_img0"]), cu(g["b_img1"]), 0.5, 0.5).cpu().numpy(), g["b_out"])
