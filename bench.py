@@ -1,13 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- interpolated frames/s of the RIFE HDv3 IFNet hot path at 1080p 2X (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|fp32] [--pairs P]
-    python bench.py --impl reference ...      # the reference's CPU path (torch-CPU port, oracle/torch_ref.py)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|bf16|fp32] [--pairs P] [--workload NAME]
+    python bench.py --impl reference ...      # the reference's CPU path (the unmodified reference when RIFE_REFERENCE /
+                                              # baseline/_ref holds it, else the torch-CPU port oracle/torch_ref.py)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one Model.inference call on a batch of P synthetic 1088x1920 (padded 1080p) frame pairs at
 timestep 0.5 per GPU (the 2X interpolation of P pairs).  Frame pairs are independent, so ranks shard pairs with
 no data-path collective (scaling = weak); torch.distributed is only used for the barrier and the max-over-ranks.
+--workload selects the other BASELINE.json configs (720p2x = config 2, 1080p4x = config 3, 4k2x = config 4).
 Prints ONE JSON line on rank 0 (see the contract in the task description).
 """
 import argparse
@@ -23,10 +25,58 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, CH = 1088, 1920, 3          # 1080p padded to a multiple of 64 (cfg3 shape)
-WORKLOAD = "1080p 2X: 1088x1920 (padded 1080p) frame pairs, timestep 0.5, scale 1.0, HDv3 v4.25 weights = seeded default init"
+CH = 3
+# BASELINE.json configs (cfg2 / cfg3 / cfg4 shapes): padded size, true frame size, pairs per step, timesteps, scale
+WORKLOADS = {
+    "1080p2x": dict(H=1088, W=1920, fh=1080, fw=1920, pairs=16, ts=(0.5,), scale=1.0,
+                    text="1080p 2X: 1088x1920 (padded 1080p) frame pairs, timestep 0.5, scale 1.0"),
+    "720p2x": dict(H=768, W=1280, fh=720, fw=1280, pairs=32, ts=(0.5,), scale=1.0,
+                   text="720p 2X: 768x1280 (padded 720p) frame pairs, timestep 0.5, scale 1.0"),
+    "1080p4x": dict(H=1088, W=1920, fh=1080, fw=1920, pairs=6, ts=(0.25, 0.5, 0.75), scale=1.0,
+                    text="1080p 4X: 1088x1920 frame pairs at timesteps 0.25 / 0.5 / 0.75 in one call (Head once per frame), scale 1.0"),
+    "4k2x": dict(H=2176, W=3840, fh=2160, fw=3840, pairs=4, ts=(0.5,), scale=0.5,
+                 text="4K 2X: 2176x3840 (padded 2160p) frame pairs, timestep 0.5, scale 0.5 (scale_list [32,16,8,4,2])"),
+}
+WEIGHTS_TEXT = "HDv3 v4.25 weights = seeded default init"
 BYTES_PER_PIXEL_MODEL = 601.9     # stage-fused HBM traffic model, elements per pixel per pair
 FLOP_PER_PIXEL = 6064 + 38372.3   # SURVEY 8d at scale = 1
+BLOCK_C = (192, 128, 96, 64, 32)
+
+
+def stage_model(P, H, W, esz, io_esz, nframes):
+    """Algorithmic (compulsory) HBM bytes and real FLOPs of every pipeline stage of ONE step at scale = 1 -- each kernel
+    reads its inputs once and writes its outputs once.  Keys = the stage names of
+    rife_plan_get_profile; P outputs, `nframes` SRC frames (2P for independent pairs)."""
+    N, NF = P * H * W, nframes * H * W
+    m = {}
+    m["prep"] = (NF * CH * io_esz + NF / 4 * 16 * esz, 0.0)
+    m["head.cnn0"] = (2 * NF / 4 * 16 * esz, 2.0 * NF / 4 * 27 * 16)
+    one = (2 * NF / 4 * 16 * esz, 2.0 * NF / 4 * 9 * 16 * 16)
+    m["head.cnn1"] = m["head.cnn2"] = one
+    m["head.cnn1+2"] = (one[0], 2 * one[1])                      # fused pair: the intermediate never reaches HBM
+    m["head.cnn3"] = (NF / 4 * 16 * esz * 2 + NF * 8 * esz, 2.0 * NF * 4 * 4 * 16)   # features + s2d frame in, SRC out
+    for i, c in enumerate(BLOCK_C):
+        s = 16 >> i
+        n = N / (s * s)
+        p_in = 15 if i == 0 else 28
+        if i == 0:
+            gather = N * 4 / 256 * 2 * 8 * esz
+        else:
+            samp = N if s == 1 else N * 4 / (s * s)             # full-resolution pixels the 1/s resize reads
+            gather = samp * 2 * 8 * esz                          # one 8-channel SRC pixel per frame per sample
+            gather += N / ((2 * s) ** 2) * 16 * esz              # newest tmp level (block i - 1)
+            if s <= 2:
+                gather += samp * 16 * (2 if s == 1 else 1)       # fp32 flow buffer: written at s = 2, read + rewritten at s = 1
+        m[f"b{i}.input"] = (gather + n * 32 * esz, 0.0)
+        m[f"b{i}.conv0.0"] = (n * 32 * esz + n / 4 * (c // 2) * esz, 2.0 * n / 4 * 9 * p_in * (c // 2))
+        m[f"b{i}.conv0.1"] = (n / 4 * (c // 2) * esz + n / 16 * c * esz, 2.0 * n / 16 * 9 * (c // 2) * c)
+        # 8 ResConv layers; the fused pairs of block 4 (conv_strip.cu) read and write HBM once per two layers
+        m[f"b{i}.res"] = (8 * 2 * n / 16 * c * esz, 8 * 2.0 * n / 16 * 9 * c * c)
+        m[f"b{i}.res/fused-pairs"] = (4 * 2 * n / 16 * c * esz, 8 * 2.0 * n / 16 * 9 * c * c)
+        tmp_c = 8 if i == 4 else 16                              # Model.inference: flow + mask only from the last block
+        m[f"b{i}.lastconv"] = (n / 16 * c * esz + n * tmp_c * esz, 2.0 * n / 16 * 16 * c * (20 if i == 4 else 52))
+    m["merge"] = (N * (16 + 8 * esz + 2 * 4 * esz + CH * io_esz), 0.0)   # flow buffer + tmp4 + image halves of 2 SRC pixels + frame out
+    return m
 
 
 def peaks():
@@ -146,36 +196,74 @@ def smooth_pairs(n, h, w, seed, dtype):
     return a.clamp(0, 1).to(dtype).contiguous(), b.clamp(0, 1).to(dtype).contiguous()
 
 
-def cpu_reference_fps(n_pairs, warmup=1):
-    """The reference's CPU path (fp32, all host threads): oracle/torch_ref.py issues the same ATen operator sequence
-    as train_log/RIFE_HDv3.py:56-60 (the unmodified reference only exists in the build container)."""
+def find_reference():
+    """The unmodified reference, when this box has it: $RIFE_REFERENCE, baseline/_ref, or the build container's mount."""
+    for d in (os.environ.get("RIFE_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if d and os.path.exists(os.path.join(d, "train_log", "RIFE_HDv3.py")):
+            return d
+    return None
+
+
+def cpu_reference_fps(wl, n_calls, warmup=1):
+    """The reference's CPU path (fp32, all host threads) on single frame pairs of the workload's shape.  kind "reference":
+    the unmodified train_log/RIFE_HDv3.Model imported from find_reference(), same seeded weights; kind "port":
+    oracle/torch_ref.py issues the same ATen operator sequence as train_log/RIFE_HDv3.py:56-60 (the reference is pure
+    Python on PyTorch, has no setup.py to install from, and only exists in the build container)."""
     import torch
-    from oracle import torch_ref as T
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    torch.set_grad_enabled(False)
     sd = seeded_state_dict()
-    a, b = smooth_pairs(1, H, W, 0, torch.float32)
-    for _ in range(warmup):
-        T.model_inference(sd, a, b)
+    a, b = smooth_pairs(1, wl["H"], wl["W"], 0, torch.float32)
+    ref_dir = find_reference()
+    kind = "port"
+    if ref_dir:
+        try:
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, ref_dir)
+            from train_log.RIFE_HDv3 import Model as RefModel   # the reference itself
+            import model.warplayer as ref_wl
+            ref_wl.device = torch.device("cpu")
+            m = RefModel()
+            m.flownet.load_state_dict(sd)
+            m.flownet.to("cpu")
+            m.eval()
+            run = lambda t: m.inference(a, b, t, wl["scale"])
+            kind = "reference"
+        except Exception as e:   # missing optional dependency of the reference's import chain etc.
+            sys.stderr.write(f"bench: unmodified reference at {ref_dir} not importable ({e}); using the port\n")
+            sys.path.remove(ref_dir)
+    if kind == "port":
+        from oracle import torch_ref as T
+        run = lambda t: T.model_inference(sd, a, b, timestep=t, scale=wl["scale"])
+    ts = wl["ts"]
+    for i in range(warmup):
+        run(ts[i % len(ts)])
     t0 = time.perf_counter()
-    for _ in range(n_pairs):
-        T.model_inference(sd, a, b)
+    for i in range(n_calls):
+        run(ts[i % len(ts)])
     dt = time.perf_counter() - t0
-    return n_pairs / dt, dt / n_pairs, cores
+    return n_calls / dt, dt / n_calls, cores, kind
+
+
+def metric_name(wname):
+    return "interpolated frames/sec at 1080p 2X" if wname == "1080p2x" else f"interpolated frames/sec, workload {wname}"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    fps, sec, cores = cpu_reference_fps(args.steps, args.warmup)
+    wl = WORKLOADS[args.workload]
+    fps, sec, cores, kind = cpu_reference_fps(wl, args.steps, args.warmup)
+    what = ("unmodified reference train_log/RIFE_HDv3.Model.inference on CPU" if kind == "reference" else
+            "torch-CPU fp32 port of the reference op sequence (oracle/torch_ref.py)")
     line = {
-        "impl": "reference", "metric": "interpolated frames/sec at 1080p 2X", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": 1, "device": "cpu"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} single 1088x1920 pairs after {args.warmup} warm-up, torch-CPU fp32 port "
-                                   f"of the reference op sequence (oracle/torch_ref.py), {cores} threads"},
+        "config": {"workload": wl["text"] + ", " + WEIGHTS_TEXT, "pairs_per_step": 1, "device": "cpu"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} single {wl['H']}x{wl['W']} pairs after {args.warmup} warm-up, {what}, {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -188,11 +276,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RIFE_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
-    ap.add_argument("--pairs", type=int, default=16, help="frame pairs per step per GPU (batch of one Model.inference)")
+    ap.add_argument("--precision", default=os.environ.get("RIFE_BENCH_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--workload", default="1080p2x", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (0 = the workload's default)")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("RIFE_CHUNK_PAIRS", "0")),
                     help="pairs per pass of the 1/2- and full-resolution stages (rife_plan_set_chunk); 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-leg", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -214,14 +304,17 @@ def main():
     pkg = importlib.import_module("eccv2022-rife_b200")
     lib = pkg._lib.load()
     numa_cores = pkg.sharding.bind_to_gpu_numa(local_rank) if world > 1 else 0   # pinned buffers on the GPU's NUMA node
-    pkg.model.device = dev
     torch.manual_seed(1234)
     model = pkg.Model(precision=args.precision)
     model.eval()
     net = model.flownet
-    P = args.pairs
-    dt = torch.float16 if args.precision == "fp16" else torch.float32
-    esz = 2 if args.precision == "fp16" else 4
+    wl = WORKLOADS[args.workload]
+    H, W, FH, FW = wl["H"], wl["W"], wl["fh"], wl["fw"]
+    P = args.pairs or wl["pairs"]
+    TS, scale = wl["ts"], wl["scale"]
+    NT = len(TS)
+    dt = torch.float32 if args.precision == "fp32" else torch.float16
+    esz = 4 if args.precision == "fp32" else 2
 
     # ---- synthetic inputs: NSETS distinct batches so that no step finds its inputs in L2 (each step also streams
     #      far more than the 126 MB L2 through its intermediates)
@@ -243,10 +336,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def infer_dev(a, b):
+        if NT == 1:
+            return model.inference(a, b, TS[0], scale)
+        return model.inference_multi(a, b, TS, scale)
+
     # ---- (1) device-resident throughput: `value`
     for i in range(args.warmup):
         a, b = dev_sets[i % NSETS]
-        out = model.inference(a, b)
+        out = infer_dev(a, b)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = lib.rife_launch_count()
@@ -254,80 +352,105 @@ def main():
     e0.record()
     for i in range(args.steps):
         a, b = dev_sets[i % NSETS]
-        out = model.inference(a, b)
+        out = infer_dev(a, b)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.rife_launch_count() - n0
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms / args.steps
-    value = world * P * args.steps / (ms / 1e3)
+    value = world * P * NT * args.steps / (ms / 1e3)
 
-    # ---- (2) end to end through the host-buffer C-ABI call (rife_inference_host): pinned host frames exactly as a video
-    #      decoder delivers them -- uint8 HWC, true 1080 x 1920 (the library pads to 1088 and crops back) -> H2D ->
-    #      inference -> D2H of the uint8 result, every step.  Three plan slots rotate over one H2D, one compute and one
-    #      D2H stream (rife_inference_host_pipelined): the PCIe copies of a step overlap the kernels of its neighbours
-    #      and the kernels of consecutive steps run back to back.
+    # ---- (2) end to end through the host-buffer C-ABI call (rife_inference_host_pipelined): pinned host frames exactly
+    #      as a video decoder delivers them -- uint8 HWC, true frame size (the library pads and crops) -> H2D -> inference
+    #      -> D2H of the uint8 result, every step.  Three plan slots rotate over one H2D, one compute and one D2H stream:
+    #      the PCIe copies of a step overlap the kernels of its neighbours.
+    #      (a) `e2e`, video order (inference_video.py:215-270 walks consecutive frames; "2X" = one new frame between
+    #          every two decoded ones): a step uploads P + 1 consecutive frames and downloads the P in-between frames --
+    #          every decoded frame crosses the host link (and the Head) once;
+    #      (b) `e2e_pairs`: P independent pairs per step (2P frames up, P down), the round-1 definition.
     NSLOT = 3
-    FH, FW = 1080, 1920
-    u8_sets = []
-    for a, b in host_sets:
-        fa = (a[:, :, :FH, :FW].float() * 255).byte().permute(0, 2, 3, 1).contiguous().pin_memory()
-        fb = (b[:, :, :FH, :FW].float() * 255).byte().permute(0, 2, 3, 1).contiguous().pin_memory()
-        u8_sets.append((fa, fb))
+    u8 = lambda t: (t[:, :, :FH, :FW].float() * 255).byte().permute(0, 2, 3, 1).contiguous().pin_memory()
+    u8_sets = [(u8(a), u8(b)) for a, b in host_sets]
+    seq_sets = [torch.cat((fa, fb[:1]), 0).contiguous().pin_memory() for fa, fb in u8_sets]    # P + 1 frames
     host_out = [torch.empty((P, FH, FW, CH), dtype=torch.uint8).pin_memory() for _ in range(NSLOT)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSLOT)]
     cur = torch.cuda.current_stream()
+    frame_bytes = CH * FH * FW
+    e2e_legs = {}
 
-    def e2e_steps(n):
-        for i in range(n):
-            k = i % NSLOT
-            a, b = u8_sets[i % NSETS]
-            model.inference_host(a, b, host_out[k], slot=k, streams=streams)
+    def timed(fn, nwarm):
+        fn(nwarm)
+        barrier()
+        e0.record()
+        for st_ in streams:
+            st_.wait_stream(cur)
+        fn(args.steps)
+        for st_ in streams:
+            cur.wait_stream(st_)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    e2e_steps(2 * NSLOT)
-    barrier()
-    e0.record()
-    for st_ in streams:
-        st_.wait_stream(cur)
-    e2e_steps(args.steps)
-    for st_ in streams:
-        cur.wait_stream(st_)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e = world * P * args.steps / (ms_e2e / 1e3)
-    frame_bytes = P * CH * FH * FW
+    if NT == 1:
+        def seq_steps(n):
+            for i in range(n):
+                model.inference_host(seq_sets[i % NSETS], None, host_out[i % NSLOT], TS[0], scale, slot=i % NSLOT,
+                                     streams=streams, device=dev)
 
-    # ---- (2b) the same PCIe traffic with no kernels: what the host <-> device link alone sustains with every rank
-    #      copying at once (explains e2e when several GPUs share the host's PCIe / memory bandwidth)
-    d_in = [torch.empty_like(u8_sets[0][0], device=dev) for _ in range(2)]
-    d_out = torch.empty((P, FH, FW, CH), dtype=torch.uint8, device=dev)
+        def pair_steps(n):
+            for i in range(n):
+                a, b = u8_sets[i % NSETS]
+                model.inference_host(a, b, host_out[i % NSLOT], TS[0], scale, slot=i % NSLOT, streams=streams, device=dev)
 
-    def copy_steps(n):
-        for i in range(n):
-            a, b = u8_sets[i % NSETS]
-            with torch.cuda.stream(streams[0]):
+        for name, fn, up in (("video", seq_steps, P + 1), ("pairs", pair_steps, 2 * P)):
+            ms_leg = timed(fn, 2 * NSLOT)
+            e2e_legs[name] = {"value": world * P * args.steps / (ms_leg / 1e3), "unit": "frames/s",
+                              "h2d_bytes_per_step": up * frame_bytes, "d2h_bytes_per_step": P * frame_bytes,
+                              "ms_per_step": ms_leg / args.steps}
+    else:
+        # several timesteps per pair: pinned uint8 frames -> device -> inference_multi -> pinned uint8 result, one stream
+        multi_out = torch.empty((P, NT, FH, FW, CH), dtype=torch.uint8).pin_memory()
+        d_in = [torch.empty_like(u8_sets[0][0], device=dev) for _ in range(2)]
+
+        def multi_steps(n):
+            for i in range(n):
+                a, b = u8_sets[i % NSETS]
                 d_in[0].copy_(a, non_blocking=True)
                 d_in[1].copy_(b, non_blocking=True)
-            with torch.cuda.stream(streams[2]):
-                host_out[i % NSLOT].copy_(d_out, non_blocking=True)
+                multi_out.copy_(model.inference_multi(d_in[0], d_in[1], TS, scale, pad=True), non_blocking=True)
 
-    copy_steps(3)
-    barrier()
-    e0.record()
-    for st_ in streams:
-        st_.wait_stream(cur)
-    copy_steps(args.steps)
-    for st_ in streams:
-        cur.wait_stream(st_)
-    e1.record()
-    barrier()
-    ms_copy = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        ms_leg = timed(multi_steps, 3)
+        e2e_legs["pairs"] = {"value": world * P * NT * args.steps / (ms_leg / 1e3), "unit": "frames/s",
+                             "h2d_bytes_per_step": 2 * P * frame_bytes, "d2h_bytes_per_step": P * NT * frame_bytes,
+                             "ms_per_step": ms_leg / args.steps}
+
+    # ---- (2b) the same PCIe traffic with no kernels, each direction alone and both at once: what the host <-> device
+    #      link sustains with every rank copying at the same time (names the limit of e2e on a box whose GPUs share it)
+    d_seq = torch.empty_like(seq_sets[0], device=dev)
+    d_out = torch.empty((P, FH, FW, CH), dtype=torch.uint8, device=dev)
+
+    def copy_steps(h2d, d2h):
+        def fn(n):
+            for i in range(n):
+                if h2d:
+                    with torch.cuda.stream(streams[0]):
+                        d_seq.copy_(seq_sets[i % NSETS], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(streams[2]):
+                        host_out[i % NSLOT].copy_(d_out, non_blocking=True)
+        return fn
+
+    ms_h2d = timed(copy_steps(True, False), 3) / args.steps
+    ms_d2h = timed(copy_steps(False, True), 3) / args.steps
+    ms_both = timed(copy_steps(True, True), 3) / args.steps
+    link = {"h2d_GBps_per_gpu": (P + 1) * frame_bytes / ms_h2d / 1e6, "d2h_GBps_per_gpu": P * frame_bytes / ms_d2h / 1e6,
+            "both_ms_per_step": ms_both, "h2d_alone_ms_per_step": ms_h2d, "d2h_alone_ms_per_step": ms_d2h,
+            "what": "video-order copies of one step (P + 1 frames up, P frames down), no kernels, all ranks at once"}
 
     # ---- (3) per-kernel CUDA-event timing (separate pass over the same steps so that `value` is undisturbed)
-    plan = net._plans[next(k for k in net._plans if k[-1] == 0)]
-    lib.rife_plan_set_frame_size(plan.handle, H, W)   # slot 0 was last used by the 1080-row e2e path
+    plan = net._plans[next(k for k in net._plans if k[-3] == 0 and k[1] == P and not k[-1] and k[-2] == NT)]
+    lib.rife_plan_set_frame_size(plan.handle, H, W)   # slot 0 was last used by the true-frame-size e2e path
     plan.frame = (H, W)
     lib.rife_plan_set_profiling(plan.handle, 1)
     acc, cnt = {}, {}
@@ -336,7 +459,7 @@ def main():
     prof_steps = min(args.steps, 5)
     for i in range(prof_steps):
         a, b = dev_sets[i % NSETS]
-        model.inference(a, b)
+        infer_dev(a, b)
         torch.cuda.synchronize()
         n = lib.rife_plan_get_profile(plan.handle, names, msbuf, 128)
         for k in range(n):
@@ -347,59 +470,103 @@ def main():
     stage_ms = {k: acc[k] / prof_steps for k in acc}          # ms per step, summed over that stage's launches
     stage_launches = {k: cnt[k] / prof_steps for k in cnt}
 
+    # ---- (4) roofline: every stage against its own bound.  t_hbm = algorithmic bytes / measured copy peak, t_tc = real
+    #      FLOPs / measured sustained dense bf16 rate (MEASURED_PEAKS.json); the stage's bound is the larger of the two and
+    #      frac = that time / the CUDA-event time of the stage.  Scale-1, single-timestep workloads only.
     hbm_peak, tf_peak, peak_src = peaks()
-    N = P * H * W
-    # algorithmic bytes of the dominant HBM-bound kernel, the block-4 input gather:
-    #   reads src0+src1 (2 x 8 ch) + tmp_3 (16 ch at 1/4 of the pixels) + tmp_0..2 (negligible), writes 32 ch
-    alg = {
-        # src0 + src1 (8 ch each) + tmp_3 (16 ch at 1/4 of the pixels) + xin (32 ch), in E-byte elements,
-        # plus the fp32 flow buffer read and re-written (2 x 16 bytes per pixel)
-        "b4.input": N * esz * (16 + 16 / 4 + 32) + N * 32,
-        "merge": N * esz * (16 + 16 + 16 / 4 + 16 / 16 + 16 / 64 + 16 / 256) + N * CH * esz,
-        "prep": 2 * N * CH * esz + 2 * N * esz * (8 + 16 / 4),
-    }
-    top = max(stage_ms, key=lambda k: stage_ms[k])
-    rk = "b4.input"
-    n_l = max(stage_launches.get(rk, 1), 1)            # launches of that kernel per step (= passes, --chunk)
-    k_ms = stage_ms.get(rk, 0.0) / n_l
-    alg_launch = alg[rk] / n_l
-    achieved = alg_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tp) and args.precision == "fp16":
-        tj = json.load(open(tp))
-        traffic = tj.get("traffic_bytes_per_launch") * (P / n_l) / float(tj.get("pairs", 4))   # bytes scale with the pairs per launch
-    roofline = {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_launch, "kernel_ms": k_ms, "launches_per_step": n_l,
-                "top_stage_by_time": top,
-                "pipeline_model": {"bytes_per_pair_stage_fused_model": BYTES_PER_PIXEL_MODEL * H * W * esz,
-                                   "frac_of_hbm_peak": (BYTES_PER_PIXEL_MODEL * H * W * esz * value / world) / (hbm_peak * 1e9),
-                                   "tflops": FLOP_PER_PIXEL * H * W * value / world / 1e12},
-                "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
+    stages = []
+    if scale == 1.0 and NT == 1:
+        sm = stage_model(P, H, W, esz, esz, 2 * P)
+        for nm, t_ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
+            key = nm
+            if nm == "b4.res" and stage_launches.get(nm, 8) <= 4.5:
+                key = "b4.res/fused-pairs"
+            if key not in sm or t_ms <= 0:
+                continue
+            by, fl = sm[key]
+            t_hbm, t_tc = by / (hbm_peak * 1e9), fl / (tf_peak * 1e12)
+            bound = "tensor" if t_tc > t_hbm else "hbm"
+            ach = fl / (t_ms * 1e-3) / 1e12 if bound == "tensor" else by / (t_ms * 1e-3) / 1e9
+            stages.append({"stage": nm, "ms_per_step": round(t_ms, 4), "launches_per_step": stage_launches[nm],
+                           "bound": bound, "alg_bytes": by, "flops": fl, "achieved": round(ach, 1),
+                           "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                           "frac": round(max(t_hbm, t_tc) / (t_ms * 1e-3), 4),
+                           "hbm_frac": round(t_hbm / (t_ms * 1e-3), 4), "tensor_frac": round(t_tc / (t_ms * 1e-3), 4)})
+    if stages:
+        dom = stages[0]                                        # dominant stage by time
+        worst = min((s_ for s_ in stages if s_["ms_per_step"] >= 0.01 * sum(stage_ms.values())), key=lambda s_: s_["frac"])
+        n_l = max(dom["launches_per_step"], 1)
+        roofline = {"bound": dom["bound"], "kernel": dom["stage"], "achieved": dom["achieved"],
+                    "peak": tf_peak if dom["bound"] == "tensor" else hbm_peak, "unit": dom["unit"], "frac": dom["frac"],
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom["alg_bytes"] / n_l, "kernel_ms": dom["ms_per_step"] / n_l,
+                    "launches_per_step": n_l,
+                    "worst_stage": {k: worst[k] for k in ("stage", "bound", "frac", "ms_per_step")},
+                    "time_weighted_frac": round(sum(s_["frac"] * s_["ms_per_step"] for s_ in stages) /
+                                                sum(s_["ms_per_step"] for s_ in stages), 4),
+                    "pipeline_model": {"bytes_per_pair_stage_fused_model": BYTES_PER_PIXEL_MODEL * H * W * esz,
+                                       "frac_of_hbm_peak": (BYTES_PER_PIXEL_MODEL * H * W * esz * value / world) / (hbm_peak * 1e9),
+                                       "tflops": FLOP_PER_PIXEL * H * W * value / world / 1e12},
+                    "stages": stages}
+    else:
+        roofline = {"bound": "hbm", "kernel": None, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                    "traffic": None, "peak_source": peak_src,
+                    "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
 
     line = {
-        "metric": "interpolated frames/sec at 1080p 2X", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": metric_name(args.workload), "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "pairs_per_pass_full_res_stages": int(P / n_l + 0.5),
+        "config": {"workload": wl["text"] + ", " + WEIGHTS_TEXT, "workload_name": args.workload,
+                   "pairs_per_step_per_gpu": P, "outputs_per_step_per_gpu": P * NT,
                    "precision": args.precision,
                    "parallelism": f"frame-pair sharding x{world}, no collective",
                    "host_numa_cores_bound": numa_cores,
                    "l2_policy": f"inputs rotate over {NSETS} distinct batches; each step streams >1 GB of intermediates (> 126 MB L2)"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": frame_bytes,
-                "ms_per_step": ms_e2e / args.steps, "copy_only_ms_per_step": ms_copy,
-                "api": "rife_inference_host: pinned uint8 HWC 1080x1920 frames in, uint8 HWC frame out, 3 plan slots over h2d / compute / d2h streams (rife_inference_host_pipelined)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
     }
+    api = ("Model.inference_host -> rife_inference_host_pipelined: pinned uint8 HWC %dx%d frames in, uint8 HWC frames out, "
+           "3 plan slots over h2d / compute / d2h streams" % (FH, FW))
+    if "video" in e2e_legs:
+        line["e2e"] = dict(e2e_legs["video"], api=api + "; VIDEO ORDER: each step uploads P + 1 consecutive frames and "
+                           "downloads the P in-between frames (2X interpolation of a decoded stream: every frame crosses "
+                           "the link and the Head once)", host_link=link)
+        line["e2e_pairs"] = dict(e2e_legs["pairs"], api=api + "; P independent frame pairs per step (round-1 definition)")
+    else:
+        line["e2e"] = dict(e2e_legs["pairs"], api="pinned uint8 frames -> device -> Model.inference_multi -> pinned uint8 frames, one stream",
+                           host_link=link)
+
+    # ---- (5) the fp32 mode every fp32-tensor caller of the drop-in lands on (precision="auto"), for the record
+    if args.precision != "fp32" and not args.no_fp32_leg and NT == 1:
+        del dev_sets, host_sets
+        torch.cuda.empty_cache()
+        m32 = pkg.Model(precision="fp32")
+        m32.flownet.load_state_dict(net.state_dict())
+        m32.eval()
+        P32 = min(P, 4)
+        a32, b32 = smooth_pairs(P32, H, W, 7, torch.float32)
+        a32, b32 = a32.to(dev), b32.to(dev)
+        for _ in range(2):
+            m32.inference(a32, b32, TS[0], scale)
+        barrier()
+        e0.record()
+        for _ in range(3):
+            m32.inference(a32, b32, TS[0], scale)
+        e1.record()
+        barrier()
+        line["fp32_value"] = {"value": world * P32 * 3 / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), "unit": "frames/s",
+                              "pairs_per_step_per_gpu": P32, "steps": 3,
+                              "what": "the same workload in RIFE_PRECISION_FP32 (<= 1e-4 vs the reference), device-resident"}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, sec, cores = cpu_reference_fps(6, 1)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"6 single 1088x1920 pairs after 1 warm-up ({sec:.2f} s each), torch-CPU fp32 port of "
-                                          f"the reference op sequence (oracle/torch_ref.py), {cores} threads"}
+        fps, sec, cores, kind = cpu_reference_fps(wl, 6, 1)
+        what = ("unmodified reference (train_log/RIFE_HDv3.Model.inference, CPU)" if kind == "reference" else
+                "torch-CPU fp32 port of the reference op sequence (oracle/torch_ref.py)")
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                                "sample": f"6 single {H}x{W} pairs after 1 warm-up ({sec:.2f} s each), {what}, {cores} threads"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -14,7 +14,8 @@ PRECISION_FP32, PRECISION_FP16, PRECISION_BF16 = 0, 1, 2
 # every symbol declared in include/rife_b200.h
 SYMBOLS = [
     "rife_abi_version", "rife_last_error", "rife_launch_count", "rife_weights_create", "rife_weights_destroy",
-    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_workspace_bytes_ex", "rife_plan_create_ex", "rife_plan_destroy", "rife_plan_set_frame_size",
+    "rife_plan_workspace_bytes", "rife_plan_create", "rife_plan_workspace_bytes_ex", "rife_plan_create_ex",
+    "rife_plan_workspace_bytes_list", "rife_plan_create_list", "rife_plan_destroy", "rife_plan_set_frame_size",
     "rife_plan_set_profiling", "rife_plan_set_chunk",
     "rife_plan_get_profile", "rife_inference", "rife_ifnet_forward",
     "rife_inference_host", "rife_inference_host_pipelined", "rife_warp", "rife_resize_bilinear", "rife_conv3x3", "rife_conv_transpose4x4s2",
@@ -58,6 +59,9 @@ def load():
     lib.rife_plan_workspace_bytes_ex.argtypes = [i, i, i, i, i, i, f, i]
     lib.rife_plan_workspace_bytes_ex.restype = sz
     lib.rife_plan_create_ex.argtypes = [C.POINTER(vp), vp, i, i, i, i, i, i, f, vp, sz, vp, vp]
+    lib.rife_plan_workspace_bytes_list.argtypes = [i, i, i, i, i, i, fp, i]
+    lib.rife_plan_workspace_bytes_list.restype = sz
+    lib.rife_plan_create_list.argtypes = [C.POINTER(vp), vp, i, i, i, i, i, i, fp, vp, sz, vp, vp]
     lib.rife_plan_destroy.argtypes = [vp]
     lib.rife_plan_set_frame_size.argtypes = [vp, i, i]
     lib.rife_plan_set_profiling.argtypes = [vp, i]

@@ -1,6 +1,7 @@
 // C ABI of librife_b200.so (include/rife_b200.h): weight repacking, plan/workspace, the IFNet pipeline.
 // Host-side orchestration of train_log/IFNet_HDv3.py:119-169 and train_log/RIFE_HDv3.py:56-60.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -190,7 +191,12 @@ static int upload_layer(rife_weights* w, const HostLayer& h, DevLayer* d, bool p
 }
 
 static bool strip_enabled() {
-  static const bool on = !(getenv("RIFE_STRIP") && atoi(getenv("RIFE_STRIP")) == 0);   // A/B switch: per-layer halo kernel
+  // RIFE_STRIP=1: Head.cnn1+cnn2 and the ResConv pairs of IFBlock 4 run on the fused kx-stacked strip kernel
+  // (conv_strip.cu).  Off by default: measured on B200 (16 x 1080p pairs) it is slower than the per-layer halo kernel --
+  // b4.res 0.78 vs 0.58 ms, head.cnn1+2 0.58 vs 0.42 ms -- because a tcgen05.mma's operand reads already saturate the
+  // SM's shared-memory bandwidth (N = 96: 7 KB per 56 cycles) and the epilogue's residual loads, intermediate stores and
+  // shuffles compete for it; see DESIGN.md section 5.
+  static const bool on = getenv("RIFE_STRIP") && atoi(getenv("RIFE_STRIP")) != 0;
   return on;
 }
 
@@ -340,33 +346,40 @@ int rife_weights_destroy(rife_weights* w) {
 constexpr int kTileCtrs = 1024;
 
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, ctrs, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, ctrs, io_tab, stage_in0, stage_in1,
       stage_out, total;
   int s[5];   // block i works at H / s[i] * u[i]: scale_list[i] = s[i] / u[i] (one of the two is 1)
   int u[5];
+  bool generic = false;   // scale_list is not the halving pyramid of RIFE_HDv3.py:58: generic pixel kernels only
 };
 
 // P frame pairs, T timesteps per pair (outputs B = P*T, pair-major), `seq`: the pairs are the P consecutive pairs of
 // ONE run of P+1 frames (Head features computed once per frame instead of twice)
-static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, int precision, PlanLayout* L) {
+// `sl`: the five entries of IFNet.forward's scale_list (IFNet_HDv3.py:119,139-148), each a power of two in [1/4, 64]
+static int plan_layout(int P, int T, int seq, int C, int H, int W, const float* sl5, int precision, PlanLayout* L) {
   if (P < 1 || T < 1 || H < 1 || W < 1) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: pairs, timesteps, H, W must be positive");
   const int B = P * T, F = seq ? P + 1 : 2 * P;
   if (C != 3 && C != 4) RIFE_FAIL(RIFE_ERR_SHAPE, "plan: C must be 3 or 4 (IFNet_HDv3.py:121-123 splits an RGB/RGBA pair)");
-  if (!(scale == 1.f || scale == 0.5f || scale == 0.25f || scale == 2.f || scale == 4.f))
-    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be one of 0.25, 0.5, 1, 2, 4 (inference_video.py:92)");
   if (precision != RIFE_PRECISION_FP32 && !is_half_mode(precision)) RIFE_FAIL(RIFE_ERR_DTYPE, "plan: bad precision");
-  const int base[5] = {16, 8, 4, 2, 1};
   bool any_up = false;
-  for (int i = 0; i < 5; ++i) {  // scale_list = [16, 8, 4, 2, 1] / scale, RIFE_HDv3.py:58
-    const float sl = (float)base[i] / scale;
+  L->generic = false;
+  for (int i = 0; i < 5; ++i) {
+    const float sl = sl5[i];
+    int e = 0;
+    const float m = frexpf(sl, &e);   // sl = m * 2^e, m = 0.5 for a power of two
+    if (!(sl >= 0.25f && sl <= 64.f) || m != 0.5f)
+      RIFE_FAIL(RIFE_ERR_SHAPE, "plan: every scale_list entry must be a power of two in [1/4, 64] (inference_video.py:92 with "
+                                "scale_list = [16, 8, 4, 2, 1] / scale gives exactly those); got " + std::to_string(sl));
     L->s[i] = sl >= 1.f ? (int)lroundf(sl) : 1;
-    L->u[i] = sl >= 1.f ? 1 : (int)lroundf(1.f / sl);   // scale > 1: the last block(s) work above full resolution
+    L->u[i] = sl >= 1.f ? 1 : (int)lroundf(1.f / sl);   // entry < 1: the block works above full resolution
     any_up = any_up || L->u[i] > 1;
+    if (i > 0 && sl5[i - 1] != 2.f * sl) L->generic = true;
+    // block i works on (H / s * u, W / s * u) and halves it twice more (conv0): that size must be a multiple of 4
+    if (H % L->s[i] || W % L->s[i] || (H / L->s[i] * L->u[i]) % 4 || (W / L->s[i] * L->u[i]) % 4)
+      RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale (in general of 4 * scale_list[i] for every "
+                                "block, IFNet_HDv3.py:79-81 + two stride-2 convs); got " + std::to_string(H) + "x" + std::to_string(W) +
+                                " with scale_list[" + std::to_string(i) + "] = " + std::to_string(sl));
   }
-  const int mult = (int)lroundf(64.f / scale);
-  if (H % mult || W % mult)
-    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: H and W must be multiples of 64/scale = " + std::to_string(mult) + " (got " +
-                                  std::to_string(H) + "x" + std::to_string(W) + ")");
   const size_t E = is_half_mode(precision) ? 2 : 4;
   const size_t N = (size_t)B * H * W, NF = (size_t)F * H * W;
   size_t off = 0;
@@ -399,6 +412,7 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, float scale, 
   L->tstep = take((size_t)B * 4);
   L->sync = take(256);   // grid-barrier counter of the ResConv chain kernel
   L->ctrs = take(kTileCtrs * 4);   // one dynamic-tile-scheduling counter per halo-kernel launch of a call
+  L->io_tab = take(256);           // {img0, img1, merged} of the current call, read by a replayed CUDA graph
   L->stage_in0 = take((size_t)(seq ? P + 1 : P) * H * W * C * 4);
   L->stage_in1 = take((size_t)(seq ? 0 : P) * H * W * C * 4);
   L->stage_out = take(N * C * 4);
@@ -432,7 +446,16 @@ struct rife_plan {
   size_t n_stage = 0;  // stages recorded by the last run
   // rife_inference_host_pipelined: "staging-in filled", "compute done", "staging-out drained"
   cudaEvent_t ev_in = nullptr, ev_compute = nullptr, ev_out = nullptr;
+  // CUDA-graph replay of rife_inference for small batches: the ~66 dependent launches of one
+  // call are captured once per (io dtype, frame size) and replayed; the frame pointers travel through L.io_tab
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t cap_stream = nullptr;   // capture happens on a stream of the plan's own: the caller's may be the legacy default stream
+  int g_io = -1, g_fh = 0, g_fw = 0, g_chunk = 0, g_launches = 0;
+  int graph_state = 0;   // 0 = not captured yet, 1 = captured, -1 = capture failed once: plain launches from then on
+  int plain_calls = 0;   // the first call always runs un-captured (one-time function attributes, lazy driver state)
   ~rife_plan() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (cudaEvent_t e : {ev_in, ev_compute, ev_out})
       if (e) cudaEventDestroy(e);
     for (auto& s : stages) {
@@ -474,9 +497,25 @@ size_t rife_plan_workspace_bytes(int B, int C, int H, int W, float scale, int pr
   return rife_plan_workspace_bytes_ex(B, 1, 0, C, H, W, scale, precision);
 }
 
+static int scale_to_list(float scale, float* sl5) {
+  if (!(scale == 1.f || scale == 0.5f || scale == 0.25f || scale == 2.f || scale == 4.f))
+    RIFE_FAIL(RIFE_ERR_SHAPE, "plan: scale must be one of 0.25, 0.5, 1, 2, 4 (inference_video.py:92)");
+  const float base[5] = {16.f, 8.f, 4.f, 2.f, 1.f};
+  for (int i = 0; i < 5; ++i) sl5[i] = base[i] / scale;   // scale_list = [16, 8, 4, 2, 1] / scale, RIFE_HDv3.py:58
+  return RIFE_OK;
+}
+
 size_t rife_plan_workspace_bytes_ex(int pairs, int timesteps, int sequence, int C, int H, int W, float scale, int precision) {
+  float sl[5];
+  if (scale_to_list(scale, sl) != RIFE_OK) return 0;
+  return rife_plan_workspace_bytes_list(pairs, timesteps, sequence, C, H, W, sl, precision);
+}
+
+size_t rife_plan_workspace_bytes_list(int pairs, int timesteps, int sequence, int C, int H, int W, const float* scale_list5,
+                                      int precision) {
   PlanLayout L;
-  if (plan_layout(pairs, timesteps, sequence, C, H, W, scale, precision, &L) != RIFE_OK) return 0;
+  if (!scale_list5) return 0;
+  if (plan_layout(pairs, timesteps, sequence, C, H, W, scale_list5, precision, &L) != RIFE_OK) return 0;
   return L.total;
 }
 
@@ -488,9 +527,17 @@ int rife_plan_create(rife_plan** out, const rife_weights* w, int B, int C, int H
 int rife_plan_create_ex(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C, int H, int W,
                         float scale, void* workspace, size_t workspace_bytes, const float* gridx_host,
                         const float* gridy_host) {
-  if (!out || !w || !workspace) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: null argument");
+  float sl[5];
+  RIFE_TRY(scale_to_list(scale, sl));
+  return rife_plan_create_list(out, w, pairs, timesteps, sequence, C, H, W, sl, workspace, workspace_bytes, gridx_host, gridy_host);
+}
+
+int rife_plan_create_list(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C, int H, int W,
+                          const float* scale_list5, void* workspace, size_t workspace_bytes, const float* gridx_host,
+                          const float* gridy_host) {
+  if (!out || !w || !workspace || !scale_list5) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_plan_create: null argument");
   PlanLayout L;
-  RIFE_TRY(plan_layout(pairs, timesteps, sequence ? 1 : 0, C, H, W, scale, w->precision, &L));
+  RIFE_TRY(plan_layout(pairs, timesteps, sequence ? 1 : 0, C, H, W, scale_list5, w->precision, &L));
   const int B = pairs * timesteps;
   if (workspace_bytes < L.total)
     RIFE_FAIL(RIFE_ERR_WORKSPACE, "rife_plan_create: workspace has " + std::to_string(workspace_bytes) + " bytes, need " +
@@ -608,8 +655,25 @@ static int run_conv(rife_plan* p, const DevLayer& L, const ConvIO& io_, bool hk,
   return launch_conv_f32(L.f32, io_, st);
 }
 
+// timesteps: rewritten only when they (or the stream) changed since the last call on this plan, and then through kernel
+// parameters -- a cudaMemcpyAsync here would sit on the H2D copy engine behind the next calls' frame uploads
+// (rife_inference_host_pipelined) and stall the compute stream for up to a whole frame-batch transfer
+static int update_tstep(rife_plan* p, const float* timestep_host, cudaStream_t st) {
+  const int B = p->B;
+  if (!(p->ts_valid && p->ts_stream == st && (int)p->ts_host.size() == B &&
+        memcmp(p->ts_host.data(), timestep_host, (size_t)B * 4) == 0)) {
+    RIFE_TRY(launch_set_tstep((float*)p->at(p->L.tstep), timestep_host, B, st));
+    p->ts_host.assign(timestep_host, timestep_host + B);
+    p->ts_stream = st;
+    p->ts_valid = true;
+  }
+  return RIFE_OK;
+}
+
+// graph_capture: the launches are being captured into the plan's CUDA graph -- the first / last kernel take the frame
+// pointers from the plan's table and the timesteps are already on the device
 static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const float* timestep_host,
-                        const rife_ifnet_outputs* outs, int io_dtype, cudaStream_t st) {
+                        const rife_ifnet_outputs* outs, int io_dtype, cudaStream_t st, bool graph_capture = false) {
   if (!p || !img0 || (!img1 && !p->seq) || !timestep_host || !outs) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: null argument");
   if (io_dtype != RIFE_F32 && io_dtype != RIFE_F16 && io_dtype != RIFE_U8)
     RIFE_FAIL(RIFE_ERR_DTYPE, "rife: io_dtype must be RIFE_F32, RIFE_F16 or RIFE_U8");
@@ -623,16 +687,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   const size_t E = half_act ? 2 : 4;
   const size_t N = (size_t)B * H * W;
 
-  // timesteps: rewritten only when they (or the stream) changed since the last call on this plan, and then through kernel
-  // parameters -- a cudaMemcpyAsync here would sit on the H2D copy engine behind the next calls' frame uploads
-  // (rife_inference_host_pipelined) and stall the compute stream for up to a whole frame-batch transfer
-  if (!(p->ts_valid && p->ts_stream == st && (int)p->ts_host.size() == B &&
-        memcmp(p->ts_host.data(), timestep_host, (size_t)B * 4) == 0)) {
-    RIFE_TRY(launch_set_tstep((float*)p->at(L.tstep), timestep_host, B, st));
-    p->ts_host.assign(timestep_host, timestep_host + B);
-    p->ts_stream = st;
-    p->ts_valid = true;
-  }
+  if (!graph_capture) RIFE_TRY(update_tstep(p, timestep_host, st));
 
   PixelCtx c;
   c.B = B; c.C = p->C; c.H = H; c.W = W;
@@ -648,8 +703,10 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   c.half_act = half_act;
   c.planar_head = half_act && w->head_hk;
   c.tile_ctrs = (unsigned int*)p->at(L.ctrs); c.n_tile_ctrs = kTileCtrs;
+  if (graph_capture) c.io_table = (const void* const*)p->at(L.io_tab);
   p->next_ctr = 0;
   for (int i = 0; i < 5; ++i) c.any_up = c.any_up || L.u[i] > 1;
+  c.any_up = c.any_up || L.generic;   // an arbitrary scale_list takes the generic (level-by-level) pixel kernels too
 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
   p->n_stage = 0;
@@ -824,13 +881,77 @@ int rife_ifnet_forward(rife_plan* p, const void* img0, const void* img1, const f
   return run_pipeline(p, img0, img1, timestep_host, outs, io_dtype, (cudaStream_t)stream);
 }
 
+static int graph_max_outputs() {
+  // RIFE_GRAPH_MAX=n: calls with at most n outputs replay a CUDA graph (default 4: above that the launches are hidden
+  // behind the kernels anyway); 0 turns graphs off
+  static const int v = getenv("RIFE_GRAPH_MAX") ? atoi(getenv("RIFE_GRAPH_MAX")) : 4;
+  return v;
+}
+
 int rife_inference(rife_plan* p, const void* img0, const void* img1, const float* timestep_host, void* out, int io_dtype,
                    void* stream) {
   if (!out) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife_inference: out is null");
   rife_ifnet_outputs o;
   memset(&o, 0, sizeof(o));
   o.merged = out;
-  return run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool hk_debug = getenv("RIFE_HK_DEBUG") != nullptr;
+  const bool want_graph = p && img0 && timestep_host && p->B <= graph_max_outputs() && !p->profile && p->graph_state >= 0 &&
+                          !hk_debug && (p->chunk <= 0 || p->chunk >= p->P) && default_chunk_pairs() <= 0 &&
+                          (io_dtype == RIFE_F32 || io_dtype == RIFE_F16 || io_dtype == RIFE_U8);
+  if (!want_graph || p->plain_calls < 1) {
+    if (p) p->plain_calls++;
+    return run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, st);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != p->device) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "rife: plan belongs to another device");
+  if (!p->gexec || p->g_io != io_dtype || p->g_fh != p->fh || p->g_fw != p->fw || p->g_chunk != p->chunk) {
+    if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();   // the caller is capturing this stream itself: just enqueue
+      return run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, st);
+    }
+    const uint64_t n0 = g_launch_count.load();
+    cudaGraph_t g = nullptr;
+    int rc = RIFE_ERR_CUDA;
+    std::string why = "cudaStreamCreate";
+    if (p->cap_stream || cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) == cudaSuccess) {
+      why = "cudaStreamBeginCapture";
+      if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, p->cap_stream, /*graph_capture=*/true);
+        if (rc != RIFE_OK) why = std::string("launch during capture: ") + rife_last_error();
+        const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
+        if (e != cudaSuccess || !g) {
+          if (rc == RIFE_OK) why = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e);
+          rc = RIFE_ERR_CUDA;
+        }
+      }
+    }
+    const int captured = (int)(g_launch_count.load() - n0);
+    g_launch_count.fetch_sub((uint64_t)captured);   // captured, not launched
+    if (rc == RIFE_OK) {
+      const cudaError_t e = cudaGraphInstantiate(&p->gexec, g, 0);
+      if (e != cudaSuccess) { rc = RIFE_ERR_CUDA; why = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); }
+    }
+    if (g) cudaGraphDestroy(g);
+    if (rc != RIFE_OK) {
+      cudaGetLastError();
+      p->gexec = nullptr;
+      p->graph_state = -1;   // e.g. a driver that cannot capture programmatic dependent launches: plain launches from now on
+      static std::atomic<bool> told{false};
+      if (!told.exchange(true)) fprintf(stderr, "librife_b200: CUDA-graph capture unavailable (%s); using plain launches\n", why.c_str());
+      return run_pipeline(p, img0, img1, timestep_host, &o, io_dtype, st);
+    }
+    p->graph_state = 1;
+    p->g_io = io_dtype; p->g_fh = p->fh; p->g_fw = p->fw; p->g_chunk = p->chunk; p->g_launches = captured;
+  }
+  RIFE_TRY(update_tstep(p, timestep_host, st));
+  RIFE_TRY(launch_set_io_table((const void**)p->at(p->L.io_tab), img0, img1, out, st));
+  RIFE_CUDA_TRY(cudaGraphLaunch(p->gexec, st));
+  g_launch_count.fetch_add((uint64_t)p->g_launches);
+  return RIFE_OK;
 }
 
 int rife_inference_host(rife_plan* p, const void* img0_host, const void* img1_host, const float* timestep_host,

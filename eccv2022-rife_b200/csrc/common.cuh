@@ -265,6 +265,9 @@ struct PixelCtx {
   bool planar_head = false;  // Head input stored planar-8 (conv_halo.cu) instead of pixel-major
   unsigned int* tile_ctrs = nullptr;  // the call's tile-scheduling counters, zeroed by the input-packing kernel
   int n_tile_ctrs = 0;
+  // CUDA-graph replay (api.cu): device table {img0, img1, merged} that overrides the frame pointers baked into the
+  // captured kernel nodes; null = use the launch arguments
+  const void* const* io_table = nullptr;
 };
 
 // NCHW image (io dtype) -> SRC tensor channels 4..7 (+ zeros in 0..3) and the s2d Head input [2B][H/2][W/2][16]
@@ -296,6 +299,7 @@ int launch_resize_op(const float* x, float* out, int B, int C, int H, int W, int
 int launch_fill_grid(float* g, int n, cudaStream_t st);
 // dst[0..n) = host[0..n) through kernel parameters (no copy engine involved)
 int launch_set_tstep(float* dst, const float* host, int n, cudaStream_t st);
+int launch_set_io_table(const void** tab, const void* img0, const void* img1, const void* out, cudaStream_t st);
 // layout converters for the op-level entry points
 int launch_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, bool s2d, cudaStream_t st);
 int launch_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, int Cpad, cudaStream_t st);

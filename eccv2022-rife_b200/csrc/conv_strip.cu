@@ -42,8 +42,10 @@ constexpr int S_TR = 16, S_TC = 28;     // output tile (rows 2..17, columns 2..2
 constexpr int NMT_A = 5, NMT_B = 4;     // M-tiles (4 rows each): layer A rows 1..20 (19, 20 unused), layer B rows 2..17
 constexpr int PLANE = SR * SP * 16;     // bytes per 8-channel plane of a window
 constexpr int NSLOT = 4;                // TMEM accumulator slots
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NTHREADS = 64 + 32 * NUM_EPI_WARPS;
+// epilogue warps: C = 32 runs one CTA per SM with 16 (four per SM sub-partition: the epilogue is a long dependent chain
+// -- TMEM load, shuffles, residual, pack -- and needs that many to keep the issue slots busy); C = 16 runs two CTAs per
+// SM with 8 each.  Warps w, w + 4, ... share a TMEM lane quarter; group g = (w - 2) / 4 takes the M-tiles with seq % NG == g.
+template <int C> struct EpiW { static constexpr int value = C == 32 ? 16 : 8; };
 
 struct StripParams {
   int B, H, W, tiles_x, tiles_y, ntiles;
@@ -66,6 +68,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ float lrelu_max(float x) { return fmaxf(x, 0.2f * x); }   // == x >= 0 ? x : 0.2 x
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (true) {
@@ -80,6 +83,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) return;
     if (clock64() - t0 > 4000000000LL) __trap();  // a mis-programmed pipeline traps instead of hanging the GPU
   }
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -186,10 +194,10 @@ __device__ __forceinline__ void epi_row(const StripParams& p, uint32_t tacc, con
         const float4 b1 = *reinterpret_cast<const float4*>(s_beta + 8 * g + 4);
         const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * g2 + i] * be[i] + rr[i]);
+        for (int i = 0; i < 8; ++i) a[i] = lrelu_max(fmaf(v[8 * g2 + i], be[i], rr[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 * g2 + i]);
+        for (int i = 0; i < 8; ++i) a[i] = lrelu_max(v[8 * g2 + i]);
       }
       if constexpr (TO_SMEM) {
         uint4 u = pack8x(a, bf);
@@ -205,9 +213,12 @@ __device__ __forceinline__ void epi_row(const StripParams& p, uint32_t tacc, con
 }
 
 template <int C>
-__global__ void __launch_bounds__(NTHREADS, C == 16 ? 2 : 1)
+__global__ void __launch_bounds__(64 + 32 * EpiW<C>::value, C == 16 ? 2 : 1)
 conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams p) {
   using K = StripCfg<C>;
+  constexpr int NUM_EPI_WARPS = EpiW<C>::value;
+  constexpr int NG = NUM_EPI_WARPS / 4;         // epilogue groups
+  constexpr int NTHREADS = 64 + 32 * NUM_EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full;
   __shared__ __align__(8) uint64_t in_full[2], in_empty[2], mid_full[2], mid_empty[2];
@@ -232,7 +243,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(smem_u32(&tm_full[i]), 1);
-      mbar_init(smem_u32(&tm_empty[i]), NUM_EPI_WARPS / 2);   // the four warps of the group that drains this slot
+      mbar_init(smem_u32(&tm_empty[i]), 4);                   // the four warps of the group that drains this slot
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -284,10 +295,12 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
       const uint64_t b_desc0 = make_desc_noswz(0, (uint32_t)K::N * 16u, 128u);
       mbar_wait(smem_u32(&w_full), 0);
       uint32_t seq = 0;
+      long long t_te = 0, t_in = 0, t_mid = 0;
+      const long long t_begin = clock64();
       auto issue_layer = [&](uint32_t a_buf, uint32_t w_layer, int row_first, int nmt) {
         for (int j = 0; j < nmt; ++j, ++seq) {
           const uint32_t slot = seq & (NSLOT - 1);
-          mbar_wait(smem_u32(&tm_empty[slot]), ((seq >> 2) & 1u) ^ 1u);
+          mbar_wait_t(smem_u32(&tm_empty[slot]), ((seq >> 2) & 1u) ^ 1u, t_te);
           tc_fence_after();
           const uint32_t acc = tmem_base + slot * K::SLOT;
           // window row (row_first + 4j + ky - 1), column 0: 128 consecutive pixels from there on
@@ -308,18 +321,22 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
       for (int k = 0; k <= ntl; ++k) {
         if (k < ntl) {
           const int s = k & 1;
-          mbar_wait(smem_u32(&in_full[s]), ((uint32_t)k >> 1) & 1u);
+          mbar_wait_t(smem_u32(&in_full[s]), ((uint32_t)k >> 1) & 1u, t_in);
           tc_fence_after();
           issue_layer(in_smem + s * K::BUF, w_smem, 1, NMT_A);
           umma_commit(smem_u32(&in_empty[s]));
         }
         if (k >= 1) {
           const int m = (k - 1) & 1;
-          mbar_wait(smem_u32(&mid_full[m]), ((uint32_t)(k - 1) >> 1) & 1u);
+          mbar_wait_t(smem_u32(&mid_full[m]), ((uint32_t)(k - 1) >> 1) & 1u, t_mid);
           tc_fence_after();
           issue_layer(mid_smem + m * K::BUF, w_smem + K::WBYTES, 2, NMT_B);
           umma_commit(smem_u32(&mid_empty[m]));
         }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = t_te; p.dbg[blockIdx.x * 8 + 1] = t_in; p.dbg[blockIdx.x * 8 + 2] = t_mid;
+        p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin;
       }
     }
   } else {
@@ -328,6 +345,8 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
     const int grp = (warp - 2) >> 2;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t seq = 0;
+    long long t_tf = 0, t_me = 0;
+    const long long t_begin = clock64();
     for (int k = 0; k <= ntl; ++k) {
       if (k < ntl) {
         // layer A of tile k: window rows 1..18 -> intermediate buffer k & 1
@@ -338,15 +357,15 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
         const uint32_t ibuf = in_smem + s * K::BUF, mbuf = mid_smem + s * K::BUF;
         bool first = true;
         for (int j = 0; j < NMT_A; ++j, ++seq) {
-          if ((int)(seq & 1u) != grp) continue;
+          if ((int)(seq & (uint32_t)(NG - 1)) != grp) continue;
           if (first) {
             // the intermediate buffer is free (layer B of tile k - 2 has read it); the window is visible to this warp
-            mbar_wait(smem_u32(&mid_empty[s]), (((uint32_t)k >> 1) & 1u) ^ 1u);
+            mbar_wait_t(smem_u32(&mid_empty[s]), (((uint32_t)k >> 1) & 1u) ^ 1u, t_me);
             mbar_wait(smem_u32(&in_full[s]), ((uint32_t)k >> 1) & 1u);
             first = false;
           }
           const uint32_t slot = seq & (NSLOT - 1);
-          mbar_wait(smem_u32(&tm_full[slot]), (seq >> 2) & 1u);
+          mbar_wait_t(smem_u32(&tm_full[slot]), (seq >> 2) & 1u, t_tf);
           tc_fence_after();
           const int row = 1 + 4 * j + q;
           if (row <= SR - 2) {
@@ -374,9 +393,9 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
         const int m = (k - 1) & 1;
         const uint32_t mbuf = mid_smem + m * K::BUF;
         for (int j = 0; j < NMT_B; ++j, ++seq) {
-          if ((int)(seq & 1u) != grp) continue;
+          if ((int)(seq & (uint32_t)(NG - 1)) != grp) continue;
           const uint32_t slot = seq & (NSLOT - 1);
-          mbar_wait(smem_u32(&tm_full[slot]), (seq >> 2) & 1u);
+          mbar_wait_t(smem_u32(&tm_full[slot]), (seq >> 2) & 1u, t_tf);
           tc_fence_after();
           const int row = 2 + 4 * j + q;
           const uint32_t px = (uint32_t)((row * SP + lane) * 16);
@@ -389,6 +408,10 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tm_in, const StripParams 
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&mid_empty[m]));
       }
+    }
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = t_tf; p.dbg[blockIdx.x * 8 + 5] = t_me; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 8 + 7] = ntl;
     }
   }
   tc_fence_before();
@@ -491,14 +514,30 @@ int launch_conv_strip2(const StripPair& L, const ConvIO& io, cudaStream_t st) {
   const int per_sm = L.c == 16 ? 2 : 1;
   int grid = num_sms() * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
+  static const bool debug = getenv("RIFE_HK_DEBUG") != nullptr;
+  if (debug) {
+    cudaMalloc((void**)&p.dbg, (size_t)grid * 64);
+    cudaMemsetAsync(p.dbg, 0, (size_t)grid * 64, st);
+  }
   if (L.c == 16) {
     RIFE_TRY(set_smem_attr((const void*)conv_strip2_kernel<16>, StripCfg<16>::SMEM));
-    RIFE_CUDA_TRY(launch_pdl(conv_strip2_kernel<16>, dim3(grid), dim3(NTHREADS), StripCfg<16>::SMEM, st, tm, p));
+    RIFE_CUDA_TRY(launch_pdl(conv_strip2_kernel<16>, dim3(grid), dim3(64 + 32 * EpiW<16>::value), StripCfg<16>::SMEM, st, tm, p));
   } else {
     RIFE_TRY(set_smem_attr((const void*)conv_strip2_kernel<32>, StripCfg<32>::SMEM));
-    RIFE_CUDA_TRY(launch_pdl(conv_strip2_kernel<32>, dim3(grid), dim3(NTHREADS), StripCfg<32>::SMEM, st, tm, p));
+    RIFE_CUDA_TRY(launch_pdl(conv_strip2_kernel<32>, dim3(grid), dim3(64 + 32 * EpiW<32>::value), StripCfg<32>::SMEM, st, tm, p));
   }
   RIFE_LAUNCH_CHECK();
+  if (debug) {
+    std::vector<long long> h((size_t)grid * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), p.dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    double a[8] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 8 + k] / grid;
+    fprintf(stderr, "[strip] c=%d grid=%d tiles/cta=%.1f | mma: wait tm_empty %.0f, in_full %.0f, mid_full %.0f, total %.0f | epi(w2): wait tm_full %.0f, mid_empty %.0f, total %.0f\n",
+            L.c, grid, a[7], a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
   return RIFE_OK;
 }
 

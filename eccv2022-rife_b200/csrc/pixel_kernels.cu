@@ -226,10 +226,14 @@ template <typename Tio, typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                    T* __restrict__ src_all, T* __restrict__ head_in, int F, int nf0,
                                                    int C, int H, int W, int planar, int write_src, ImgLayout lay,
-                                                   unsigned int* __restrict__ ctrs, int nctrs) {
+                                                   unsigned int* __restrict__ ctrs, int nctrs, const void* const* iot) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
   zero_tile_ctrs(ctrs, nctrs);
+  if (iot) {  // CUDA-graph replay: the frame pointers of this call come from the plan's table (common.cuh: PixelCtx::io_table)
+    img0 = reinterpret_cast<const Tio*>(iot[0]);
+    img1 = reinterpret_cast<const Tio*>(iot[1]);
+  }
   const int W2 = W >> 1, H2 = H >> 1;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nq = (size_t)F * H2 * W2;
@@ -281,10 +285,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const Tio* __restrict__ img0,
 template <typename Tio>
 __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_kernel(const Tio* __restrict__ img0, const Tio* __restrict__ img1,
                                                           __half* __restrict__ head_in, int nf0, int C, int H, int W,
-                                                          unsigned int* __restrict__ ctrs, int nctrs) {
+                                                          unsigned int* __restrict__ ctrs, int nctrs, const void* const* iot) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
   zero_tile_ctrs(ctrs, nctrs);
+  if (iot) {
+    img0 = reinterpret_cast<const Tio*>(iot[0]);
+    img1 = reinterpret_cast<const Tio*>(iot[1]);
+  }
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;  // strip index along x (8 pixels)
   const int y2 = blockIdx.y, fb = blockIdx.z;            // frame index: img0's nf0 frames first, then img1's
@@ -334,10 +342,14 @@ __global__ void __launch_bounds__(256, RIFE_PREP_MINB) prep_planar_u8_kernel(con
                                                                              const uint8_t* __restrict__ img1,
                                                                              __half* __restrict__ head_in, int nf0, int h,
                                                                              int H, int W, unsigned int* __restrict__ ctrs,
-                                                                             int nctrs) {
+                                                                             int nctrs, const void* const* iot) {
   pdl_wait();
   RIFE_PIX_TRIGGER();
   zero_tile_ctrs(ctrs, nctrs);
+  if (iot) {
+    img0 = reinterpret_cast<const uint8_t*>(iot[0]);
+    img1 = reinterpret_cast<const uint8_t*>(iot[1]);
+  }
   const int W8 = W >> 3, H2 = H >> 1, W2 = W >> 1;
   const int xs = blockIdx.x * blockDim.x + threadIdx.x;
   const int y2 = blockIdx.y, fb = blockIdx.z;
@@ -858,9 +870,10 @@ __global__ void __launch_bounds__(256) eval_kernel(LevelsArg L, int nlev, const 
                                                    Tio* __restrict__ omask, Tio* __restrict__ ow0,
                                                    Tio* __restrict__ ow1, Tio* __restrict__ omerged, int B, int C,
                                                    int H, int W, WarpGeom geom, const float* __restrict__ fbuf,
-                                                   int fbuf_levels, ImgLayout lay) {
+                                                   int fbuf_levels, ImgLayout lay, const void* const* iot) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
+  if (iot) omerged = reinterpret_cast<Tio*>(const_cast<void*>(iot[2]));
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= lay.w || y >= lay.h) return;   // outputs are cropped to the caller's frame
@@ -919,9 +932,10 @@ __global__ void __launch_bounds__(256) merge_h_kernel(const __half* __restrict__
                                                       const __half* __restrict__ src1, const float* __restrict__ gridx,
                                                       const float* __restrict__ gridy, const float* __restrict__ fbuf,
                                                       Tio* __restrict__ omerged, int C, int H, int W, WarpGeom geom,
-                                                      ImgLayout lay) {
+                                                      ImgLayout lay, const void* const* iot) {
   pdl_wait();  // inputs are earlier kernels' outputs (see common.cuh: PDL contract)
   RIFE_PIX_TRIGGER();
+  if (iot) omerged = reinterpret_cast<Tio*>(const_cast<void*>(iot[2]));
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= lay.w || y >= lay.h) return;
@@ -1113,9 +1127,9 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
   if (c.planar_head && c.half_act && c.W % 8 == 0 && fh == c.H && fw == c.W && io_dtype != RIFE_U8) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
     if (io_dtype == RIFE_F16)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<__half>, g, dim3(256), 0, st, (const __half*)img0, (const __half*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs, c.io_table));
     else if (io_dtype == RIFE_F32)
-      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
+      RIFE_CUDA_TRY(launch_pdl(prep_planar_kernel<float>, g, dim3(256), 0, st, (const float*)img0, (const float*)img1, (__half*)head_in, c.nf0, c.C, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs, c.io_table));
     else
       RIFE_FAIL(RIFE_ERR_DTYPE, "launch_prep: bad io dtype");
     RIFE_LAUNCH_CHECK();
@@ -1125,7 +1139,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
       ((uintptr_t)img0 % 8) == 0 && ((uintptr_t)img1 % 8) == 0 && ((size_t)fh * fw * 3) % 8 == 0) {
     const dim3 g(nblk((size_t)(c.W / 8), 256), (unsigned)(c.H / 2), (unsigned)c.F);
     RIFE_CUDA_TRY(launch_pdl(prep_planar_u8_kernel, g, dim3(256), 0, st, (const uint8_t*)img0, (const uint8_t*)img1,
-                             (__half*)head_in, c.nf0, fh, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs));
+                             (__half*)head_in, c.nf0, fh, c.H, c.W, c.tile_ctrs, c.n_tile_ctrs, c.io_table));
     RIFE_LAUNCH_CHECK();
     return RIFE_OK;
   }
@@ -1134,7 +1148,7 @@ int launch_prep(const PixelCtx& c, const void* img0, const void* img1, int io_dt
 #define RIFE_PREP(TIO, T)                                                                                        \
   RIFE_CUDA_TRY(launch_pdl(prep_kernel<TIO, T>, grid, dim3(256), 0, st, (const TIO*)img0, (const TIO*)img1,            \
                            (T*)src_all, (T*)head_in, c.F, c.nf0, c.C, c.H, c.W, c.planar_head ? 1 : 0,                \
-                           c.planar_head ? 0 : 1, lay, c.tile_ctrs, c.n_tile_ctrs))
+                           c.planar_head ? 0 : 1, lay, c.tile_ctrs, c.n_tile_ctrs, c.io_table))
   if (io_dtype == RIFE_F32 && !c.half_act) RIFE_PREP(float, float);
   else if (io_dtype == RIFE_F32 && c.half_act) RIFE_PREP(float, __half);
   else if (io_dtype == RIFE_F16 && !c.half_act) RIFE_PREP(__half, float);
@@ -1219,7 +1233,7 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
     const __half* tmp = (const __half*)levels[nlev - 1].ptr;
 #define RIFE_MERGE(TIO, PITCH)                                                                                       \
   RIFE_CUDA_TRY(launch_pdl(merge_h_kernel<TIO, PITCH>, egrid, dim3(256), 0, st, tmp, (const __half*)c.src0,           \
-                           (const __half*)c.src1, c.gridx, c.gridy, fbuf, (TIO*)o.merged, c.C, c.H, c.W, g, lay))
+                           (const __half*)c.src1, c.gridx, c.gridy, fbuf, (TIO*)o.merged, c.C, c.H, c.W, g, lay, c.io_table))
     if (levels[nlev - 1].pitch == 8) {
       if (io_dtype == RIFE_F32) RIFE_MERGE(float, 8);
       else if (io_dtype == RIFE_F16) RIFE_MERGE(__half, 8);
@@ -1238,7 +1252,7 @@ int launch_eval(const PixelCtx& c, int nlev, const TmpLevel* levels, const EvalO
 #define RIFE_EVAL(T, TIO)                                                                                         \
   RIFE_CUDA_TRY(launch_pdl(eval_kernel<T, T, TIO>, egrid, dim3(256), 0, st, L, nlev, (const T*)c.src0,            \
                            (const T*)c.src1, c.gridx, c.gridy, (TIO*)o.flow, (TIO*)o.mask, (TIO*)o.warped0,       \
-                           (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, fbuf_levels, lay))
+                           (TIO*)o.warped1, (TIO*)o.merged, c.B, c.C, c.H, c.W, g, fbuf, fbuf_levels, lay, c.io_table))
   if (!c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(float, float);
   else if (!c.half_act && io_dtype == RIFE_F16) RIFE_EVAL(float, __half);
   else if (c.half_act && io_dtype == RIFE_F32) RIFE_EVAL(__half, float);
@@ -1265,6 +1279,17 @@ int launch_set_tstep(float* dst, const float* host, int n, cudaStream_t st) {
     for (int i = 0; i < m; ++i) a.v[i] = host[o + i];
     set_tstep_kernel<<<1, 256, 0, st>>>(a, dst + o, m);
   }
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+// the frame pointers of one call, written through kernel parameters into the plan's table (read by the first / last
+// kernel of a replayed CUDA graph)
+__global__ void set_io_table_kernel(const void** tab, const void* a, const void* b, const void* c) {
+  if (threadIdx.x == 0) { tab[0] = a; tab[1] = b; tab[2] = c; }
+}
+int launch_set_io_table(const void** tab, const void* img0, const void* img1, const void* out, cudaStream_t st) {
+  set_io_table_kernel<<<1, 32, 0, st>>>(tab, img0, img1, out);
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }

@@ -9,6 +9,7 @@ pipeline with hand-written sm_100a kernels (see csrc/ and DESIGN.md).  There is 
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 
 import torch
@@ -156,35 +157,63 @@ class IFNet(nn.Module):
         """b frame pairs x nt timesteps per pair; seq: the pairs are the b consecutive pairs of one run of b+1 frames."""
         lib = _lib.load()
         wh = self._get_weights(device, prec)
-        key = ((device.index, prec), b, c, h, w, float(scale), slot, nt, bool(seq))
-        pl = self._plans.get(key)
+        scale = tuple(float(x) for x in scale) if isinstance(scale, (tuple, list)) else float(scale)
+        key = ((device.index, prec), b, c, h, w, scale, slot, nt, bool(seq))
+        pl = self._plans.pop(key, None)
         if pl is not None:
+            self._plans[key] = pl                  # most recently used goes last
             return pl
         with torch.cuda.device(device):
-            nbytes = lib.rife_plan_workspace_bytes_ex(b, nt, int(seq), c, h, w, float(scale), prec)
+            if isinstance(scale, tuple):   # arbitrary scale_list (IFNet.forward)
+                sl = (C.c_float * 5)(*scale)
+                nbytes = lib.rife_plan_workspace_bytes_list(b, nt, int(seq), c, h, w, sl, prec)
+            else:
+                nbytes = lib.rife_plan_workspace_bytes_ex(b, nt, int(seq), c, h, w, float(scale), prec)
             if nbytes == 0:
                 _lib.check(-2)
             pl = _Plan()
             pl.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
             gx, gy, _, _ = base_grids(h, w, device)
             hd = C.c_void_p()
-            _lib.check(lib.rife_plan_create_ex(C.byref(hd), wh, b, nt, int(seq), c, h, w, float(scale),
-                                               pl.workspace.data_ptr(), nbytes, gx.data_ptr(), gy.data_ptr()))
+            if isinstance(scale, tuple):
+                _lib.check(lib.rife_plan_create_list(C.byref(hd), wh, b, nt, int(seq), c, h, w, sl,
+                                                     pl.workspace.data_ptr(), nbytes, gx.data_ptr(), gy.data_ptr()))
+            else:
+                _lib.check(lib.rife_plan_create_ex(C.byref(hd), wh, b, nt, int(seq), c, h, w, float(scale),
+                                                   pl.workspace.data_ptr(), nbytes, gx.data_ptr(), gy.data_ptr()))
             pl.handle = hd
         self._plans[key] = pl
+        self._evict_plans(device)
         return pl
+
+    def _evict_plans(self, device):
+        """Least-recently-used eviction: a plan owns a workspace of ~0.5 GB per 1080p pair, and callers such as
+        interpolate_recursive create one per batch size.  At most RIFE_B200_MAX_PLANS (default 8) plans stay alive;
+        an evicted plan is destroyed after the device has drained (its kernels may still be running)."""
+        limit = max(1, int(os.environ.get("RIFE_B200_MAX_PLANS", "8")))
+        if len(self._plans) <= limit:
+            return
+        torch.cuda.synchronize(device)
+        lib = _lib.load()
+        while len(self._plans) > limit:
+            k = next(iter(self._plans))            # dicts keep insertion order; _get_plan re-inserts on every hit
+            lib.rife_plan_destroy(self._plans.pop(k).handle)
 
     @staticmethod
     def _scale_from_list(scale_list):
         if len(scale_list) < 5:
             raise ValueError("IFNet.forward indexes scale_list[0..4] (IFNet_HDv3.py:139-148): pass 5 entries")
         s4 = float(scale_list[4])
-        want = [16 * s4, 8 * s4, 4 * s4, 2 * s4, s4]
-        if [float(s) for s in scale_list[:5]] != want or s4 not in (0.25, 0.5, 1.0, 2.0, 4.0):
-            raise NotImplementedError(
-                f"eccv2022-rife_b200 builds the scale_list=[16,8,4,2,1]/scale pyramid of RIFE_HDv3.py:58 with scale in "
-                f"{{0.25, 0.5, 1, 2, 4}} (inference_video.py:92); got {list(scale_list)}")
-        return 1.0 / s4
+        sl = [float(s) for s in scale_list[:5]]
+        if sl == [16 * s4, 8 * s4, 4 * s4, 2 * s4, s4] and s4 in (0.25, 0.5, 1.0, 2.0, 4.0):
+            return 1.0 / s4                        # the pyramid of RIFE_HDv3.py:58: fast-path kernels
+        for s in sl:
+            m, _ = math.frexp(s)
+            if not (0.25 <= s <= 64.0) or m != 0.5:
+                raise NotImplementedError(
+                    f"eccv2022-rife_b200 takes scale_list entries that are powers of two in [1/4, 64] (every list "
+                    f"[16,8,4,2,1]/scale of RIFE_HDv3.py:58 / inference_video.py:92 is); got {list(scale_list)}")
+        return tuple(sl)                           # any other list: generic pixel kernels (rife_plan_create_list)
 
     @staticmethod
     def _timesteps(timestep, b):
@@ -213,7 +242,10 @@ class IFNet(nn.Module):
     def padded_size(h, w, scale):
         """The network needs H, W multiples of 64/scale; the reference's callers zero-pad right/bottom and
         crop the result (inference_img.py:62-67,111).  Here the first kernel pads and the last one crops."""
-        m = int(round(64 / float(scale)))
+        if isinstance(scale, (tuple, list)):
+            m = int(max(4.0, 4.0 * max(scale)))
+        else:
+            m = int(round(64 / float(scale)))
         return (h + m - 1) // m * m, (w + m - 1) // m * m
 
     def plan_for(self, device, prec, b, c, h, w, scale, slot=0, pad=True, nt=1, seq=False):

@@ -2,7 +2,8 @@
 
 The reference has no multi-GPU inference; BASELINE.json's north_star shards independent frame pairs
 across the GPUs of one box.  Each rank gets a contiguous range of pair indices; results are concatenated in index
-order.  torch.distributed is only used for the final (optional) ordered gather and for timing barriers."""
+order.  torch.distributed is only used for the final (optional) ordered gather (one all_gather of the result tensors) and
+for timing barriers."""
 from __future__ import annotations
 
 import torch
@@ -57,10 +58,32 @@ def run_sharded(infer, frames, timesteps=(0.5,), gather=True):
             local.append(infer(a, b, t))
     if not gather or world == 1:
         return local
-    payload = [x.cpu() for x in local]
-    buckets = [None] * world
-    dist.all_gather_object(buckets, payload)
+    # ordered gather as ONE tensor collective on the outputs' own device (NCCL over NVLink for CUDA tensors, gloo for
+    # CPU tensors): every rank contributes a (max_count, ...) block, padded by at most one item, then trims by the
+    # ranks' known counts.  No pickling, no host round trip for device tensors.
+    per_pair = len(timesteps)
+    counts = [(shard_range(n_pairs, r, world)[1] - shard_range(n_pairs, r, world)[0]) * per_pair for r in range(world)]
+    cmax = max(counts)
+    if local:
+        item = local[0]
+        shape, dtype, device = tuple(item.shape), item.dtype, item.device
+    else:   # a rank without pairs still takes part in the collective: learn the item shape from rank 0
+        shape = dtype = device = None
+    meta = [None]
+    if rank == 0:
+        meta = [(shape, dtype)]
+    dist.broadcast_object_list(meta, src=0)
+    shape, dtype = meta[0]
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    if dist.get_backend() != "nccl":
+        device = torch.device("cpu")   # gloo: the collective runs on host tensors
+    block = torch.zeros((cmax,) + shape, dtype=dtype, device=device)
+    for k, x in enumerate(local):
+        block[k].copy_(x)
+    blocks = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(blocks, block)
     out = []
-    for bkt in buckets:
-        out.extend(bkt)
+    for r in range(world):
+        out.extend(blocks[r][k] for k in range(counts[r]))
     return out

@@ -97,6 +97,14 @@ size_t rife_plan_workspace_bytes_ex(int pairs, int timesteps, int sequence, int 
 int rife_plan_create_ex(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C,
                         int H, int W, float scale, void* workspace, size_t workspace_bytes,
                         const float* gridx_host, const float* gridy_host);
+/* IFNet.forward with an arbitrary scale_list (train_log/IFNet_HDv3.py:119,139-148 accepts any five numbers): entry i is
+ * the down-scaling factor of block i, here a power of two in [1/4, 64]; H and W must be multiples of 4 * entry for every
+ * block.  Lists other than the halving pyramid [16,8,4,2,1]/scale run on the generic (level-by-level) pixel kernels. */
+size_t rife_plan_workspace_bytes_list(int pairs, int timesteps, int sequence, int C, int H, int W,
+                                      const float* scale_list5, int precision);
+int rife_plan_create_list(rife_plan** out, const rife_weights* w, int pairs, int timesteps, int sequence, int C,
+                          int H, int W, const float* scale_list5, void* workspace, size_t workspace_bytes,
+                          const float* gridx_host, const float* gridy_host);
 int rife_plan_destroy(rife_plan* p);
 /* Frame size seen by the caller, (h, w) <= the plan's padded (H, W) (default: H, W).  Inputs are then (B,C,h,w) /
  * (B,h,w,C) tensors, zero-padded on the right / bottom inside the first kernel and every output is cropped back to

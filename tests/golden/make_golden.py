@@ -164,6 +164,21 @@ def case_scale_up():
     save("scale_up_cases", **arrs)
 
 
+def case_scale_list():
+    """IFNet.forward with scale lists that are NOT the halving pyramid of RIFE_HDv3.py:58 (IFNet_HDv3.py:119,139-148 takes
+    any five numbers): repeated levels, a coarse-to-fine-to-coarse order, and a block above full resolution."""
+    arrs = {}
+    m = build_model(1234, AMP)
+    img0, img1 = rand_frames(81, 1, 3, 64, 96, smooth=True)
+    arrs["img0"], arrs["img1"] = f32(img0), f32(img1)
+    for name, sl in (("a", [8, 8, 4, 2, 1]), ("b", [4, 4, 2, 2, 1]), ("c", [2, 4, 8, 2, 1]), ("d", [8, 4, 2, 2, 0.5])):
+        fl, mk, mg = m.flownet(torch.cat((img0, img1), 1), 0.4, sl)
+        arrs[name + "_list"] = np.asarray(sl, np.float32)
+        arrs[name + "_flow4"], arrs[name + "_flow1"] = f32(fl[4]), f32(fl[1])
+        arrs[name + "_mask"], arrs[name + "_merged"] = f32(mk), f32(mg[4])
+    save("scale_list_cases", **arrs)
+
+
 def case_warp():
     """model/warplayer.py:8-22 on random data, small and large flows, C=3 and C=4."""
     arrs = {}
@@ -402,6 +417,10 @@ def case_eccv_ref_fp16():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eccv":
         case_eccv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "scale_list":
+        with torch.no_grad():
+            case_scale_list()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "stress":
         with torch.no_grad():

@@ -150,3 +150,15 @@ def test_stress_cases_torch_oracle(pkg):
     m = stress_model(pkg, "bigflow", "fp32")
     out = T.model_inference(torch_state_dict(m), torch.from_numpy(g["f_img0"]), torch.from_numpy(g["f_img1"]), 0.5).numpy()
     assert np.abs(out - g["f_out"]).max() < 1e-4
+
+
+def test_arbitrary_scale_lists_torch_oracle(pkg):
+    """scale lists other than the halving pyramid (tests/golden/make_golden.py:case_scale_list)."""
+    g = load_golden("scale_list_cases")
+    m = seeded_model(pkg, AMP)
+    x = torch.cat((torch.from_numpy(g["img0"]), torch.from_numpy(g["img1"])), 1)
+    for name in "abcd":
+        sl = [float(v) for v in g[name + "_list"]]
+        flows, mask, merged = T.ifnet_forward(torch_state_dict(m), x, 0.4, sl)
+        assert np.abs(flows[4].numpy() - g[name + "_flow4"]).max() < 1e-4, name
+        assert np.abs(merged[4].numpy() - g[name + "_merged"]).max() < 1e-5, name
