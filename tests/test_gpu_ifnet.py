@@ -626,3 +626,46 @@ def test_arbitrary_scale_list(pkg):
         assert np.abs(merged[4].cpu().numpy() - g[name + "_merged"]).max() < TOL32, name
         _, _, merged = n16(x.half(), 0.4, sl)
         _check16(merged[4].float().cpu().numpy(), g[name + "_merged"], "scale_list " + name)
+
+
+def test_guard_bands_around_workspace_and_output(pkg):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_closed.txt), so out-of-bounds WRITES are hunted
+    with canaries instead: the plan's workspace and the output frame are carved out of larger allocations whose guard bands
+    (1 MiB each side, pattern 0xA5) must survive inference at ragged shapes (tiles that overhang the image on every edge),
+    in all three precisions, through the plain path and the CUDA-graph replay.  The result must also equal the normal
+    (unguarded) call bit for bit."""
+    import ctypes as C
+    lib = pkg._lib.load()
+    GUARD = 1 << 20
+    g = torch.Generator().manual_seed(44)
+    for prec, pname in ((pkg._lib.PRECISION_FP16, "fp16"), (pkg._lib.PRECISION_BF16, "bf16"), (pkg._lib.PRECISION_FP32, "fp32")):
+        m = seeded_model(pkg, AMP, pname)
+        net = m.flownet
+        dev = torch.device(DEV)
+        wh = net._get_weights(dev, prec)
+        for (b, h, w) in ((1, 64, 192), (3, 192, 320), (2, 320, 64)):
+            dt = torch.float32 if pname == "fp32" else torch.float16
+            a = torch.rand(b, 3, h, w, generator=g).to(DEV).to(dt)
+            c = torch.rand(b, 3, h, w, generator=g).to(DEV).to(dt)
+            want = m.inference(a, c, 0.4)
+            nbytes = lib.rife_plan_workspace_bytes(b, 3, h, w, 1.0, prec)
+            assert nbytes > 0
+            big = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+            off = GUARD + (-(big.data_ptr() + GUARD)) % 1024
+            out_big = torch.full((want.numel() * want.element_size() + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+            ooff = GUARD + (-(out_big.data_ptr() + GUARD)) % 256
+            plan = C.c_void_p()
+            pkg._lib.check(lib.rife_plan_create(C.byref(plan), wh, b, 3, h, w, 1.0, big.data_ptr() + off, nbytes, None, None))
+            ts = (C.c_float * b)(*([0.4] * b))
+            io = pkg._lib.RIFE_F32 if pname == "fp32" else pkg._lib.RIFE_F16
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(3):        # plain, graph capture + replay, replay
+                pkg._lib.check(lib.rife_inference(plan, a.data_ptr(), c.data_ptr(), ts, out_big.data_ptr() + ooff, io, st))
+            torch.cuda.synchronize()
+            lib.rife_plan_destroy(plan)
+            nout = want.numel() * want.element_size()
+            got = out_big[ooff:ooff + nout].view(want.dtype).view(want.shape)
+            # the library's own linspace (gridx/gridy = NULL) may differ from torch's by an ulp: compare within the mode's bar
+            assert (got.float() - want.float()).abs().max() < (1e-4 if pname == "fp32" else 2e-3), (pname, b, h, w)
+            for name, t, lo, n in (("workspace", big, off, nbytes), ("output", out_big, ooff, nout)):
+                assert bool((t[:lo] == 0xA5).all()) and bool((t[lo + n:] == 0xA5).all()), (name, pname, b, h, w)
