@@ -221,11 +221,20 @@ class IFNet(nn.Module):
         (flow_list[3], sigmoid(mask), merged[3], None, None, 0).  `timestep` is ignored by this network; the IFNet_m
         subclass feeds it to every block as a constant plane (float, or a (B,1,1,1) tensor) and honours `returnflow`
         (model/IFNet_m.py:63-64,104-105)."""
+        return self._run(x, None, scale, timestep, returnflow)
+
+    def _run(self, x, img1, scale=[4, 2, 1], timestep=0.5, returnflow=False):
+        """`img1` None: `x` is the reference's (B, 6, H, W) cat(img0, img1); else `x` = img0 and `img1` two (B, 3, H, W)
+        frames, packed straight into the working tensor (the `torch.cat` of model/RIFE.py:59 never happens)."""
+        if img1 is not None:
+            if img1.shape != x.shape or img1.dtype != x.dtype or img1.device != x.device or x.shape[1] != 3:
+                raise ValueError("img0 and img1 must be (B, 3, H, W) tensors of one dtype on one device")
+            img1 = img1.contiguous()
         if not x.is_cuda:
             raise RuntimeError("eccv2022-rife_b200: CUDA tensors required -- the B200 hot path has no CPU fallback")
         if x.dtype not in (torch.float32, torch.float16):
             raise TypeError("float32 or float16 frames required")
-        if x.shape[1] != 6:
+        if img1 is None and x.shape[1] != 6:
             raise NotImplementedError("training branch (ground truth appended to x, model/IFNet.py:66,88-97) is out of scope")
         s3 = [float(v) for v in scale[:3]]
         if any(v not in (1.0, 2.0, 4.0, 8.0, 16.0) for v in s3):
@@ -314,7 +323,11 @@ class IFNet(nn.Module):
             # full-resolution fp32 working tensor in Unet.down0's cat order (model/refine.py:73):
             # [img0 0:3 | img1 3:6 | warped0 6:9 | warped1 9:12 | mask 12 | flow 13:17 | pad]
             full = z(H, W, 24, f32)
-            chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), _dt(full), B, 6, H, W, 24, 0, st))
+            if img1 is None:
+                chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), _dt(full), B, 6, H, W, 24, 0, st))
+            else:
+                chk(lib.rife_nhwc_from_nchw(x.data_ptr(), io, full.data_ptr(), _dt(full), B, 3, H, W, 24, 0, st))
+                chk(lib.rife_nhwc_from_nchw(img1.data_ptr(), io, full.data_ptr(), _dt(full), B, 3, H, W, 24, 3, st))
             flow_list, merged, mask_sig = [], [], None
             out_dt = x.dtype
             for i in range(3):                                                        # model/IFNet.py:74-86
@@ -470,9 +483,9 @@ class Model:
     def inference(self, img0, img1, scale=1, scale_list=[4, 2, 1], TTA=False, timestep=0.5):
         """model/RIFE.py:56-65.  (The reference rescales its default `scale_list` argument in place; here a copy is used.)"""
         sl = [scale_list[i] * 1.0 / scale for i in range(3)]
-        imgs = torch.cat((img0, img1), 1)
-        merged = self.flownet(imgs, sl, timestep=timestep)[2]
+        merged = self.flownet._run(img0, img1, sl, timestep)[2]      # both frames packed by the library: no torch.cat
         if not TTA:
             return merged[2]
-        merged2 = self.flownet(imgs.flip(2).flip(3), sl, timestep=timestep)[2]
+        # test-time augmentation (model/RIFE.py:61-65): the same pair flipped in both axes, results averaged
+        merged2 = self.flownet._run(img0.flip(2).flip(3), img1.flip(2).flip(3), sl, timestep)[2]
         return (merged[2] + merged2[2].flip(2).flip(3)) / 2

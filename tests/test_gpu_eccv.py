@@ -48,6 +48,10 @@ def test_eccv_batch_and_tta(pkg):
     assert np.abs(full.cpu().numpy() - ref).max() < 1e-4
     tta = m.inference(a, b, TTA=True)
     assert tta.shape == full.shape and float(tta.min()) >= 0 and float(tta.max()) <= 1
+    # TTA parity (model/RIFE.py:61-65): mean of the plain result and the un-flipped result of the doubly flipped pair
+    ac, bc = a.cpu(), b.cpu()
+    ref2 = T.eccv_model_inference(sd, ac.flip(2).flip(3), bc.flip(2).flip(3)).flip(2).flip(3).numpy()
+    assert np.abs(tta.cpu().numpy() - (ref + ref2) / 2).max() < 1e-4
     with pytest.raises(RuntimeError):
         m.inference(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))               # CPU tensors
     with pytest.raises(RuntimeError, match="multiples of"):
@@ -151,3 +155,25 @@ def test_eccv_2r_variant(pkg):
     assert np.abs(o16 - g["a_merged2"]).max() < FP16_MAX_ABS and _psnr(o16, g["a_merged2"]) > FP16_MIN_PSNR
     with pytest.raises(RuntimeError, match="multiples of 8"):
         net(torch.zeros(1, 6, 36, 64, device=DEV), [4, 2, 1])
+
+
+def test_eccv_config5_batch64(pkg):
+    """BASELINE config 5 at its stated size: a Vimeo90K-shape batch of 64 pairs of 256x448 (benchmark/Vimeo90K.py) through
+    model/RIFE.py's Model.inference, against the torch-CPU restatement of the reference on the same seeded weights
+    (default init, lastconv x4): fp32 <= 1e-4; fp16 inside the reduced-precision bar; every batch item equals the same
+    pair run alone."""
+    m = seeded_eccv(pkg)
+    g = torch.Generator().manual_seed(64)
+    lo = torch.rand(64, 3, 256 // 8 + 2, 448 // 8 + 2, generator=g)
+    big = torch.nn.functional.interpolate(lo, size=(256 + 16, 448 + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+    a, b = big[:, :, 8:8 + 256, 8:8 + 448].contiguous(), big[:, :, 5:5 + 256, 11:11 + 448].contiguous()
+    sd = {k: v.detach().cpu().float() for k, v in m.flownet.state_dict().items()}
+    ref = T.eccv_model_inference(sd, a, b).numpy()
+    out = m.inference(a.to(DEV), b.to(DEV))
+    assert out.shape == (64, 3, 256, 448)
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
+    for i in (0, 31, 63):
+        assert torch.equal(out[i:i + 1], m.inference(a[i:i + 1].to(DEV), b[i:i + 1].to(DEV)))
+    o16 = m.inference(a.to(DEV).half(), b.to(DEV).half()).float().cpu().numpy()
+    assert np.isfinite(o16).all()
+    assert np.abs(o16 - ref).max() < FP16_MAX_ABS and _psnr(o16, ref) > FP16_MIN_PSNR
