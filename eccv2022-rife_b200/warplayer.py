@@ -9,8 +9,13 @@ _grid_cache = {}
 
 
 def base_grids(h, w, device):
-    """torch.linspace(-1, 1, W) / (-1, 1, H) exactly as model/warplayer.py:11-14 builds them on the CPU
-    (float32), uploaded once per (device, H, W).  Returns (host_x, host_y, dev_x, dev_y)."""
+    """The base grids torch.linspace(-1, 1, W) / (-1, 1, H) of model/warplayer.py:11-14, computed with ATen's CPU
+    linspace kernel (float32) and uploaded once per (device, H, W).  The reference evaluates the same expression on its
+    module-level `device`, i.e. with the CUDA linspace kernel when a GPU is present; the two kernels may differ by one
+    ulp at some entries (as ATen's vectorised CPU kernel differs from the scalar formula), which
+    moves a warped pixel by < 1e-5.  The goldens are recorded from the reference on CPU, so the CPU grid is what is
+    pinned; tests/test_gpu_ops.py::test_base_grid_vs_cuda_linspace bounds the difference to the CUDA kernel.
+    Returns (host_x, host_y, dev_x, dev_y)."""
     k = (str(device), h, w)
     if k not in _grid_cache:
         gx = torch.linspace(-1.0, 1.0, w, dtype=torch.float32)

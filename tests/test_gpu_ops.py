@@ -224,3 +224,26 @@ def test_conv_transpose_bf16_tcgen05(pkg, ci):
                                                 52, 1, 2, _stream()))
     ref = O.pixel_shuffle2(O.conv_transpose2d_k4s2p1(x, wt, b))
     assert np.abs(y.cpu().numpy() - ref).max() < 4e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_base_grid_vs_cuda_linspace(pkg):
+    """model/warplayer.py:11-14 builds its base grid on the module-level device -- on a GPU box with ATen's CUDA linspace.
+    This package pins the CPU kernel's values (the goldens are CPU recordings); the two differ by at most one ulp, and a
+    warp with either grid by < 1e-5 on white noise."""
+    from importlib import import_module
+    wl = import_module("eccv2022-rife_b200.warplayer")
+    rng = np.random.default_rng(3)
+    for h, w in ((256, 448), (1088, 1920)):
+        gx, gy, dx, dy = wl.base_grids(h, w, torch.device(DEV))
+        cx, cy = torch.linspace(-1.0, 1.0, w, device=DEV), torch.linspace(-1.0, 1.0, h, device=DEV)
+        assert float((dx - cx).abs().max()) <= 1.2e-7 and float((dy - cy).abs().max()) <= 1.2e-7
+    x = torch.from_numpy(rng.random((1, 3, 256, 448), dtype=np.float32)).to(DEV)
+    fl = torch.from_numpy((rng.random((1, 2, 256, 448), dtype=np.float32) * 2 - 1) * 20).to(DEV)
+    ours = wl.warp(x, fl)
+    gxx = torch.linspace(-1.0, 1.0, 448, device=DEV).view(1, 1, 1, 448).expand(1, -1, 256, -1)
+    gyy = torch.linspace(-1.0, 1.0, 256, device=DEV).view(1, 1, 256, 1).expand(1, -1, -1, 448)
+    grid = torch.cat((gxx, gyy), 1)
+    flow_n = torch.cat((fl[:, 0:1] / ((448 - 1.0) / 2.0), fl[:, 1:2] / ((256 - 1.0) / 2.0)), 1)
+    ref = torch.nn.functional.grid_sample(x, (grid + flow_n).permute(0, 2, 3, 1), mode="bilinear", padding_mode="border",
+                                          align_corners=True)       # the reference's warp, evaluated by ATen on the GPU
+    assert float((ours - ref).abs().max()) < 1e-5

@@ -6,7 +6,9 @@ import sys
 
 path, mode = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "hdv3")
 op = gzip.open if path.endswith(".gz") else open
-rows = list(csv.reader(op(path, "rt")))
+lines = op(path, "rt").read().splitlines()
+start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))   # skip ncu's ==PROF== preamble of --log-file dumps
+rows = list(csv.reader(lines[start:]))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
 
