@@ -622,13 +622,15 @@ static bool narrow_off() {
   return off;
 }
 
-static int chain_min_c() {
+static int chain_min_c(const rife_plan* p) {
   // RIFE_HK_CHAIN=c: the 8 ResConv layers of every block with >= c channels run as ONE cooperative launch with grid
-  // barriers (conv_halo.cu).  Off by default: measured on B200 at 12 x 1080p it shortens the ResConv stages by 8-20 %
-  // under per-stage event timing but the free-running pipeline gets 0.5 % slower -- programmatic dependent launch already
-  // hides most of a kernel boundary, and a cooperative grid has to wait for the previous kernel to drain completely.
-  static const int v = getenv("RIFE_HK_CHAIN") && atoi(getenv("RIFE_HK_CHAIN")) > 0 ? atoi(getenv("RIFE_HK_CHAIN")) : 1 << 30;
-  return v;
+  // barriers (conv_halo.cu).  Off by default, at every batch size -- measured on B200: 16 x 1080p pairs 2542 vs 2611
+  // frames/s; one 1080p pair 0.895 vs 0.877 ms, one 448x256 pair 0.54 vs 0.50 ms (programmatic dependent launch already
+  // hides most of a kernel boundary, a cooperative grid has to wait for the previous kernel to drain completely, and a
+  // grid-wide barrier costs about what a boundary does).  The barrier re-arms itself, so the chain is CUDA-graph safe.
+  (void)p;
+  static const int env = getenv("RIFE_HK_CHAIN") ? atoi(getenv("RIFE_HK_CHAIN")) : 0;
+  return env > 0 ? env : 1 << 30;
 }
 
 static int default_chunk_pairs() {
@@ -785,17 +787,19 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     void* cur = p->at(L.act_a);
     void* nxt = p->at(L.act_b);
     bool chained = false;
-    if (hk_tail && c_ >= chain_min_c()) {
+    if (hk_tail && c_ >= chain_min_c(p)) {
       // ResConv x8 (IFNet_HDv3.py:63-72) as ONE cooperative launch with grid barriers between the layers; the result
       // of the 8th layer lands in act_a again
       const HaloLayer* ls[8];
       for (int j = 0; j < 8; ++j) ls[j] = &w->blk[i].res[j].hk;
       io.in = cur; io.res = cur; io.out = nxt; io.epi = EPI_RES; io.out_c = c_;
+      io.in_bf16 = io.out_bf16 = w->blk[i].res[0].in_bf16 ? 1 : 0;
       int rc;
       {
         StageTimer _t(p, st, bn + ".res");
         rc = launch_conv_halo_chain(ls, 8, io, (unsigned int*)p->at(L.sync), &p->sync_host, st);
       }
+      io.in_bf16 = io.out_bf16 = 0;
       if (rc < 0) return rc;
       chained = rc == 0;   // 1: this shape cannot be chained (no instantiation / not co-resident)
     }

@@ -54,8 +54,10 @@ struct HaloParams {
   const float* bias_l[8];
   const float* beta_l[8];
   __half* out_l[2];        // destination of even / odd layers
-  unsigned int* sync;      // grid barrier counter: monotonic across launches (never reset)
-  unsigned int sync_base;  // its value when this launch starts
+  unsigned int* sync;      // grid barrier: sync[0] arrival counter, sync[1] finished-CTA counter; both zero when a launch
+                           // starts and again when it ends (the last CTA to finish resets them), so a launch carries no
+                           // host-side state and can be replayed from a CUDA graph
+  unsigned int sync_base;  // always 0 (kept for the wait arithmetic)
   unsigned int* tile_ctr;  // dynamic tile scheduling: zero-initialised counter of this launch (null: static round robin)
   int pdl_trig;    // launch_dependents: 0 implicit at CTA exit (default; measured best), 1 after the prologue, 2 after the last MMA
   long long* dbg;  // RIFE_HK_DEBUG=1: per-CTA role timers (8 x int64), else null
@@ -834,6 +836,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }
+  if (p.nlayers > 1 && threadIdx.x == 0) {
+    // chain: every CTA that gets here has passed all of its barrier waits; the last one to finish re-arms the counters
+    __threadfence();
+    const unsigned int d = atomicAdd(p.sync + 1, 1u);
+    if (d == gridDim.x - 1) {
+      p.sync[0] = 0u;
+      p.sync[1] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------- layout converters (tests)
@@ -1164,7 +1176,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
     p.out_l[0] = (__half*)io.out;
     p.out_l[1] = (__half*)const_cast<void*>(io.in);
     p.sync = chain->sync;
-    p.sync_base = *chain->sync_host;
+    p.sync_base = 0;
   }
   const bool coop = chain != nullptr;
   int grid = num_sms() * per_sm;
@@ -1215,7 +1227,6 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
 #undef RIFE_HK_STREAM
   if (!done && L.stream && coop) return 1;
   if (!done && L.stream) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no streamed instantiation for this layer / epilogue");
-  if (done && chain) *chain->sync_host += (unsigned int)(chain->n - 1) * (unsigned int)grid;
   if (!done && p.epi == EPI_PS8) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "conv_halo: no EPI_PS8 instantiation for this layer");
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));

@@ -33,7 +33,7 @@ int halo_pack_weights(const HostLayer& h, int ps_layout, std::vector<__half>* pa
 int launch_conv_halo(const HaloLayer& L, const ConvIO& io, cudaStream_t st);
 // n (2..8) ResConv layers of one shape in ONE cooperative launch: layer l reads io.in (l even) / io.out (l odd) and writes
 // the other tensor; a grid-wide barrier replaces the kernel boundary.  `sync`: one device uint32, zero-initialised once
-// and monotonic from then on; `sync_host`: the caller's mirror of its value after all launches enqueued so far.
+// (two counters; every launch leaves them zero again, so launches can be replayed from a CUDA graph); `sync_host` is unused.
 // Returns 1 (nothing launched) when the shape has no compile-time instantiation or its grid is not co-resident.
 int launch_conv_halo_chain(const HaloLayer* const* layers, int n, const ConvIO& io, unsigned int* sync,
                            unsigned int* sync_host, cudaStream_t st);

@@ -13,7 +13,7 @@ def base_grids(h, w, device):
     linspace kernel (float32) and uploaded once per (device, H, W).  The reference evaluates the same expression on its
     module-level `device`, i.e. with the CUDA linspace kernel when a GPU is present; the two kernels may differ by one
     ulp at some entries (as ATen's vectorised CPU kernel differs from the scalar formula), which
-    moves a warped pixel by < 1e-5.  The goldens are recorded from the reference on CPU, so the CPU grid is what is
+    moves a warped pixel by ~1e-5.  The goldens are recorded from the reference on CPU, so the CPU grid is what is
     pinned; tests/test_gpu_ops.py::test_base_grid_vs_cuda_linspace bounds the difference to the CUDA kernel.
     Returns (host_x, host_y, dev_x, dev_y)."""
     k = (str(device), h, w)
