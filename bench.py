@@ -69,6 +69,10 @@ def stage_model(P, H, W, esz, io_esz, nframes):
                 gather += samp * 16 * (2 if s == 1 else 1)       # fp32 flow buffer: written at s = 2, read + rewritten at s = 1
         m[f"b{i}.input"] = (gather + n * 32 * esz, 0.0)
         m[f"b{i}.conv0.0"] = (n * 32 * esz + n / 4 * (c // 2) * esz, 2.0 * n / 4 * 9 * p_in * (c // 2))
+        if s == 1:
+            # gather fused into conv0.0 (conv_gather.cu): the block input never reaches HBM; the flow buffer is read and a
+            # second one written
+            m[f"b{i}.input+conv0.0"] = (gather + n / 4 * (c // 2) * esz, 2.0 * n / 4 * 9 * p_in * (c // 2))
         m[f"b{i}.conv0.1"] = (n / 4 * (c // 2) * esz + n / 16 * c * esz, 2.0 * n / 16 * 9 * (c // 2) * c)
         # 8 ResConv layers; the fused pairs of block 4 (conv_strip.cu) read and write HBM once per two layers
         m[f"b{i}.res"] = (8 * 2 * n / 16 * c * esz, 8 * 2.0 * n / 16 * 9 * c * c)

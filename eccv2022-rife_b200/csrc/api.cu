@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_gather.cuh"
 #include "conv_halo.cuh"
 #include "conv_strip.cuh"
 #include "conv_umma.cuh"
@@ -346,7 +347,7 @@ int rife_weights_destroy(rife_weights* w) {
 constexpr int kTileCtrs = 1024;
 
 struct PlanLayout {
-  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, gridx, gridy, tstep, sync, ctrs, io_tab, stage_in0, stage_in1,
+  size_t src, head_in, head_a, head_b, xin, xfull, c0, act_a, act_b, tmp[5], fbuf, fbuf2, gridx, gridy, tstep, sync, ctrs, io_tab, stage_in0, stage_in1,
       stage_out, total;
   int s[5];   // block i works at H / s[i] * u[i]: scale_list[i] = s[i] / u[i] (one of the two is 1)
   int u[5];
@@ -407,6 +408,8 @@ static int plan_layout(int P, int T, int seq, int C, int H, int W, const float* 
   L->act_b = take(act * E);
   for (int i = 0; i < 5; ++i) L->tmp[i] = take(N / ((size_t)L->s[i] * L->s[i]) * L->u[i] * L->u[i] * TMP_C * E);
   L->fbuf = take(N * 4 * 4);  // full-resolution fp32 flow carried between the last stages
+  // second flow buffer: the gather fused into the scale-1 block's conv0.0 (conv_gather.cu) cannot update fbuf in place
+  L->fbuf2 = take(is_half_mode(precision) && !any_up && !L->generic && L->s[4] == 1 ? N * 4 * 4 : 0);
   L->gridx = take((size_t)W * 4);
   L->gridy = take((size_t)H * 4);
   L->tstep = take((size_t)B * 4);
@@ -639,6 +642,12 @@ static int default_chunk_pairs() {
   return v;
 }
 
+static bool gather_conv_on() {
+  // RIFE_GATHER_CONV=0: the scale-1 block's input gather and its conv0.0 as two kernels with `xin` in HBM between them
+  static const bool on = !(getenv("RIFE_GATHER_CONV") && atoi(getenv("RIFE_GATHER_CONV")) == 0);
+  return on;
+}
+
 static bool dyn_tiles_on() {
   static const bool on = !(getenv("RIFE_HK_DYN") && atoi(getenv("RIFE_HK_DYN")) == 0);  // A/B: static round robin
   return on;
@@ -766,10 +775,20 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     const int hkm = half_act ? w->blk_hk[i] : 0;
     const bool hk = hkm == 1;            // conv0.* on the halo kernel (planar-8 block input)
     const bool hk_tail = hkm != 0;       // ResConv x8 + lastconv on the halo kernel
+    // the last block at block scale 1 (1080p pyramid: block 4): input gather fused into conv0.0
+    const bool fused = hk && i == 4 && s == 1 && up == 1 && !c.any_up && gather_conv_on() && w->blk[i].conv00.use_hk &&
+                       gather_conv_fits(w->blk[i].conv00.hk);
+    float* fb_eval = fbuf;               // flow buffer the evaluation after this block reads
     if (up > 1) {
       // scale_list[i] < 1: the block input is the full-resolution one, bilinearly up-sampled (IFNet_HDv3.py:79-81)
       RIFE_STAGE(bn + ".input", launch_block_input(cc, i, lev, 1, p->at(L.xfull), false, fbuf, fbuf_levels, i > 0, st));
       RIFE_STAGE(bn + ".upsample", launch_upsample_xin(cc, p->at(L.xfull), p->at(L.xin), up, hk, st));
+    } else if (fused) {
+      // gather + conv0.0 in one kernel: the block input lives in shared memory only (conv_gather.cu)
+      RIFE_STAGE(bn + ".input+conv0.0",
+                 launch_gather_conv00(cc, i, lev, fbuf, (float*)p->at(L.fbuf2), fbuf_levels, w->blk[i].conv00.hk, p->at(L.c0),
+                                      w->blk[i].conv00.out_bf16 ? 1 : 0, st));
+      fb_eval = (float*)p->at(L.fbuf2);
     } else {
       RIFE_STAGE(bn + ".input", launch_block_input(cc, i, lev, s, p->at(L.xin), hk, fbuf, fbuf_levels, i > 0 && s <= 2, st));
     }
@@ -778,7 +797,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     io.B = Bc;
     // conv0.0: stride 2 on (hs, wsz) == 2x2 taps on the s2d grid (hs/2, wsz/2); output stored s2d again
     io.H = hs / 2; io.W = wsz / 2; io.in = p->at(L.xin); io.out = p->at(L.c0); io.epi = EPI_LRELU_S2D; io.out_c = c_ / 2;
-    RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, hk, st));
+    if (!fused) RIFE_STAGE(bn + ".conv0.0", run_conv(p, w->blk[i].conv00, io, hk, st));
     // conv0.1: stride 2 on (hs/2, wsz/2) == 2x2 taps on (hs/4, wsz/4)
     io.H = hs / 4; io.W = wsz / 4; io.in = p->at(L.c0); io.out = p->at(L.act_a); io.epi = EPI_LRELU; io.out_c = c_;
     io.planar_out = (hk_tail && !hk) ? 1 : 0;
@@ -851,7 +870,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
       eo.merged = outs->merged ? (char*)outs->merged + (size_t)b0 * out_frame : nullptr;
     }
     if (eo.flow || eo.warped0 || eo.warped1 || eo.mask || eo.merged)
-      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(cc, i + 1, lev, eo, io_dtype, fbuf, fbuf_levels, st));
+      RIFE_STAGE(i == 4 ? std::string("merge") : bn + ".eval", launch_eval(cc, i + 1, lev, eo, io_dtype, fb_eval, fbuf_levels, st));
     (void)last_pass;
     return RIFE_OK;
   };

@@ -1,0 +1,336 @@
+// Block-input gather fused into conv0.0 of the scale-1 IFBlock (block 4 of the 1080p pyramid; 28 -> 16 channels, stride 2:
+// train_log/IFNet_HDv3.py:57-62,79-83,141-152; model/warplayer.py:8-22).
+//
+// Un-fused, the gather writes the s2d block input `xin` (64 B per full-resolution pixel) to HBM and conv0.0 reads it straight
+// back: 2 x 2.1 GB per 16-pair step at 1080p, 19 % of the DRAM traffic of a pass.  Here one persistent CTA per SM
+//   * builds the block input of a 16 x 16 tile of the s2d grid (32 x 32 full-resolution pixels + the top row and left
+//     column conv0.0's stride-2 3x3 window reaches into: 33 x 33 = 1089 pixels, 6.3 % recomputed) with NG gather warps:
+//     lazy flow on top of the fp32 flow buffer, the two backward warps, the concat -- gather_s1_px() of gather.cuh, the same
+//     arithmetic as block_input_h_kernel<1> -- and stores every pixel's 4 x 16 B channel groups into shared memory in the
+//     planar-8 / tcgen05 no-swizzle K-major canonical layout conv_halo.cu's TMA box would have produced
+//     ([plane = parity * 4 + group][17 rows][17 cols][8 ch]);
+//   * one elected thread issues the 2 x 18 tcgen05 MMAs of the tile (2 M-tiles of 16 x 8 s2d pixels; N = 16, K = 16; the 14
+//     structurally-zero (tap, parity) products of the s2d formulation are not issued, conv_halo.cu) into a double-buffered
+//     TMEM accumulator;
+//   * four epilogue warps add bias, apply LeakyReLU(0.2) and store the activation space-to-depth, planar-8, exactly as
+//     conv_halo.cu's EPI_LRELU_S2D does (conv0.1 reads it unchanged).
+// Two smem stages: the gather of tile i+1 overlaps the MMAs and the epilogue of tile i.  A gather warp takes 32-pixel chunks
+// of a continuous (tile, chunk) stream -- chunk c of the CTA's t-th tile belongs to warp (c + 35 t) mod NG -- so the 35
+// chunks of a tile spread evenly over any number of warps in steady state; every warp arrives once per tile.
+// `xin` is never written; the flow summed over [0, level) goes to a second flow buffer (halo pixels of neighbouring tiles
+// read the first one, so it cannot be updated in place).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "conv_gather.cuh"
+#include "gather.cuh"
+#include "tc_dev.cuh"
+
+namespace rife {
+namespace {
+
+constexpr int GT = 16;                          // tile edge on the s2d grid
+constexpr int GP = GT + 1;                      // rows / row pitch (pixels) of a plane: one halo row / column
+constexpr int G_PLANE16 = GP * GP;              // 16-byte units per plane
+constexpr int G_PLANE_BYTES = G_PLANE16 * 16;   // 4624
+constexpr int G_NPLANES = 16;                   // 4 parities x 32 channels / 8
+constexpr int G_STAGE_BYTES = G_NPLANES * G_PLANE_BYTES;   // 73984 (a multiple of 128)
+constexpr int G_KSTEPS = 8, G_NE = 16;
+constexpr int G_W_BYTES = 4 * G_NPLANES * G_NE * 16;       // 4 taps x [cin/8][ne][8] fp16 = 16384
+constexpr int G_EDGE = 2 * GT + 1;              // 33 full-resolution rows / columns per tile
+constexpr int G_PX = G_EDGE * G_EDGE;           // 1089
+constexpr int G_CHUNKS = (G_PX + 31) / 32;      // 35
+constexpr int G_CTRL_THREADS = 32 + 128;        // MMA warp + 4 epilogue warps
+
+struct GParams {
+  LevelsArg L;
+  int level, fbuf_levels;
+  const __half* src0;
+  const __half* src1;
+  const float* tstep;
+  const float* fbuf_in;
+  float* fbuf_out;
+  int B, H, W;           // full resolution
+  int tiles_x, tiles_y, ntiles;
+  WarpGeom geom;
+  const __half* w;       // conv_halo.cu packing: [tap][cin/8][ne][8]
+  const float* bias;
+  __half* out;           // [B][8][H/4][W/4][8]
+  int out_bf;
+};
+
+// structural zeros of the stride-2 conv on the s2d input (conv_halo.cu: mma_nonzero<1, 8, E, KK>)
+template <int E, int KK>
+__device__ __forceinline__ constexpr bool g_nonzero() {
+  constexpr int par = KK / (G_KSTEPS / 4), py = par >> 1, px = par & 1;
+  constexpr int dy = E / 2 - 1, dx = E % 2 - 1;
+  return (dy == 0 || py == 1) && (dx == 0 || px == 1);
+}
+template <int E, int KK = 0>
+__device__ __forceinline__ constexpr int g_first_kk() {
+  if constexpr (g_nonzero<E, KK>()) return KK;
+  else return g_first_kk<E, KK + 1>();
+}
+// the 18 MMAs of one M-tile, every operand offset an immediate
+template <int E = 0, int KK = 0>
+__device__ __forceinline__ void g_issue_tile(uint32_t acc, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
+  if constexpr (E < 4) {
+    if constexpr (g_nonzero<E, KK>()) {
+      constexpr int dy = E / 2 - 1, dx = E % 2 - 1;
+      constexpr int a_off = 2 * KK * G_PLANE16 + (dy + 1) * GP + (dx + 1);
+      constexpr int b_off = E * (2 * G_KSTEPS) * G_NE + 2 * KK * G_NE;
+      constexpr bool first = E == 0 && KK == g_first_kk<0>();
+      tc::umma_f16<!first>(acc, a_base + (uint64_t)a_off, b_base + (uint64_t)b_off, idesc);
+    }
+    if constexpr (KK + 1 < G_KSTEPS) g_issue_tile<E, KK + 1>(acc, a_base, b_base, idesc);
+    else g_issue_tile<E + 1, 0>(acc, a_base, b_base, idesc);
+  }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(G_CTRL_THREADS + 32 * NG, 1) gather_conv00_kernel(const __grid_constant__ GParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[2];
+  __shared__ __align__(8) uint64_t a_empty[2];
+  __shared__ __align__(8) uint64_t t_full[2];
+  __shared__ __align__(8) uint64_t t_empty[2];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[G_NE];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_smem = (tc::smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t a_smem = w_smem + G_W_BYTES;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(tc::smem_u32(&a_full[i]), NG);   // one arrive per gather warp
+      tc::mbar_init(tc::smem_u32(&a_empty[i]), 1);   // tcgen05.commit
+      tc::mbar_init(tc::smem_u32(&t_full[i]), 1);    // tcgen05.commit
+      tc::mbar_init(tc::smem_u32(&t_empty[i]), 4);   // one arrive per epilogue warp
+    }
+    tc::mbar_init(tc::smem_u32(&w_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_slot)), "r"(64u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + G_NE) s_bias[threadIdx.x - 32] = p.bias[threadIdx.x - 32];
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- weights (constants: loaded before the dependency wait), then the MMAs of every tile
+      const uint32_t wb = tc::smem_u32(&w_full);
+      tc::mbar_expect_tx(wb, (uint32_t)G_W_BYTES);
+      tc::bulk_load(w_smem, p.w, (uint32_t)G_W_BYTES, wb);
+      tc::mbar_wait(wb, 0);
+      // instruction descriptor: D = f32, A / B = f16, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(G_NE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t a_desc0 = tc::make_desc_noswz(0, (uint32_t)G_PLANE_BYTES, (uint32_t)GP * 16u);
+      const uint64_t b_base = tc::make_desc_noswz(w_smem, (uint32_t)G_NE * 16u, 128u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+        tc::mbar_wait(tc::smem_u32(&a_full[s]), ph);
+        tc::mbar_wait(tc::smem_u32(&t_empty[s]), ph ^ 1u);
+        tc::fence_after();
+        const uint32_t sa16 = (a_smem + (uint32_t)s * G_STAGE_BYTES) >> 4;
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx)
+          g_issue_tile<>(tmem_base + (uint32_t)(s * 2 * G_NE + cx * G_NE), a_desc0 + (uint64_t)(sa16 + (uint32_t)cx * 8u), b_base,
+                         idesc);
+        tc::umma_commit(tc::smem_u32(&a_empty[s]));
+        tc::umma_commit(tc::smem_u32(&t_full[s]));
+      }
+    }
+  } else if (warp < 5) {
+    // ---------------- epilogue: TMEM lane quarter warp % 4; thread = GEMM row m = ty_ * 8 + tx_ of both M-tiles
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty_ = m >> 3, tx_ = m & 7;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int H2 = p.H >> 1, W2 = p.W >> 1, H4 = p.H >> 2, W4 = p.W >> 2;
+    const size_t pl = (size_t)H4 * W4 * 8;   // elements per planar-8 group of the destination
+    float bias[G_NE];
+#pragma unroll
+    for (int i = 0; i < G_NE; ++i) bias[i] = s_bias[i];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      tc::mbar_wait(tc::smem_u32(&t_full[s]), ph);
+      tc::fence_after();
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        float v[16];
+        tc::tmem_ld16(trow + (uint32_t)(s * 2 * G_NE + cx * G_NE), v);
+        const int y = ty * GT + ty_, x = tx * GT + cx * 8 + tx_;   // s2d grid
+        if (y < H2 && x < W2) {
+          // EPI_LRELU_S2D of conv_halo.cu: planar-8 on the quarter-resolution grid, channel = parity * 16 + n
+          const int par = (y & 1) * 2 + (x & 1);
+          __half* dst = p.out + ((size_t)b * 8 + par * 2) * pl + ((size_t)(y >> 1) * W4 + (x >> 1)) * 8;
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[i] + bias[i]);
+          st8x(dst, a, p.out_bf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = lrelu02(v[8 + i] + bias[8 + i]);
+          st8x(dst + pl, a, p.out_bf);
+        }
+      }
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&t_empty[s]));
+    }
+  } else {
+    // ---------------- gather warps
+    pdl_wait();   // SRC, the tmp levels and the flow buffer are earlier kernels' outputs (common.cuh: PDL contract)
+    const int gw = warp - 5;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y0 = ty * 2 * GT - 1, x0 = tx * 2 * GT - 1;   // full-resolution position of the halo corner
+      const int fr = p.geom.src_div == 1 ? b : b / p.geom.src_div;
+      const __half* s0 = p.src0 + (size_t)fr * p.H * p.W * SRC_C;
+      const __half* s1 = p.src1 + (size_t)fr * p.H * p.W * SRC_C;
+      int first = (gw - it * G_CHUNKS) % NG;
+      if (first < 0) first += NG;
+      tc::mbar_wait(tc::smem_u32(&a_empty[s]), ph ^ 1u);   // the MMAs of the tile two steps back have read this stage
+      const uint32_t stage = a_smem + (uint32_t)s * G_STAGE_BYTES;
+#pragma unroll 1
+      for (int c = first; c < G_CHUNKS; c += NG) {
+        const int idx = c * 32 + lane;
+        if (idx < G_PX) {
+          const int ry = idx / G_EDGE, rx = idx - ry * G_EDGE;
+          const int y = y0 + ry, x = x0 + rx;
+          uint4 u[4];
+          if (y >= 0 && x >= 0 && y < p.H && x < p.W) {
+            __half2 o[16];
+            gather_s1_px(p.L, p.level, s0, s1, p.tstep, b, y, x, p.H, p.W, p.geom, p.fbuf_in, p.fbuf_out, p.fbuf_levels,
+                         ry > 0 && rx > 0, o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __half2* hh = reinterpret_cast<__half2*>(&u[k]);
+              hh[0] = o[4 * k]; hh[1] = o[4 * k + 1]; hh[2] = o[4 * k + 2]; hh[3] = o[4 * k + 3];
+            }
+          } else {
+            // conv0.0's zero padding (top / left), or beyond the image (bottom / right: only feeds outputs that are not stored)
+            u[0] = zero4; u[1] = zero4; u[2] = zero4; u[3] = zero4;
+          }
+          // s2d pixel ((ry + 1) >> 1, (rx + 1) >> 1) of the stage (row / column 0 = halo), parity ((ry + 1) & 1, (rx + 1) & 1)
+          const int par = ((ry + 1) & 1) * 2 + ((rx + 1) & 1);
+          const uint32_t a = stage + (uint32_t)(par * 4 * G_PLANE_BYTES + (((ry + 1) >> 1) * GP + ((rx + 1) >> 1)) * 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + (uint32_t)(k * G_PLANE_BYTES)), "r"(u[k].x),
+                         "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
+                         : "memory");
+        }
+      }
+      tc::fence_async_smem();   // generic-proxy stores -> the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&a_full[s]));
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int opt_in_smem(const void* fn, int bytes) {
+  static std::vector<std::pair<const void*, int>> seen;
+  static std::mutex mu;   // one host thread per GPU may launch concurrently
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& s : seen)
+    if (s.first == fn && s.second == dev) return RIFE_OK;
+  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  seen.emplace_back(fn, dev);
+  return RIFE_OK;
+}
+
+template <int NG>
+int launch_ng(const GParams& p, cudaStream_t st) {
+  const int smem = G_W_BYTES + 2 * G_STAGE_BYTES + 128;
+  RIFE_TRY(opt_in_smem((const void*)gather_conv00_kernel<NG>, smem));
+  int grid = sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  RIFE_CUDA_TRY(launch_pdl(gather_conv00_kernel<NG>, dim3(grid), dim3(G_CTRL_THREADS + 32 * NG), smem, st, p));
+  RIFE_LAUNCH_CHECK();
+  return RIFE_OK;
+}
+
+}  // namespace
+
+bool gather_conv_fits(const HaloLayer& L) {
+  return L.kind == CONV_S2D && L.cin == 4 * XIN_C && L.nentries == 4 && L.ne == G_NE && L.ncols == G_NE && !L.stream &&
+         L.w_bytes == G_W_BYTES && L.ps_cols == 0;
+}
+
+int launch_gather_conv00(const PixelCtx& c, int level, const TmpLevel* levels, const float* fbuf_in, float* fbuf_out,
+                         int fbuf_levels, const HaloLayer& conv00, void* out, int out_bf16, cudaStream_t st) {
+  if (!gather_conv_fits(conv00)) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "gather_conv00: conv0.0 is not the 4 x 32 -> 16 channel s2d layer");
+  if (!c.half_act || c.any_up || level < 1 || level > MAXLEV)
+    RIFE_FAIL(RIFE_ERR_INVALID_ARG, "gather_conv00: fp16 / bf16 pipeline, scale-1 block, level >= 1 only");
+  if (c.H % 4 || c.W % 4) RIFE_FAIL(RIFE_ERR_SHAPE, "gather_conv00: H and W must be multiples of 4");
+  if (fbuf_levels > 0 && !fbuf_in) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "gather_conv00: fbuf_in is null");
+  if (!fbuf_out || fbuf_out == fbuf_in) RIFE_FAIL(RIFE_ERR_INVALID_ARG, "gather_conv00: fbuf_out must be a second buffer");
+  for (int j = fbuf_levels; j < level; ++j)
+    if (levels[j].s <= 1 || levels[j].pitch != TMP_C)
+      RIFE_FAIL(RIFE_ERR_INVALID_ARG, "gather_conv00: coarser 16-channel tmp levels only");
+  GParams p{};
+  p.L = pack_levels(levels, level);
+  p.level = level; p.fbuf_levels = fbuf_levels;
+  p.src0 = (const __half*)c.src0; p.src1 = (const __half*)c.src1;
+  p.tstep = c.tstep;
+  p.fbuf_in = fbuf_in; p.fbuf_out = fbuf_out;
+  p.B = c.B; p.H = c.H; p.W = c.W;
+  p.tiles_x = (c.W / 2 + GT - 1) / GT;
+  p.tiles_y = (c.H / 2 + GT - 1) / GT;
+  p.ntiles = p.tiles_x * p.tiles_y * c.B;
+  p.geom = make_geom(c.H, c.W);
+  p.geom.src_div = c.src_div;
+  p.w = conv00.w; p.bias = conv00.bias;
+  p.out = (__half*)out; p.out_bf = out_bf16 ? 1 : 0;
+  // gather warps per CTA (one CTA per SM): 27 = a full 1024-thread CTA at 64 registers per thread
+  static const int ng = getenv("RIFE_GC_WARPS") ? atoi(getenv("RIFE_GC_WARPS")) : 27;
+  if (ng <= 16) return launch_ng<16>(p, st);
+  if (ng <= 20) return launch_ng<20>(p, st);
+  if (ng <= 24) return launch_ng<24>(p, st);
+  return launch_ng<27>(p, st);
+}
+
+}  // namespace rife

@@ -393,7 +393,9 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
       IFNet_HDv3.py:148-159) -- RIFE_NO_NARROW_LAST=1 restores the 13-channel lastconv;
     * RIFE_HK_CHAIN=64: the 8 ResConv layers of blocks 1-3 run as ONE cooperative launch each, with grid barriers
       between the layers (conv_halo.cu; optional, off by default);
-    * RIFE_GRAPH_MAX=0: no CUDA-graph replay of small-batch calls.
+    * RIFE_GRAPH_MAX=0: no CUDA-graph replay of small-batch calls;
+    * RIFE_GATHER_CONV=0: block 4's input gather and its conv0.0 as two kernels with the block input in HBM between them
+      instead of the fused kernel of conv_gather.cu (same per-pixel arithmetic, same MMA order).
     IFNet.forward (all outputs, 16-channel tmp) agrees with the frame as well."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -408,11 +410,12 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
         "torch.save((m.inference(a, b, 0.4).cpu(), m.inference(c, d, 0.5).cpu(), torch.cat(small)), sys.argv[1])" % (root, root))
     outs = {}
     for tag, env in (("default", {}), ("wide", {"RIFE_NO_NARROW_LAST": "1"}), ("chain", {"RIFE_HK_CHAIN": "64"}),
-                     ("strip", {"RIFE_STRIP": "1"}), ("nograph", {"RIFE_GRAPH_MAX": "0"})):
+                     ("strip", {"RIFE_STRIP": "1"}), ("nograph", {"RIFE_GRAPH_MAX": "0"}),
+                     ("unfused", {"RIFE_GATHER_CONV": "0"})):
         f = str(tmp_path / (tag + ".pt"))
         subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env}, timeout=600)
         outs[tag] = torch.load(f)
-    for tag in ("wide", "chain", "nograph"):
+    for tag in ("wide", "chain", "nograph", "unfused"):
         assert torch.equal(outs[tag][0], outs["default"][0]) and torch.equal(outs[tag][1], outs["default"][1]), tag
     # calls with <= 4 outputs replay a CUDA graph from the second call on (rife_inference): five B = 1 calls with fresh
     # tensors and timesteps each -- plain, capture + replay, three replays -- equal the graph-free run bit for bit
