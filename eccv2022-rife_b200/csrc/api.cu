@@ -777,7 +777,7 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
     const bool hk_tail = hkm != 0;       // ResConv x8 + lastconv on the halo kernel
     // the last block at block scale 1 (1080p pyramid: block 4): input gather fused into conv0.0
     const bool fused = hk && i == 4 && s == 1 && up == 1 && !c.any_up && gather_conv_on() && w->blk[i].conv00.use_hk &&
-                       gather_conv_fits(w->blk[i].conv00.hk);
+                       gather_conv_fits(w->blk[i].conv00.hk) && gather_conv_levels_fit(i, lev, fbuf_levels, H, W);
     float* fb_eval = fbuf;               // flow buffer the evaluation after this block reads
     if (up > 1) {
       // scale_list[i] < 1: the block input is the full-resolution one, bilinearly up-sampled (IFNet_HDv3.py:79-81)

@@ -1,6 +1,6 @@
 // Device helpers of the block-input gather shared by pixel_kernels.cu (stand-alone gather kernels) and conv_gather.cu
 // (the gather fused into block 4's conv0.0): bilinear index / weight helpers, the packed-half2 warp taps, the per-level
-// flow accumulation, and gather_s1_px() = everything one full-resolution pixel of a scale-1 block input needs.
+// flow accumulation.
 // Reference semantics: train_log/IFNet_HDv3.py:79-82,86-89,141-152; model/warplayer.py:8-22.
 #pragma once
 #include "common.cuh"
@@ -133,51 +133,6 @@ inline LevelsArg pack_levels(const TmpLevel* levels, int n) {
     L.sc[i] = levels[i].s > 0 ? (float)levels[i].s : 1.f / (float)(-levels[i].s);   // "* scale" of IFNet_HDv3.py:87
   }
   return L;
-}
-
-// One full-resolution pixel (b, y, x) of the block input of block `level` at block scale 1 (the NS = 1 path of
-// block_input_h_kernel): lazy flow over the levels [fbuf_levels, level) on top of the fp32 flow buffer `fbuf_in` (the sum
-// over [0, level) goes to `fbuf_out` when `fbuf_store`), the two warps, the concat.  Returns the 32 channels as 16 half2 in the order of IFNet_HDv3.py:145-147 + :82
-// [warped img0 (3) | warped img1 (3) | warped f0 (4) | warped f1 (4) | timestep | mask | feat (8) | flow (4) | 0 x 4].
-__device__ __forceinline__ void gather_s1_px(const LevelsArg& L, int level, const __half* __restrict__ s0,
-                                             const __half* __restrict__ s1, const float* __restrict__ tstep, int b, int y,
-                                             int x, int H, int W, const WarpGeom& geom,
-                                             const float* __restrict__ fbuf_in, float* __restrict__ fbuf_out,
-                                             int fbuf_levels, bool fbuf_store, __half2 (&o)[16]) {
-  float flow[4];
-  const size_t fo = (((size_t)b * H + y) * W + x) * 4;
-  if (fbuf_levels > 0) ld4(fbuf_in + fo, flow);
-  __half2 mfh[6];  // channels 4..15 of the newest level (mask, feat x8, pad), packed half2
-#pragma unroll 1
-  for (int j = fbuf_levels; j < level; ++j) {
-    const __half* base = reinterpret_cast<const __half*>(L.ptr[j]) + (size_t)b * L.h[j] * L.w[j] * TMP_C;
-    const int h = L.h[j], w = L.w[j];
-    if (L.s[j] == 1) continue;  // only possible as the newest level of a scale-1 eval; not reached from block inputs
-    const Lerp2 ly = make_lerp2(y, h, L.rs[j]), lx = make_lerp2(x, w, L.rs[j]);
-    const float ay = ly.a0, ax = lx.a0;
-    const float wq[4] = {(1.f - ay) * (1.f - ax), (1.f - ay) * ax, ay * (1.f - ax), ay * ax};
-    level_taps_h1(base + ly.i0 * w * TMP_C, base + ly.i1 * w * TMP_C, lx.i0 * TMP_C, lx.i1 * TMP_C, j == level - 1, wq,
-                  L.sc[j], j == 0, flow, mfh);
-  }
-  if (fbuf_store) st4(fbuf_out + fo, flow);
-  __half2 A[4], Cc[4];
-  warp8_h2(s0, H, W, geom, x, y, flow[0], flow[1], A);   // IFNet_HDv3.py:145,155
-  warp8_h2(s1, H, W, geom, x, y, flow[2], flow[3], Cc);  // IFNet_HDv3.py:146,156
-  const float t = tstep[b];
-  o[0] = A[2];                                   // warped img0 r, g
-  o[1] = __halves2half2(__low2half(A[3]), __low2half(Cc[2]));   // img0 b, img1 r
-  o[2] = __halves2half2(__high2half(Cc[2]), __low2half(Cc[3])); // img1 g, b
-  o[3] = A[0]; o[4] = A[1];                      // warped f0
-  o[5] = Cc[0]; o[6] = Cc[1];                    // warped f1
-  o[7] = __halves2half2(__float2half_rn(t), __low2half(mfh[0]));      // timestep, mask
-  o[8] = __halves2half2(__high2half(mfh[0]), __low2half(mfh[1]));     // feat 0..7
-  o[9] = __halves2half2(__high2half(mfh[1]), __low2half(mfh[2]));
-  o[10] = __halves2half2(__high2half(mfh[2]), __low2half(mfh[3]));
-  o[11] = __halves2half2(__high2half(mfh[3]), __low2half(mfh[4]));
-  o[12] = __floats2half2_rn(flow[0], flow[1]);   // interpolate(flow, 1/s) * 1/s with s = 1 (IFNet_HDv3.py:81)
-  o[13] = __floats2half2_rn(flow[2], flow[3]);
-  o[14] = __float2half2_rn(0.f);
-  o[15] = o[14];
 }
 
 }  // namespace
