@@ -17,9 +17,11 @@
 //     TMEM accumulator;
 //   * four epilogue warps add bias, apply LeakyReLU(0.2) and store the activation space-to-depth, planar-8, exactly as
 //     conv_halo.cu's EPI_LRELU_S2D does (conv0.1 reads it unchanged).
-// Two smem stages: the gather of tile i+1 overlaps the MMAs and the epilogue of tile i.  A gather warp takes 32-pixel chunks
-// of a continuous (tile, chunk) stream -- chunk c of the CTA's t-th tile belongs to warp (c + 35 t) mod NG -- so the 35
-// chunks of a tile spread evenly over any number of warps in steady state; every warp arrives once per tile.
+// The MMA and epilogue roles wait with a back-off (they are idle most of a tile's time and would otherwise spend issue slots
+// of the gather warps on polling).  Two smem stages: the gather of tile i+1 overlaps the MMAs and the epilogue of tile i.
+// A gather warp takes 32-pixel chunks (one interior row of the tile, the halo row, the halo column, the corner) of a
+// continuous (tile, chunk) stream -- chunk c of the CTA's t-th tile belongs to warp (c + 35 t) mod NG -- so the 35 chunks of
+// a tile spread evenly over any number of warps in steady state; every warp arrives once per tile.
 // `xin` is never written; the flow summed over [0, level) goes to a second flow buffer (halo pixels of neighbouring tiles
 // read the first one, so it cannot be updated in place).
 #include <cuda.h>
@@ -51,10 +53,13 @@ constexpr int G_CHUNKS = (G_PX + 31) / 32;      // 35
 constexpr int G_CTRL_THREADS = 32 + 128;        // MMA warp + 4 epilogue warps
 // staged inputs of one tile: flow-buffer window [33][33] float4 and tmp-level window [18][18][16] fp16
 constexpr int G_TE = GT + 2;                    // 18 rows / columns of the half-resolution level under a 33 x 33 tile
+// (the two 16-byte halves of a tmp pixel land in separate planes: lanes that read neighbouring pixels then touch consecutive
+// 16-byte slots instead of every other one -- no shared-memory bank conflicts on the eight tap loads of a pixel)
 constexpr int G_FB_BYTES = G_EDGE * G_EDGE * 16;                // 17424
 constexpr int G_FB_AL = (G_FB_BYTES + 127) / 128 * 128;         // 17536
-constexpr int G_TM_BYTES = G_TE * G_TE * TMP_C * 2;             // 10368
-constexpr int G_TM_AL = (G_TM_BYTES + 127) / 128 * 128;         // 10496
+constexpr int G_TM_BYTES = 2 * G_TE * G_TE * 16;                // 10368 bytes arrive per window
+constexpr int G_TM_HALF = (G_TE * G_TE * 16 + 127) / 128 * 128; // one plane (channels 0..7 or 8..15), 128-byte aligned for TMA
+constexpr int G_TM_AL = 2 * G_TM_HALF;                          // 10496
 constexpr int G_IN_BYTES = G_FB_AL + G_TM_AL;                   // per input stage
 constexpr int G_SMEM = G_W_BYTES + 2 * G_STAGE_BYTES + 2 * G_IN_BYTES + 128;
 
@@ -117,7 +122,7 @@ __device__ __forceinline__ void level_taps_h1_s(uint32_t r0, uint32_t r1, uint32
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint32_t a = ((k >> 1) ? r1 : r0) + ((k & 1) ? c1 : c0);
-    const uint4 lo = lds128(a), hi = lds128(a + 16);
+    const uint4 lo = lds128(a), hi = lds128(a + G_TM_HALF);
     const __half2* hl = reinterpret_cast<const __half2*>(&lo);
     const __half2* hh = reinterpret_cast<const __half2*>(&hi);
     const float2 f01 = __half22float2(hl[0]), f23 = __half22float2(hl[1]);
@@ -192,8 +197,10 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
         tc::mbar_expect_tx(bar, (uint32_t)(G_FB_BYTES + G_TM_BYTES));
         // flow buffer [B][H][W][4] fp32 as {4W, H, B}: 33 pixels x 33 rows from (32 tx - 1, 32 ty - 1); outside = zero fill
         tc::tma_load_3d(dst, &tm_fb, bar, 4 * (tx * 2 * GT - 1), ty * 2 * GT - 1, b);
-        // tmp level [B][th][tw][16] fp16 as {8 tw, th, B} 32-bit words: 18 x 18 pixels from (16 tx - 1, 16 ty - 1)
-        tc::tma_load_3d(dst + G_FB_AL, &tm_tmp, bar, 8 * (tx * GT - 1), ty * GT - 1, b);
+        // tmp level [B][th][tw][16] fp16 as {4 words, 2 halves, tw, th, B}: 18 x 18 pixels from (16 tx - 1, 16 ty - 1), one
+        // plane per 16-byte half
+        tc::tma_load_5d(dst + G_FB_AL, &tm_tmp, bar, 0, 0, tx * GT - 1, ty * GT - 1, b);
+        tc::tma_load_5d(dst + G_FB_AL + G_TM_HALF, &tm_tmp, bar, 0, 1, tx * GT - 1, ty * GT - 1, b);
       };
       if ((int)blockIdx.x < p.ntiles) prefetch(blockIdx.x, 0);
       if ((int)(blockIdx.x + gridDim.x) < p.ntiles) prefetch(blockIdx.x + gridDim.x, 1);
@@ -206,10 +213,10 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t ph = ((uint32_t)it >> 1) & 1u;
-        tc::mbar_wait(tc::smem_u32(&a_full[s]), ph);
+        tc::mbar_wait_backoff(tc::smem_u32(&a_full[s]), ph);
         // every gather warp is done with tile `it`, hence with input stage s: refill it for tile it + 2
         if (tile + 2 * (int)gridDim.x < p.ntiles) prefetch(tile + 2 * (int)gridDim.x, s);
-        tc::mbar_wait(tc::smem_u32(&t_empty[s]), ph ^ 1u);
+        tc::mbar_wait_backoff(tc::smem_u32(&t_empty[s]), ph ^ 1u);
         tc::fence_after();
         const uint32_t sa16 = (a_smem + (uint32_t)s * G_STAGE_BYTES) >> 4;
 #pragma unroll
@@ -237,7 +244,7 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
       const uint32_t ph = ((uint32_t)it >> 1) & 1u;
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      tc::mbar_wait(tc::smem_u32(&t_full[s]), ph);
+      tc::mbar_wait_backoff(tc::smem_u32(&t_full[s]), ph);
       tc::fence_after();
 #pragma unroll
       for (int cx = 0; cx < 2; ++cx) {
@@ -288,9 +295,15 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
       tc::mbar_wait(tc::smem_u32(&in_full[s]), ph);        // this tile's flow-buffer and tmp windows have landed
 #pragma unroll 1
       for (int c = first; c < G_CHUNKS; c += NG) {
-        const int idx = c * 32 + lane;
-        if (idx < G_PX) {
-          const int ry = idx / G_EDGE, rx = idx - ry * G_EDGE;
+        // chunks 0..31: interior rows (ry = c + 1, rx = 1..32: 16-byte-slot aligned shared-memory stores, 512-byte aligned
+        // flow-buffer stores); 32: the top halo row (rx = 1..32); 33: the left halo column (ry = 1..32); 34: the corner
+        int ry, rx;
+        if (c < 2 * GT) { ry = c + 1; rx = lane + 1; }
+        else if (c == 2 * GT) { ry = 0; rx = lane + 1; }
+        else if (c == 2 * GT + 1) { ry = lane + 1; rx = 0; }
+        else { ry = 0; rx = lane == 0 ? 0 : -1; }
+        if (rx >= 0) {
+          const int idx = ry * G_EDGE + rx;
           const int y = y0 + ry, x = x0 + rx;
           uint4 u[4];
           if (y >= 0 && x >= 0 && y < p.H && x < p.W) {
@@ -306,8 +319,8 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
               const Lerp2 ly = make_lerp2(y, p.th, 0.5f), lx = make_lerp2(x, p.tw, 0.5f);
               const float ay = ly.a0, ax = lx.a0;
               const float wq[4] = {(1.f - ay) * (1.f - ax), (1.f - ay) * ax, ay * (1.f - ax), ay * ax};
-              level_taps_h1_s(tms + (uint32_t)((ly.i0 - ty0) * (G_TE * 32)), tms + (uint32_t)((ly.i1 - ty0) * (G_TE * 32)),
-                              (uint32_t)((lx.i0 - tx0) * 32), (uint32_t)((lx.i1 - tx0) * 32), wq, 2.f, flow, mfh);
+              level_taps_h1_s(tms + (uint32_t)((ly.i0 - ty0) * (G_TE * 16)), tms + (uint32_t)((ly.i1 - ty0) * (G_TE * 16)),
+                              (uint32_t)((lx.i0 - tx0) * 16), (uint32_t)((lx.i1 - tx0) * 16), wq, 2.f, flow, mfh);
             }
             if (ry > 0 && rx > 0) st4(fbo + (y * p.W + x) * 4, flow);
             __half2 A[4], Cc[4];
@@ -452,12 +465,12 @@ int launch_gather_conv00(const PixelCtx& c, int level, const TmpLevel* levels, c
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(flow buffer) failed: " + std::to_string((int)r));
   }
   {
-    // [B][th][tw][16] fp16 seen as 32-bit words (8 per pixel): a box row of 18 pixels = 144 elements (<= 256)
-    cuuint64_t dims[3] = {(cuuint64_t)tl.w * 8, (cuuint64_t)tl.h, (cuuint64_t)c.B};
-    cuuint64_t strides[2] = {(cuuint64_t)tl.w * 32, (cuuint64_t)tl.h * tl.w * 32};
-    cuuint32_t box[3] = {(cuuint32_t)(G_TE * 8), (cuuint32_t)G_TE, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&tm_tmp, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(tl.ptr), dims, strides, box, es,
+    // [B][th][tw][16] fp16 seen as 32-bit words: {4 words = 16 B, 2 halves, tw, th, B}; one box = one half of 18 x 18 pixels
+    cuuint64_t dims[5] = {4, 2, (cuuint64_t)tl.w, (cuuint64_t)tl.h, (cuuint64_t)c.B};
+    cuuint64_t strides[4] = {16, 32, (cuuint64_t)tl.w * 32, (cuuint64_t)tl.h * tl.w * 32};
+    cuuint32_t box[5] = {4, 1, (cuuint32_t)G_TE, (cuuint32_t)G_TE, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tm_tmp, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void*>(tl.ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(tmp level) failed: " + std::to_string((int)r));
