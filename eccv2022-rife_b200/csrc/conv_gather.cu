@@ -76,6 +76,7 @@ struct GParams {
   const float* bias;
   __half* out;           // [B][8][H/4][W/4][8]
   int out_bf;
+  int src_margin;        // >= 0: L2 prefetch of the SRC windows with this many pixels of margin; < 0: off
 };
 
 // structural zeros of the stride-2 conv on the s2d input (conv_halo.cu: mma_nonzero<1, 8, E, KK>)
@@ -141,6 +142,7 @@ __device__ __forceinline__ void level_taps_h1_s(uint32_t r0, uint32_t r1, uint32
 template <int NG>
 __global__ void __launch_bounds__(G_CTRL_THREADS + 32 * NG, 1)
 gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_constant__ CUtensorMap tm_tmp,
+                     const __grid_constant__ CUtensorMap tm_s0, const __grid_constant__ CUtensorMap tm_s1,
                      const __grid_constant__ GParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[2];
@@ -201,6 +203,13 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
         // plane per 16-byte half
         tc::tma_load_5d(dst + G_FB_AL, &tm_tmp, bar, 0, 0, tx * GT - 1, ty * GT - 1, b);
         tc::tma_load_5d(dst + G_FB_AL + G_TM_HALF, &tm_tmp, bar, 0, 1, tx * GT - 1, ty * GT - 1, b);
+        if (p.src_margin >= 0) {
+          // the tile's window of both SRC frames (+ a margin for the flow) on its way into L2: the warp taps then pay an
+          // L2 hit instead of a DRAM round trip.  A hint only -- taps beyond the margin go to DRAM as before.
+          const int fr = p.geom.src_div == 1 ? b : b / p.geom.src_div;
+          tc::tma_prefetch_3d(&tm_s0, 4 * (tx * 2 * GT - 1 - p.src_margin), ty * 2 * GT - 1 - p.src_margin, fr);
+          tc::tma_prefetch_3d(&tm_s1, 4 * (tx * 2 * GT - 1 - p.src_margin), ty * 2 * GT - 1 - p.src_margin, fr);
+        }
       };
       if ((int)blockIdx.x < p.ntiles) prefetch(blockIdx.x, 0);
       if ((int)(blockIdx.x + gridDim.x) < p.ntiles) prefetch(blockIdx.x + gridDim.x, 1);
@@ -274,12 +283,26 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
     const int gw = warp - 5;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     const int HW = p.H * p.W;
+    // (b, ty, tx) of the CTA's tiles advance by a fixed step: no integer division per tile in the 27 gather warps
+    int b = blockIdx.x / tiles_per_img, ty, tx;
+    {
+      const int r = blockIdx.x - b * tiles_per_img;
+      ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+    }
+    const int db = gridDim.x / tiles_per_img, dr = gridDim.x - db * tiles_per_img;
+    const int dty = dr / p.tiles_x, dtx = dr - dty * p.tiles_x;
+    int first = gw;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      if (it > 0) {
+        tx += dtx; ty += dty; b += db;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+        first -= G_CHUNKS % NG;   // chunk c of the CTA's t-th tile belongs to warp (c + 35 t) mod NG
+        if (first < 0) first += NG;
+      }
       const int s = it & 1;
       const uint32_t ph = ((uint32_t)it >> 1) & 1u;
-      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y0 = ty * 2 * GT - 1, x0 = tx * 2 * GT - 1;   // full-resolution position of the halo corner
       const int ty0 = ty * GT - 1, tx0 = tx * GT - 1;         // origin of the staged tmp window
       const int fr = p.geom.src_div == 1 ? b : b / p.geom.src_div;
@@ -287,8 +310,6 @@ gather_conv00_kernel(const __grid_constant__ CUtensorMap tm_fb, const __grid_con
       const __half* s1 = p.src1 + (size_t)fr * HW * SRC_C;
       float* fbo = p.fbuf_out + (size_t)b * HW * 4;
       const __half tsh = __float2half_rn(p.tstep[b]);
-      int first = (gw - it * G_CHUNKS) % NG;
-      if (first < 0) first += NG;
       const uint32_t stage = a_smem + (uint32_t)s * G_STAGE_BYTES;
       const uint32_t fbs = in_smem + (uint32_t)s * G_IN_BYTES, tms = fbs + G_FB_AL;
       tc::mbar_wait(tc::smem_u32(&a_empty[s]), ph ^ 1u);   // the MMAs of the tile two steps back have read this stage
@@ -408,11 +429,13 @@ int opt_in_smem(const void* fn, int bytes) {
 }
 
 template <int NG>
-int launch_ng(const CUtensorMap& tm_fb, const CUtensorMap& tm_tmp, const GParams& p, cudaStream_t st) {
+int launch_ng(const CUtensorMap& tm_fb, const CUtensorMap& tm_tmp, const CUtensorMap& tm_s0, const CUtensorMap& tm_s1,
+              const GParams& p, cudaStream_t st) {
   RIFE_TRY(opt_in_smem((const void*)gather_conv00_kernel<NG>, G_SMEM));
   int grid = sm_count();
   if (grid > p.ntiles) grid = p.ntiles;
-  RIFE_CUDA_TRY(launch_pdl(gather_conv00_kernel<NG>, dim3(grid), dim3(G_CTRL_THREADS + 32 * NG), G_SMEM, st, tm_fb, tm_tmp, p));
+  RIFE_CUDA_TRY(launch_pdl(gather_conv00_kernel<NG>, dim3(grid), dim3(G_CTRL_THREADS + 32 * NG), G_SMEM, st, tm_fb, tm_tmp, tm_s0, tm_s1,
+                           p));
   RIFE_LAUNCH_CHECK();
   return RIFE_OK;
 }
@@ -475,12 +498,30 @@ int launch_gather_conv00(const PixelCtx& c, int level, const TmpLevel* levels, c
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(tmp level) failed: " + std::to_string((int)r));
   }
+  // SRC frames [F][H][W][8] fp16 as {4 W words, H, F}: prefetch box = (33 + 2 margin)^2 pixels
+  static const int margin = getenv("RIFE_GC_SRC_MARGIN") ? atoi(getenv("RIFE_GC_SRC_MARGIN")) : 4;
+  p.src_margin = margin > 15 ? 15 : margin;
+  CUtensorMap tm_s0 = tm_fb, tm_s1 = tm_fb;
+  if (p.src_margin >= 0) {
+    const int nfr = (c.B + c.src_div - 1) / c.src_div;   // frames of src0 / src1 this (sub-)batch warps
+    const int e = G_EDGE + 2 * p.src_margin;
+    cuuint64_t strides[2] = {(cuuint64_t)c.W * 16, (cuuint64_t)c.H * c.W * 16};
+    cuuint32_t box[3] = {(cuuint32_t)(e * 4), (cuuint32_t)e, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    for (int k = 0; k < 2; ++k) {
+      cuuint64_t dims[3] = {(cuuint64_t)c.W * 4, (cuuint64_t)c.H, (cuuint64_t)nfr};
+      CUresult r = enc(k ? &tm_s1 : &tm_s0, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(k ? c.src1 : c.src0), dims,
+                       strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) RIFE_FAIL(RIFE_ERR_CUDA, "cuTensorMapEncodeTiled(SRC) failed: " + std::to_string((int)r));
+    }
+  }
   // gather warps per CTA (one CTA per SM): 27 = a full 1024-thread CTA at 64 registers per thread
   static const int ng = getenv("RIFE_GC_WARPS") ? atoi(getenv("RIFE_GC_WARPS")) : 27;
-  if (ng <= 16) return launch_ng<16>(tm_fb, tm_tmp, p, st);
-  if (ng <= 20) return launch_ng<20>(tm_fb, tm_tmp, p, st);
-  if (ng <= 24) return launch_ng<24>(tm_fb, tm_tmp, p, st);
-  return launch_ng<27>(tm_fb, tm_tmp, p, st);
+  if (ng <= 16) return launch_ng<16>(tm_fb, tm_tmp, tm_s0, tm_s1, p, st);
+  if (ng <= 20) return launch_ng<20>(tm_fb, tm_tmp, tm_s0, tm_s1, p, st);
+  if (ng <= 24) return launch_ng<24>(tm_fb, tm_tmp, tm_s0, tm_s1, p, st);
+  return launch_ng<27>(tm_fb, tm_tmp, tm_s0, tm_s1, p, st);
 }
 
 }  // namespace rife

@@ -537,6 +537,22 @@ int launch_conv_umma(const UmmaLayer& L, const ConvIO& io, cudaStream_t st) {
   int stages = (104 * 1024) / stage_bytes;  // two CTAs per SM stay co-resident (no second wave, overlapped epilogues)
   if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // a grid of at most one CTA per SM (the coarse blocks' layers) has the SM's shared memory to itself: a deeper ring keeps
+  // more of the latency-bound (tap, chunk) loads in flight.  RIFE_UMMA_DEEP=0 restores the two-CTA budget.
+  {
+    static const bool deep = !(getenv("RIFE_UMMA_DEEP") && atoi(getenv("RIFE_UMMA_DEEP")) == 0);
+    static const int nsm = []() {
+      int n = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n > 0 ? n : 148;
+    }();
+    const long long ctas = (long long)p.tiles_x * p.tiles_y * io.B * (L.npad / p.nw);
+    if (deep && ctas <= nsm) {
+      stages = (198 * 1024) / stage_bytes;
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+    }
+  }
   const int ksteps = p.ntaps * p.nchunks;
   if (stages > ksteps) stages = ksteps;
   p.stages = stages;
