@@ -54,6 +54,9 @@ def stage_model(P, H, W, esz, io_esz, nframes):
     one = (2 * NF / 4 * 16 * esz, 2.0 * NF / 4 * 9 * 16 * 16)
     m["head.cnn1"] = m["head.cnn2"] = one
     m["head.cnn1+2"] = (one[0], 2 * one[1])                      # fused pair: the intermediate never reaches HBM
+    # the four layers in one kernel (conv_head.cu): the s2d frame in, SRC out; the real FLOPs of the four layers
+    m["head.fused"] = (NF / 4 * 16 * esz + NF * 8 * esz,
+                       2.0 * NF / 4 * 27 * 16 + 2 * one[1] + 2.0 * NF * 4 * 4 * 16)
     m["head.cnn3"] = (NF / 4 * 16 * esz * 2 + NF * 8 * esz, 2.0 * NF * 4 * 4 * 16)   # features + s2d frame in, SRC out
     for i, c in enumerate(BLOCK_C):
         s = 16 >> i

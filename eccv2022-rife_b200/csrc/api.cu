@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "conv_gather.cuh"
 #include "conv_halo.cuh"
+#include "conv_head.cuh"
 #include "conv_strip.cuh"
 #include "conv_umma.cuh"
 
@@ -138,6 +139,8 @@ struct rife_weights {
   StripPair strip_res4[4];
   bool has_strip_res4 = false;
   DevLayer head[4];
+  HeadFused head_fused;     // the four Head layers as one kernel (conv_head.cu); 16-bit modes
+  bool has_head_fused = false;
   struct Block {
     DevLayer conv00, conv01, res[8], last;
     HaloLayer last8;       // block 4 only, fp16 halo path: lastconv restricted to flow + mask (8-channel tmp pixel)
@@ -266,6 +269,23 @@ int rife_weights_create(rife_weights** out, int n, const char* const* names, con
     if ((st = upload_layer(w, pack_conv3x3(w1, b1, 16, 16, 16), &w->head[1], false, bf, bf))) return fail(st);
     if ((st = upload_layer(w, pack_conv3x3(w2, b2, 16, 16, 16), &w->head[2], false, bf, bf))) return fail(st);
     if ((st = upload_layer(w, pack_convT(w3, b3, 16, 4, 16), &w->head[3], false, bf, false))) return fail(st);
+    if (is_half_mode(precision) && !w->force_nhwc) {
+      const HostLayer hh[4] = {pack_conv3x3_s2d(w0, b0, 16, 3, 3, 16), pack_conv3x3(w1, b1, 16, 16, 16),
+                               pack_conv3x3(w2, b2, 16, 16, 16), pack_convT(w3, b3, 16, 4, 16)};
+      if (head_fused_fits(hh)) {
+        std::vector<__half> packed;
+        std::vector<float> hb;
+        void *pw = nullptr, *pb = nullptr;
+        if ((st = head_fused_pack(hh, bf, &packed, &hb))) return fail(st);
+        if ((st = upload(w, packed.data(), packed.size() * sizeof(__half), &pw))) return fail(st);
+        if ((st = upload(w, hb.data(), hb.size() * 4, &pb))) return fail(st);
+        w->head_fused.w = (const __half*)pw;
+        w->head_fused.bias = (const float*)pb;
+        w->head_fused.bf16 = bf ? 1 : 0;
+        w->head_fused.w_bytes = (int)(packed.size() * sizeof(__half));
+        w->has_head_fused = true;
+      }
+    }
     if (is_half_mode(precision) && strip_enabled() && w->head[1].use_hk && w->head[2].use_hk) {
       const HostLayer h1 = pack_conv3x3(w1, b1, 16, 16, 16), h2 = pack_conv3x3(w2, b2, 16, 16, 16);
       if (strip_fits(h1) && strip_fits(h2)) {
@@ -642,6 +662,16 @@ static int default_chunk_pairs() {
   return v;
 }
 
+static bool head_fused_on() {
+  // RIFE_HEAD_FUSED=1: the four Head layers as ONE kernel with their activations in shared memory (conv_head.cu).  Off by
+  // default -- measured on B200 (16 x 1080p pairs): 1.10 ms against 0.97 ms for the four per-layer launches.  It moves 3.7x
+  // less HBM traffic and needs half the MMAs (row-stacked N = 64), but one CTA per SM then carries MMA operand reads (48
+  // L1-data-pipe wavefronts per MMA: 43 % of the pipe), the epilogues' shared-memory stores and the TMEM reads of four layers
+  // on the same SM: tensor pipe 29 % active, epilogue warps 80 % busy (profiles/r02_ncu_head_fused.md).
+  static const bool on = getenv("RIFE_HEAD_FUSED") && atoi(getenv("RIFE_HEAD_FUSED")) != 0;
+  return on;
+}
+
 static bool gather_conv_on() {
   // RIFE_GATHER_CONV=0: the scale-1 block's input gather and its conv0.0 as two kernels with `xin` in HBM between them
   static const bool on = !(getenv("RIFE_GATHER_CONV") && atoi(getenv("RIFE_GATHER_CONV")) == 0);
@@ -722,7 +752,10 @@ static int run_pipeline(rife_plan* p, const void* img0, const void* img1, const 
   // ---- inputs + Head (IFNet_HDv3.py:128-129, both frames as one batch of 2B)
   p->n_stage = 0;
   RIFE_STAGE("prep", launch_prep(c, img0, img1, io_dtype, p->at(L.src), p->at(L.head_in), st));
-  {
+  if (c.planar_head && w->has_head_fused && head_fused_on()) {
+    // cnn0 -> cnn1 -> cnn2 -> cnn3 + SRC assembly in one kernel: the 16-channel activations stay in shared memory
+    RIFE_STAGE("head.fused", launch_head_fused(w->head_fused, p->at(L.head_in), p->at(L.src), c.F, H / 2, W / 2, st));
+  } else {
     ConvIO io;
     io.B = c.F; io.H = H / 2; io.W = W / 2;
     io.in = p->at(L.head_in); io.out = p->at(L.head_a); io.epi = EPI_LRELU; io.out_c = 16;

@@ -394,12 +394,19 @@ __device__ __forceinline__ void epi_chunk_rt(const HaloParams& p, const EpiCtx& 
 // EPI >= 0 additionally fixes the epilogue at compile time (fully unrolled over M-tiles and 16-column chunks).
 // Epilogue warps: 4 (one per SM sub-partition); the column-heavy PixelShuffle epilogue (256 columns per M-tile) uses 8,
 // warps w and w+4 sharing a TMEM lane quarter and splitting the output rows.
-template <int EPI> struct EpiWarps { static constexpr int value = (EPI == EPI_PS || EPI == EPI_PS8) ? 8 : 4; };
+// Measured per layer shape (B200, 16 x 1080p pairs): the second warp per quarter pays for the ConvTranspose tails (EPI_PS /
+// EPI_PS8 / Head.cnn3's EPI_HEADT: 0.407 -> 0.364 ms) and for the s2d conv0.1 layers (N >= 32: 0.078 -> 0.074, 0.047 -> 0.043
+// ms); it costs the ResConv layers (0.56 -> 0.59 ms: their epilogue shares the smem tile with the MMAs) and the N = 16 Head
+// layers (0.212 -> 0.229 ms).
+template <int KIND, int NE, int EPI> struct EpiWarps {
+  static constexpr int value =
+      (EPI == EPI_PS || EPI == EPI_PS8 || EPI == EPI_HEADT || (EPI == EPI_LRELU && KIND == 1 && NE >= 32)) ? 8 : 4;
+};
 
 // STREAM: the layer's weights do not fit in smem next to the activation ring (c >= 96): an extra producer warp streams
 // one weight tile per schedule entry through a ring of p.nb slots, re-using every tile for the MT stacked M-tiles.
 template <int KIND, int KSTEPS, int NE, int MT, int EPI, bool STREAM = false>
-__global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value + (STREAM ? 32 : 0))
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<KIND, NE, EPI>::value + (STREAM ? 32 : 0))
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_STAGES];
@@ -425,7 +432,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __shared__ uint32_t tab_a[NTAB];               // A start-address field relative to the stage base (16-byte units)
   __shared__ uint32_t tab_d[NTAB];               // accumulator column offset | (accumulate << 31)
 
-  constexpr int NUM_EPI_WARPS = EpiWarps<EPI>::value;
+  constexpr int NUM_EPI_WARPS = EpiWarps<KIND, NE, EPI>::value;
   constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // without the optional weight-streaming warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1197,7 +1204,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
 #define RIFE_HK_CASE(K, KS, N_, MT_, E_)                                                                     \
   if (!done && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {                   \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_>));                              \
-    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_>, grid, 64 + 32 * EpiWarps<E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
+    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_>, grid, 64 + 32 * EpiWarps<K, N_, E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
     done = true;                                                                                             \
   }
   RIFE_HK_CASE(1, 1, 16, 2, EPI_LRELU)      // Head.cnn0            (s2d, cin 16 -> 16)
@@ -1216,7 +1223,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
 #define RIFE_HK_STREAM(K, KS, N_, MT_, E_)                                                                   \
   if (!done && L.stream && p.mt == MT_ && kind == K && p.ksteps == KS && p.ne == N_ && p.epi == E_) {       \
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<K, KS, N_, MT_, E_, true>));                        \
-    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_, true>, grid, 96 + 32 * EpiWarps<E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
+    { const int rc_ = launch_hk(conv_halo_kernel<K, KS, N_, MT_, E_, true>, grid, 96 + 32 * EpiWarps<K, N_, E_>::value, smem, st, tm_a, tm_b, p, coop); if (rc_) return rc_; } \
     done = true;                                                                                             \
   }
   RIFE_HK_STREAM(0, 6, 96, 2, EPI_RES)      // block2 ResConv       (3x3, 96 -> 96), two stacked M-tiles
@@ -1231,7 +1238,7 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   if (!done) {
     RIFE_TRY(set_smem_attr((const void*)conv_halo_kernel<-1, 0, 0, 0, -1>));
     if (coop) return 1;  // no compile-time instantiation for this shape: the caller launches layer by layer
-    RIFE_TRY(launch_hk(conv_halo_kernel<-1, 0, 0, 0, -1>, grid, 64 + 32 * EpiWarps<-1>::value, smem, st, tm_a, tm_b, p, false));
+    RIFE_TRY(launch_hk(conv_halo_kernel<-1, 0, 0, 0, -1>, grid, 64 + 32 * EpiWarps<-1, 0, -1>::value, smem, st, tm_a, tm_b, p, false));
   }
   RIFE_LAUNCH_CHECK();
   if (debug) {

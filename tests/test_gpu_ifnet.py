@@ -411,7 +411,7 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
     outs = {}
     for tag, env in (("default", {}), ("wide", {"RIFE_NO_NARROW_LAST": "1"}), ("chain", {"RIFE_HK_CHAIN": "64"}),
                      ("strip", {"RIFE_STRIP": "1"}), ("nograph", {"RIFE_GRAPH_MAX": "0"}),
-                     ("unfused", {"RIFE_GATHER_CONV": "0"})):
+                     ("unfused", {"RIFE_GATHER_CONV": "0"}), ("headfused", {"RIFE_HEAD_FUSED": "1"})):
         f = str(tmp_path / (tag + ".pt"))
         subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env}, timeout=600)
         outs[tag] = torch.load(f)
@@ -423,9 +423,12 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
     # RIFE_STRIP=1 (conv_strip.cu: Head.cnn1+2 and block 4's ResConv pairs fused, kx-stacked MMAs): another summation
     # order, so not bit-identical -- equal up to fp16 rounding of the activations (white-noise frames, amplified flows: a
     # one-ulp activation difference moves single pixels by up to ~1e-2, the mean difference stays ~5e-4)
-    for k in range(2):
-        d = (outs["strip"][k].float() - outs["default"][k].float()).abs()
-        assert float(d.max()) < TOL16 and float(d.mean()) < 1e-3, (k, float(d.max()), float(d.mean()))
+    # RIFE_HEAD_FUSED=1 (conv_head.cu: the four Head layers as one kernel, row-stacked MMAs, activations in shared memory;
+    # optional, off by default): the taps are added up in another order -- same bound
+    for tag in ("strip", "headfused"):
+        for k in range(2):
+            d = (outs[tag][k].float() - outs["default"][k].float()).abs()
+            assert float(d.max()) < TOL16 and float(d.mean()) < 1e-3, (tag, k, float(d.max()), float(d.mean()))
     m = seeded_model(pkg, AMP, "fp16")
     g = torch.Generator().manual_seed(21)
     a, b = torch.rand(2, 3, 192, 320, generator=g).to(DEV).half(), torch.rand(2, 3, 192, 320, generator=g).to(DEV).half()
