@@ -21,7 +21,7 @@ def test_eccv_ifnet_forward_structure(pkg):
     flows, mask, merged, ft, mt, ld = m.flownet(x, [4, 2, 1])
     assert ft is None and mt is None and ld == 0 and len(flows) == 3 and len(merged) == 3
     for i in range(3):
-        assert np.abs(flows[i].cpu().numpy() - g[f"a_flow{i}"]).max() < 1e-3, i      # |flow| up to ~28 px
+        assert np.abs(flows[i].cpu().numpy() - g[f"a_flow{i}"]).max() < 1e-4, i      # measured 4e-5 at |flow| up to ~28 px
         assert np.abs(merged[i].cpu().numpy() - g[f"a_merged{i}"]).max() < 1e-4, i
     assert np.abs(mask.cpu().numpy() - g["a_mask"]).max() < 1e-4
 
@@ -122,7 +122,7 @@ def test_eccv_m_arbitrary_timestep(pkg):
     x = torch.cat((a, b), 1)
     for t in (0.25, 0.5, 0.8):
         flows, mask, merged, *_ = m.flownet(x, [4, 2, 1], timestep=t)
-        assert np.abs(flows[2].cpu().numpy() - g[f"flow2_t{t}"]).max() < 1e-3
+        assert np.abs(flows[2].cpu().numpy() - g[f"flow2_t{t}"]).max() < 1e-4         # |flow| up to ~28 px
         assert np.abs(mask.cpu().numpy() - g[f"mask_t{t}"]).max() < 1e-4
         assert np.abs(merged[2].cpu().numpy() - g[f"out_t{t}"]).max() < 1e-4
         o16 = m.inference(a.half(), b.half(), scale_list=[4, 2, 1], timestep=t).float().cpu().numpy()
@@ -130,7 +130,7 @@ def test_eccv_m_arbitrary_timestep(pkg):
     out = m.inference(a, b, scale=0.5, scale_list=[4, 2, 1], timestep=0.25).cpu().numpy()
     assert np.abs(out - g["out_scale05_t0.25"]).max() < 1e-4
     fl = m.flownet(x, [4, 2, 1], timestep=0.5, returnflow=True)
-    assert np.abs(fl.cpu().numpy() - g["flow_only_t0.5"]).max() < 1e-3
+    assert np.abs(fl.cpu().numpy() - g["flow_only_t0.5"]).max() < 1e-4
     tt = torch.tensor([0.25, 0.8], device=DEV).reshape(2, 1, 1, 1)                     # per-sample timesteps
     mixed = m.inference(a, b, scale_list=[4, 2, 1], timestep=tt).cpu().numpy()
     assert np.abs(mixed[0] - g["out_t0.25"][0]).max() < 1e-4 and np.abs(mixed[1] - g["out_t0.8"][1]).max() < 1e-4
@@ -138,14 +138,14 @@ def test_eccv_m_arbitrary_timestep(pkg):
 
 def test_eccv_2r_variant(pkg):
     """IFNet_2R (model/IFNet_2R.py + model/refine_2R.py) against outputs recorded from the reference: fp32 <= 1e-4
-    (flows 1e-3 at |flow| ~ 11 px), fp16 inside the reduced-precision bar; scale list [8, 4, 2]."""
+    (flows included: measured 1e-5 at |flow| ~ 11 px), fp16 inside the reduced-precision bar; scale list [8, 4, 2]."""
     g = load_golden("eccv_2r_cases")
     net = seeded_eccv_2r(pkg)
     x = torch.cat((cu(g["a_img0"]), cu(g["a_img1"])), 1)
     flows, mask, merged, ft, mt, ld = net(x, [4, 2, 1])
     assert ft is None and mt is None and ld == 0
     for i in range(3):
-        assert np.abs(flows[i].cpu().numpy() - g[f"a_flow{i}"]).max() < 1e-3, i
+        assert np.abs(flows[i].cpu().numpy() - g[f"a_flow{i}"]).max() < 1e-4, i
     assert np.abs(mask.cpu().numpy() - g["a_mask"]).max() < 1e-4
     assert np.abs(merged[0].cpu().numpy() - g["a_merged0"]).max() < 1e-4
     assert np.abs(merged[2].cpu().numpy() - g["a_merged2"]).max() < 1e-4

@@ -54,7 +54,7 @@ def test_ifnet_forward_structure_fp32(pkg):
     flows, mask, merged = net(x, 0.5, [16, 8, 4, 2, 1])
     assert len(flows) == 5 and len(merged) == 5 and isinstance(merged[0], tuple) and torch.is_tensor(merged[4])
     for i in range(5):
-        assert np.abs(flows[i].cpu().numpy() - g[f"flow{i}"]).max() < 5e-4, i
+        assert np.abs(flows[i].cpu().numpy() - g[f"flow{i}"]).max() < TOL32, i       # measured 4e-6 at |flow| ~ 6 px
     for i in range(4):
         assert np.abs(merged[i][0].cpu().numpy() - g[f"merged{i}_0"]).max() < TOL32
         assert np.abs(merged[i][1].cpu().numpy() - g[f"merged{i}_1"]).max() < TOL32
@@ -163,8 +163,8 @@ def test_scale_above_one(pkg):
         _check16(m16.inference(a.half(), b.half(), 0.5, scale).float().cpu().numpy(), g[tag + "_out"], tag)
     a, b = torch.from_numpy(g["s2_img0"]).to(DEV), torch.from_numpy(g["s2_img1"]).to(DEV)
     flows, mask, merged = m32.flownet(torch.cat((a, b), 1), 0.3, [8, 4, 2, 1, 0.5])
-    assert np.abs(flows[4].cpu().numpy() - g["s2_flow4"]).max() < 1e-3 and np.abs(flows[3].cpu().numpy() - g["s2_flow3"]).max() < 1e-3
-    assert np.abs(mask.cpu().numpy() - g["s2_mask"]).max() < 1e-3
+    assert np.abs(flows[4].cpu().numpy() - g["s2_flow4"]).max() < TOL32 and np.abs(flows[3].cpu().numpy() - g["s2_flow3"]).max() < TOL32
+    assert np.abs(mask.cpu().numpy() - g["s2_mask"]).max() < TOL32                  # measured 6e-6 / 1e-6 (|flow| ~ 7 px)
     assert np.abs(merged[4].cpu().numpy() - g["s2_merged_t03"]).max() < TOL32
     # any frame size through pad=True (multiples of 64/scale = 32)
     c, d = a[:, :, :50, :70].contiguous(), b[:, :, :50, :70].contiguous()

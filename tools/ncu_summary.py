@@ -21,7 +21,13 @@ def num(r, k):
 
 
 names = []
-if mode == "hdv3" and len(data) == 66:
+if mode == "hdv3" and len(data) == 65:   # block 4's input gather fused into its conv0.0 (conv_gather.cu)
+    names = ["prep"] + ["head.cnn%d" % i for i in range(4)]
+    for b in range(5):
+        names += ([f"b{b}.input+conv0.0"] if b == 4 else [f"b{b}.input", f"b{b}.conv0.0"]) + [f"b{b}.conv0.1"]
+        names += [f"b{b}.res{j}" for j in range(8)] + [f"b{b}.lastconv"]
+    names += ["merge"]
+elif mode == "hdv3" and len(data) == 66:
     names = ["prep"] + ["head.cnn%d" % i for i in range(4)]
     for b in range(5):
         names += [f"b{b}.input", f"b{b}.conv0.0", f"b{b}.conv0.1"] + [f"b{b}.res{j}" for j in range(8)] + [f"b{b}.lastconv"]
