@@ -142,6 +142,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load without its wait, and the wait for all loads issued so far.  tmem_regs_ready() ties the loaded registers to
+// the wait (volatile asm statements keep their order; the empty one makes every later use depend on it), so that several
+// accumulator chunks can be in flight before one wait.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_regs_ready(float (&v)[16]) {
+  asm volatile(""
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void store16h(__half* dst, const float (&v)[16]) {
   float a[8];
 #pragma unroll
@@ -788,6 +807,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
           if (mi > 0 && (ty * MT + mi) * TH >= p.H) continue;   // M-tile below the image: not computed (see the MMA issuer)
+#ifndef RIFE_EPI_NO_BATCH
+          if constexpr (ESPLIT == 1 && NCOLS <= 64) {
+            // all of the M-tile's accumulator chunks are requested before the one wait (TMEM latency paid once per M-tile)
+            float v[NCOLS / 16][16];
+#pragma unroll
+            for (int j = 0; j < NCOLS / 16; ++j) tmem_ld16_nowait(trow + (uint32_t)((buf * MT + mi) * NCOLS + j * 16), v[j]);
+            tmem_ld_wait_all();
+#pragma unroll
+            for (int j = 0; j < NCOLS / 16; ++j) tmem_regs_ready(v[j]);
+#pragma unroll
+            for (int j = 0; j < NCOLS / 16; ++j) {
+              epi_chunk<EPI>(p, c, s_bias, s_beta, pitch, mi, j, v[j]);
+              __syncwarp();
+            }
+            continue;
+          }
+#endif
 #pragma unroll
           for (int j = 0; j < NCOLS / 16; ++j) {
             if (ESPLIT == 2 && ((mi * (NCOLS / 16) + j) & 1) != ehalf) continue;

@@ -33,6 +33,7 @@
 
 #include "conv_head.cuh"
 #include "tc_dev.cuh"
+#include "tc_host.cuh"
 
 namespace rife {
 namespace {
@@ -321,44 +322,10 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return (EncodeTiledFn)f;
-  }();
-  return fn;
-}
-
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-int opt_in_smem(const void* fn, int bytes) {
-  static std::vector<std::pair<const void*, int>> seen;
-  static std::mutex mu;   // one host thread per GPU may launch concurrently
-  std::lock_guard<std::mutex> lock(mu);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  for (auto& s : seen)
-    if (s.first == fn && s.second == dev) return RIFE_OK;
-  RIFE_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  seen.emplace_back(fn, dev);
-  return RIFE_OK;
-}
+using tch::EncodeTiledFn;
+using tch::encode_fn;
+using tch::opt_in_smem;
+using tch::sm_count;
 
 }  // namespace
 
