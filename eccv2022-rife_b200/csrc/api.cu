@@ -9,6 +9,8 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "conv_gather.cuh"
 #include "conv_halo.cuh"
@@ -489,11 +491,23 @@ struct rife_plan {
 };
 
 // brackets one launch with events when profiling is on
+static bool nvtx_on() {
+  // RIFE_NVTX=1: one NVTX range per pipeline stage (same names as rife_plan_get_profile) around its launches, for
+  // ncu --nvtx / Nsight timelines; header-only NVTX v3, nothing happens without an attached tool
+  static const bool on = getenv("RIFE_NVTX") && atoi(getenv("RIFE_NVTX")) != 0;
+  return on;
+}
+
 struct StageTimer {
   rife_plan* p;
   cudaStream_t st;
   rife_plan::Stage* s = nullptr;
+  bool range = false;
   StageTimer(rife_plan* p_, cudaStream_t st_, const std::string& name) : p(p_), st(st_) {
+    if (nvtx_on()) {
+      nvtxRangePushA(name.c_str());
+      range = true;
+    }
     if (!p->profile) return;
     if (p->n_stage == p->stages.size()) {
       p->stages.emplace_back();
@@ -506,6 +520,7 @@ struct StageTimer {
   }
   ~StageTimer() {
     if (s) cudaEventRecord(s->e1, st);
+    if (range) nvtxRangePop();
   }
 };
 #define RIFE_STAGE(name, expr)          \
