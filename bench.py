@@ -41,6 +41,10 @@ WEIGHTS_TEXT = "HDv3 v4.25 weights = seeded default init"
 BYTES_PER_PIXEL_MODEL = 601.9     # stage-fused HBM traffic model, elements per pixel per pair
 FLOP_PER_PIXEL = 6064 + 38372.3   # SURVEY 8d at scale = 1
 BLOCK_C = (192, 128, 96, 64, 32)
+# DRAM bytes per full-resolution output pixel (dram__bytes_read.sum + dram__bytes_write.sum) of the three largest stages, from
+# the committed `ncu --set full` capture of one 8-pair 1080p pass of this build (profiles/r02_ncu_full_hdv3_1080p_P8.md rows 53,
+# 41, 64: 1317.2 / 1074.7 / 1166.2 MB over 8 x 1088 x 1920 pixels).  Per-pixel figures scale with the batch, not with a clock.
+NCU_DRAM_BYTES_PER_PX = {"b4.input+conv0.0": 78.8, "b3.input": 64.3, "merge": 69.8}
 
 
 def stage_model(P, H, W, esz, io_esz, nframes):
@@ -505,7 +509,11 @@ def main():
         n_l = max(dom["launches_per_step"], 1)
         roofline = {"bound": dom["bound"], "kernel": dom["stage"], "achieved": dom["achieved"],
                     "peak": tf_peak if dom["bound"] == "tensor" else hbm_peak, "unit": dom["unit"], "frac": dom["frac"],
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": (NCU_DRAM_BYTES_PER_PX[dom["stage"]] * P * H * W / n_l
+                                if dom["stage"] in NCU_DRAM_BYTES_PER_PX and (H, W) == (1088, 1920) else None),
+                    "traffic_source": "ncu --set full capture of this build at 8 pairs (profiles/r02_ncu_full_hdv3_1080p_P8.md), "
+                                      "DRAM read + written per output pixel x the pixels of this launch",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom["alg_bytes"] / n_l, "kernel_ms": dom["ms_per_step"] / n_l,
                     "launches_per_step": n_l,
                     "worst_stage": {k: worst[k] for k in ("stage", "bound", "frac", "ms_per_step")},
