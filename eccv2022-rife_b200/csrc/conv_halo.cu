@@ -16,9 +16,11 @@
 //   * ConvTranspose2d(4,2,1)+PixelShuffle (lastconv) runs as 4 output parities x 4 taps (16 MMAs groups of N=64)
 //     instead of 9 dense taps of N=208/256.
 #include <cuda.h>
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <utility>
 
@@ -454,6 +456,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   constexpr int NUM_EPI_WARPS = EpiWarps<KIND, NE, EPI>::value;
   constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // without the optional weight-streaming warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.dbg && threadIdx.x == 0) {
+    long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 16 + 8] = g;
+  }
   const uint32_t w_smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = w_smem + (STREAM ? (uint32_t)(p.nb * p.wtile_al) : (((uint32_t)p.w_bytes + 1023u) & ~1023u));
 
@@ -504,6 +511,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.dbg && threadIdx.x == 0) {
+    long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 16 + 9] = g;
+  }
   if (p.pdl_trig == 1) pdl_trigger();  // the next kernel's CTAs may start their prologue as SMs free up (they block in pdl_wait())
   const uint32_t tmem_base = tmem_slot;
   const int pitch = TW + p.R;  // halo row pitch in pixels
@@ -567,7 +579,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_arrive(smem_u32(&a_full[stage]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = t_wait;
+      if (p.dbg) p.dbg[blockIdx.x * 16 + 0] = t_wait;
     }
   } else if (STREAM && warp == 2 + NUM_EPI_WARPS) {
     if (lane == 0) {
@@ -657,10 +669,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       if (p.pdl_trig == 2) pdl_trigger();  // only the last epilogue is left: let the next kernel's CTAs set up meanwhile
       if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 1] = t_w;
-        p.dbg[blockIdx.x * 8 + 2] = t_te;
-        p.dbg[blockIdx.x * 8 + 3] = t_af;
-        p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+        long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.dbg[blockIdx.x * 16 + 10] = g;
+        p.dbg[blockIdx.x * 16 + 1] = t_w;
+        p.dbg[blockIdx.x * 16 + 2] = t_te;
+        p.dbg[blockIdx.x * 16 + 3] = t_af;
+        p.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin;
       }
     }
   } else {
@@ -867,9 +882,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     }
     if (p.dbg && warp == 2 && lane == 0) {  // timers of the first epilogue warp
-      p.dbg[blockIdx.x * 8 + 5] = t_tf;
-      p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
-      p.dbg[blockIdx.x * 8 + 7] = it;
+      p.dbg[blockIdx.x * 16 + 5] = t_tf;
+      p.dbg[blockIdx.x * 16 + 6] = clock64() - t_begin;
+      p.dbg[blockIdx.x * 16 + 7] = it;
     }
   }
   tc_fence_before();
@@ -878,6 +893,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
+  }
+  if (p.dbg && threadIdx.x == 0) {
+    long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 16 + 11] = g;
   }
   if (p.nlayers > 1 && threadIdx.x == 0) {
     // chain: every CTA that gets here has passed all of its barrier waits; the last one to finish re-arms the counters
@@ -1231,9 +1251,12 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   p.dbg = nullptr;
   static const int pdl_trig = getenv("RIFE_PDL_HALO_TRIGGER") ? atoi(getenv("RIFE_PDL_HALO_TRIGGER")) : 0;
   p.pdl_trig = pdl_trig;
+  // (an early trigger does not pay even for the kernels that own a whole SM: measured 5.52 -> 5.99 ms per 16-pair step --
+  // the dependent of the dependent is launched early too and can take a freed SM before the kernel in between has placed its
+  // CTA there)
   if (debug) {
-    cudaMalloc((void**)&p.dbg, (size_t)grid * 64);
-    cudaMemsetAsync(p.dbg, 0, (size_t)grid * 64, st);
+    cudaMalloc((void**)&p.dbg, (size_t)grid * 128);
+    cudaMemsetAsync(p.dbg, 0, (size_t)grid * 128, st);
   }
   const int kind = L.ps_cols ? 2 : (L.kind == CONV_3x3 ? 0 : 1);
   bool done = false;
@@ -1278,13 +1301,25 @@ int launch_conv_halo_impl(const HaloLayer& L, const ConvIO& io, cudaStream_t st,
   }
   RIFE_LAUNCH_CHECK();
   if (debug) {
-    std::vector<long long> h((size_t)grid * 8);
+    std::vector<long long> h((size_t)grid * 16);
     cudaStreamSynchronize(st);
-    cudaMemcpy(h.data(), p.dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data(), p.dbg, (size_t)grid * 128, cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
     double a[8] = {0};
     for (int i = 0; i < grid; ++i)
-      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 8 + k] / grid;
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 16 + k] / grid;
+    // slots 8..11: %globaltimer (ns) at CTA entry, after the prologue's __syncthreads, at the end of the MMA role, at CTA exit
+    long long g0 = LLONG_MAX, g1 = 0;
+    double pro = 0, life = 0, tail = 0;
+    for (int i = 0; i < grid; ++i) {
+      const long long* r = &h[(size_t)i * 16];
+      g0 = std::min(g0, r[8]); g1 = std::max(g1, r[11]);
+      pro += (double)(r[9] - r[8]) / grid; life += (double)(r[11] - r[8]) / grid; tail += (double)(r[11] - r[10]) / grid;
+    }
+    long long first_exit = LLONG_MAX, last_entry = 0;
+    for (int i = 0; i < grid; ++i) { first_exit = std::min(first_exit, h[(size_t)i * 16 + 11]); last_entry = std::max(last_entry, h[(size_t)i * 16 + 8]); }
+    fprintf(stderr, "[hk-t] span first entry -> last exit %.1f us | last entry at +%.1f us, first exit at +%.1f us | per CTA: prologue %.1f us, lifetime %.1f us, after the last MMA %.1f us\n",
+            (g1 - g0) / 1e3, (last_entry - g0) / 1e3, (first_exit - g0) / 1e3, pro / 1e3, life / 1e3, tail / 1e3);
     fprintf(stderr, "[hk] kind=%d cin=%d ne=%d mt=%d grid=%d per_sm=%d stages=%d steps/cta=%.1f | prod wait a_empty %.0f | mma: wait w %.0f, t_empty %.0f, a_full %.0f, total %.0f | epi: wait t_full %.0f, total %.0f\n",
             kind, L.cin, L.ne, p.mt, grid, per_sm, p.stages, a[7], a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }
