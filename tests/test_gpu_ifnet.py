@@ -407,7 +407,13 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
         "c = torch.rand(3, 3, 576, 1024, generator=g).cuda().half(); d = torch.rand(3, 3, 576, 1024, generator=g).cuda().half();"
         "xs = [torch.rand(1, 3, 128, 192, generator=g).cuda().half() for _ in range(6)];"
         "small = [m.inference(xs[i], xs[i + 1], 0.25 + 0.1 * i).cpu() for i in range(5)];"   # B = 1: plain, capture, 3 replays
-        "torch.save((m.inference(a, b, 0.4).cpu(), m.inference(c, d, 0.5).cpu(), torch.cat(small)), sys.argv[1])" % (root, root))
+        # the other callers of the pipeline: bf16 mode, several timesteps per pair, video order, uint8 frames with a ragged
+        # frame size (padded and cropped in-kernel)
+        "mb = seeded_model(pkg, AMP, 'bf16');"
+        "u0 = (torch.rand(2, 120, 180, 3, generator=g) * 255).byte().cuda(); u1 = (torch.rand(2, 120, 180, 3, generator=g) * 255).byte().cuda();"
+        "extra = (mb.inference(a, b, 0.4).cpu(), m.inference_multi(a, b, (0.25, 0.75)).cpu(), m.inference_sequence(c, (0.5,)).cpu(),"
+        "         m.flownet.run(u0, u1, 0.5, 1.0, False, True).cpu());"
+        "torch.save((m.inference(a, b, 0.4).cpu(), m.inference(c, d, 0.5).cpu(), torch.cat(small), extra), sys.argv[1])" % (root, root))
     outs = {}
     for tag, env in (("default", {}), ("wide", {"RIFE_NO_NARROW_LAST": "1"}), ("chain", {"RIFE_HK_CHAIN": "64"}),
                      ("strip", {"RIFE_STRIP": "1"}), ("nograph", {"RIFE_GRAPH_MAX": "0"}),
@@ -417,6 +423,8 @@ def test_last_block_flow_mask_only_is_bit_identical(pkg, tmp_path):
         outs[tag] = torch.load(f)
     for tag in ("wide", "chain", "nograph", "unfused"):
         assert torch.equal(outs[tag][0], outs["default"][0]) and torch.equal(outs[tag][1], outs["default"][1]), tag
+    for k in range(4):   # bf16 mode / inference_multi / inference_sequence / uint8 ragged frames: fused == two kernels
+        assert torch.equal(outs["unfused"][3][k], outs["default"][3][k]), k
     # calls with <= 4 outputs replay a CUDA graph from the second call on (rife_inference): five B = 1 calls with fresh
     # tensors and timesteps each -- plain, capture + replay, three replays -- equal the graph-free run bit for bit
     assert torch.equal(outs["nograph"][2], outs["default"][2])
